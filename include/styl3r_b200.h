@@ -1,0 +1,171 @@
+/*
+ * styl3r_b200 — C-ABI of the B200-native (sm_100a) Styl3R hot path.
+ *
+ * Every entry point is `extern "C"`, takes plain device pointers / sizes / a
+ * cudaStream_t (passed as void*), returns 0 or a negative S3R_ERR_* code, never
+ * throws, never allocates on the caller's behalf and never synchronises the
+ * stream unless the name says so.  The caller (PyTorch on the Python side) owns
+ * all memory.
+ *
+ * Reference interfaces these entry points replace (paths relative to the
+ * Styl3R repo):
+ *   - s3r_raster_*      : third-party `diff_gaussian_rasterization._C.
+ *                         rasterize_gaussians{,_backward}` as driven by
+ *                         src/model/decoder/cuda_splatting.py:101-129 (one call
+ *                         per view there; here one call renders all views).
+ *   - s3r_rope2d        : src/model/encoder/backbone/croco/curope/curope.cpp:49-69
+ *                         (`rope_2d`) / kernels.cu:84-108 (`rope_2d_cuda`).
+ *   - s3r_se3_update_w2c: src/misc/cam_utils.py:103-137 (SE3_exp, update_pose).
+ */
+#ifndef STYL3R_B200_H_
+#define STYL3R_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define S3R_ABI_VERSION 1
+
+/* error codes */
+#define S3R_OK 0
+#define S3R_ERR_INVALID_ARG (-1)
+#define S3R_ERR_UNSUPPORTED (-2) /* shape outside the compiled limits          */
+#define S3R_ERR_STATE_TOO_SMALL (-3)
+#define S3R_ERR_CUDA (-4) /* a CUDA runtime call / launch failed            */
+#define S3R_ERR_NO_DEVICE (-5)
+
+/* compiled limits */
+#define S3R_TILE 16          /* tile edge in pixels (BLOCK_X = BLOCK_Y)     */
+#define S3R_MAX_TILES 4096   /* tiles per view (<= 1024x1024 image)         */
+#define S3R_MAX_SH_COEFFS 16 /* SH degree <= 3                              */
+
+/* ------------------------------------------------------------------------
+ * Rasterizer
+ * ------------------------------------------------------------------------ */
+
+/* Inputs of one batched rasterization: `n_views` cameras; view i renders the
+ * Gaussian set `view_set[i]` (or set i when view_set == NULL, which requires
+ * n_sets == n_views).  All pointers are device pointers to contiguous fp32
+ * unless noted.  Matrices use the layout the reference hands to its
+ * rasterizer: 16 floats, m[4*col + row] of the mathematical matrix, i.e. the
+ * row-major storage of the *transposed* matrix (cuda_splatting.py:86-88). */
+typedef struct s3r_raster_params {
+  int32_t n_views;
+  int32_t n_sets;
+  int32_t P;          /* Gaussians per set                                    */
+  int32_t width;      /* image width  (pixels)                                */
+  int32_t height;     /* image height (pixels)                                */
+  int32_t sh_degree;  /* active SH degree, 0..3                               */
+  int32_t sh_coeffs;  /* stored coefficients per Gaussian M >= (deg+1)^2      */
+  int32_t cov_stride; /* 6: packed (xx,xy,xz,yy,yz,zz); 9: full row-major 3x3 */
+  const float* means3D;        /* [n_sets, P, 3]                              */
+  const float* cov3D;          /* [n_sets, P, cov_stride]                     */
+  const float* shs;            /* [n_sets, P, M, 3] or NULL                   */
+  const float* colors_precomp; /* [n_sets, P, 3] or NULL (exactly one of two) */
+  const float* opacities;      /* [n_sets, P]                                 */
+  const int32_t* view_set;     /* [n_views] or NULL                           */
+  const float* viewmatrix;     /* [n_views, 16] world->camera                 */
+  const float* projmatrix;     /* [n_views, 16] full projection (view @ proj) */
+  const float* projmatrix_raw; /* [n_views, 16] projection only (backward)    */
+  const float* campos;         /* [n_views, 3]                                */
+  const float* tanfov;         /* [n_views, 2] (tanfovx, tanfovy)             */
+  const float* scales;         /* [n_views] scale-invariant factor 1/near, or
+                                  NULL (= 1).  Applied in-kernel exactly like
+                                  cuda_splatting.py:65-72: mean*s, cov*(s*s). */
+  const float* background;     /* [n_views, 3]                                */
+} s3r_raster_params;
+
+typedef struct s3r_raster_outputs {
+  float* color;       /* [n_views, 3, H, W]                                   */
+  float* depth;       /* [n_views, H, W]  (alpha-blended, not normalised)     */
+  float* opacity;     /* [n_views, H, W]  (1 - final transmittance)           */
+  int32_t* radii;     /* [n_views, P]     screen radius in px, 0 = culled     */
+  int32_t* n_touched; /* [n_views, P] or NULL; caller zero-fills              */
+} s3r_raster_outputs;
+
+/* Byte offsets of the arrays inside the opaque `state` buffer (exposed so that
+ * parity tests can read tile assignment / sort order without a copy API).
+ * nvP = n_views*P, nvT = n_views*tiles, cap = instance capacity.            */
+typedef struct s3r_raster_layout {
+  int64_t total_bytes;
+  int64_t status;        /* int64[4]: R_total, overflow, max_tile_count, rsvd */
+  int64_t depths;        /* float   [nvP]   camera-space z                    */
+  int64_t xy;            /* float2  [nvP]   pixel-space mean                  */
+  int64_t conic_opacity; /* float4  [nvP]                                     */
+  int64_t rgb;           /* float4  [nvP]   (r,g,b, clamp-mask as int bits)   */
+  int64_t rect;          /* uint32  [nvP]   xmin|ymin<<8|xmax<<16|ymax<<24    */
+  int64_t chunk_hist;    /* uint16  [n_views, chunks, tiles]                  */
+  int64_t chunk_base;    /* uint32  [n_views, chunks, tiles]                  */
+  int64_t ranges;        /* uint2   [nvT]   (start,end) into the sorted list  */
+  int64_t keys_unsorted; /* uint64  [cap]   (depth_bits<<32 | gaussian) tile-binned */
+  int64_t point_list;    /* uint32  [cap]   sorted gaussian index             */
+  int64_t point_keys;    /* uint64  [cap]   sorted ((view*T+tile)<<32 | depth_bits) */
+  int64_t records;       /* 48 B    [cap]   sorted-gathered blend records     */
+  int64_t final_T;       /* float   [n_views*H*W]                             */
+  int64_t n_contrib;     /* uint32  [n_views*H*W]                             */
+  int32_t tiles_x, tiles_y, tiles, chunks;
+} s3r_raster_layout;
+
+int s3r_abi_version(void);
+const char* s3r_error_string(int code);
+
+/* Fills `out`; returns S3R_OK or S3R_ERR_UNSUPPORTED/INVALID_ARG. Pure host. */
+int s3r_raster_layout_query(int32_t n_views, int32_t P, int32_t width, int32_t height,
+                            int64_t capacity, s3r_raster_layout* out);
+
+/* Forward: preprocess -> tile binning (MSD radix digit, global memory) ->
+ * per-tile depth radix sort -> blend.  Stream-ordered, no host sync.  If the
+ * number of (tile, Gaussian) instances exceeds `capacity` the surplus is
+ * dropped and status.overflow is set (read it with s3r_raster_read_status). */
+int s3r_raster_forward(const s3r_raster_params* params, const s3r_raster_outputs* out, void* state,
+                       size_t state_bytes, int64_t capacity, void* stream);
+
+/* Blocking: copies status {num_instances, overflow, max_tile_count, 0}. */
+int s3r_raster_read_status(const void* state, int64_t host_out[4], void* stream);
+
+typedef struct s3r_raster_grads {
+  /* inputs */
+  const float* dL_dcolor; /* [n_views, 3, H, W]                              */
+  const float* dL_ddepth; /* [n_views, H, W] or NULL                         */
+  /* outputs — accumulated with atomicAdd, caller zero-fills; any may be NULL */
+  float* dL_dmeans3D;   /* [n_sets, P, 3]                                    */
+  float* dL_dcov3D;     /* [n_sets, P, cov_stride] (same packing as input; for
+                           stride 9 the symmetric gradient is written to the
+                           upper triangle positions only)                    */
+  float* dL_dshs;       /* [n_sets, P, M, 3]                                 */
+  float* dL_dcolors;    /* [n_sets, P, 3]                                    */
+  float* dL_dopacities; /* [n_sets, P]                                       */
+  float* dL_dmeans2D;   /* [n_views, P, 3] NDC-space mean gradient (x,y,0)   */
+  float* dL_dtau;       /* [n_views, 6] (rho, theta) pose gradient           */
+  /* scratch */
+  void* scratch;        /* >= s3r_raster_backward_scratch_bytes              */
+  size_t scratch_bytes;
+} s3r_raster_grads;
+
+size_t s3r_raster_backward_scratch_bytes(int32_t n_views, int32_t P);
+
+int s3r_raster_backward(const s3r_raster_params* params, const void* state, size_t state_bytes,
+                        int64_t capacity, const s3r_raster_grads* grads, void* stream);
+
+/* ------------------------------------------------------------------------
+ * RoPE-2D (curope replacement). tokens[B,N,H,D] modified in place.
+ * dtype: 0 = fp32, 1 = fp16, 2 = bf16.  pos is int64 [B,N,2] (y,x).
+ * ------------------------------------------------------------------------ */
+int s3r_rope2d(void* tokens, const int64_t* pos, int32_t B, int32_t N, int32_t H, int32_t D,
+               int64_t stride_b, int64_t stride_n, int64_t stride_h, float base, float fwd,
+               int32_t dtype, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Pose update: w2c_out[i] = SE3_exp([rho_i, theta_i]) @ w2c_in[i] (row-major
+ * 4x4, fp32).  Mirrors cam_utils.py:103-137 without the per-view host loop.
+ * ------------------------------------------------------------------------ */
+int s3r_se3_update_w2c(const float* w2c_in, const float* rho, const float* theta, float* w2c_out,
+                       int32_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STYL3R_B200_H_ */
