@@ -92,6 +92,7 @@ typedef struct s3r_raster_outputs {
 typedef struct s3r_raster_layout {
   int64_t total_bytes;
   int64_t status;        /* int64[4]: R_total, overflow, max_tile_count, rsvd */
+  int64_t counters;      /* uint32[8] device-side tickets                     */
   int64_t depths;        /* float   [nvP]   camera-space z                    */
   int64_t xy;            /* float2  [nvP]   pixel-space mean                  */
   int64_t conic_opacity; /* float4  [nvP]                                     */
@@ -99,8 +100,10 @@ typedef struct s3r_raster_layout {
   int64_t rect;          /* uint32  [nvP]   xmin|ymin<<8|xmax<<16|ymax<<24    */
   int64_t chunk_hist;    /* uint16  [n_views, chunks, tiles]                  */
   int64_t chunk_base;    /* uint32  [n_views, chunks, tiles]                  */
+  int64_t tile_count;    /* uint32  [nvT]   instances per (view, tile)        */
   int64_t ranges;        /* uint2   [nvT]   (start,end) into the sorted list  */
   int64_t keys_unsorted; /* uint64  [cap]   (depth_bits<<32 | gaussian) tile-binned */
+  int64_t keys_tmp;      /* uint64  [cap]   ping-pong buffer (oversized tiles)  */
   int64_t point_list;    /* uint32  [cap]   sorted gaussian index             */
   int64_t point_keys;    /* uint64  [cap]   sorted ((view*T+tile)<<32 | depth_bits) */
   int64_t records;       /* 48 B    [cap]   sorted-gathered blend records     */

@@ -1,0 +1,216 @@
+"""Host side of the B200 rasterizer: torch tensors in, C-ABI calls (ctypes) underneath.
+
+`rasterize(...)` is the batched, differentiable entry used by `styl3r_b200.decoder.render_cuda`; it replaces
+the per-view loop around the third-party `GaussianRasterizer` in the reference
+(src/model/decoder/cuda_splatting.py:93-133): one launch chain renders all views, without `.item()` syncs
+and without materialising per-view copies of the Gaussians (a `view_set` index maps views to Gaussian sets).
+
+PyTorch only provides device memory, the current stream and autograd plumbing here; there is no PyTorch/CPU
+fallback for the computation.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+
+from . import _lib
+
+_DT = {"u8": torch.uint8, "i32": torch.int32, "f32": torch.float32, "i64": torch.int64, "u16": torch.int16}
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def query_layout(n_views: int, P: int, W: int, H: int, capacity: int) -> _lib.RasterLayout:
+    lay = _lib.RasterLayout()
+    _lib.check(_lib.lib().s3r_raster_layout_query(n_views, P, W, H, capacity, lay), "s3r_raster_layout_query")
+    return lay
+
+
+@dataclass
+class RasterContext:
+    """Everything the backward pass (and the parity tests) need from one forward call."""
+    params: _lib.RasterParams
+    layout: _lib.RasterLayout
+    state: torch.Tensor
+    capacity: int
+    keep: tuple  # tensors referenced by raw pointers in `params`
+    n_views: int
+    n_sets: int
+    P: int
+    W: int
+    H: int
+
+    def view(self, name: str) -> torch.Tensor:
+        """Typed view of one internal array of the state buffer (tile assignment, sort order, ...)."""
+        L, nv, P, cap = self.layout, self.n_views, self.P, self.capacity
+        HW = self.W * self.H
+        spec = {
+            "status": ("i64", 4), "depths": ("f32", nv * P), "xy": ("f32", nv * P * 2),
+            "conic_opacity": ("f32", nv * P * 4), "rgb": ("f32", nv * P * 4), "rect": ("i32", nv * P),
+            "tile_count": ("i32", nv * L.tiles), "ranges": ("i32", nv * L.tiles * 2),
+            "keys_unsorted": ("i64", cap), "point_list": ("i32", cap), "point_keys": ("i64", cap),
+            "records": ("f32", cap * 12), "final_T": ("f32", nv * HW), "n_contrib": ("i32", nv * HW),
+            "chunk_hist": ("u16", nv * L.chunks * L.tiles), "chunk_base": ("i32", nv * L.chunks * L.tiles),
+        }[name]
+        dt = _DT[spec[0]]
+        off = getattr(L, name)
+        nbytes = spec[1] * torch.empty((), dtype=dt).element_size()
+        return self.state[off:off + nbytes].view(dt)
+
+    def status(self):
+        out = (C.c_int64 * 4)()
+        _lib.check(_lib.lib().s3r_raster_read_status(_ptr(self.state), out,
+                                                    C.c_void_p(torch.cuda.current_stream(self.state.device).cuda_stream)),
+                   "s3r_raster_read_status")
+        return dict(num_instances=int(out[0]), overflow=bool(out[1]), max_tile_count=int(out[2]))
+
+
+_capacity_hint: dict = {}
+
+
+def forward_raw(means, cov, opacities, viewmatrix, projmatrix, tanfov, background, W: int, H: int, *, shs=None,
+                colors_precomp=None, sh_degree: int = 0, campos=None, projmatrix_raw=None, scales=None,
+                view_set=None, want_n_touched: bool = False, capacity: Optional[int] = None, check: str = "sync"):
+    """Non-differentiable forward. Shapes: means [S,P,3]; cov [S,P,6] or [S,P,3,3]; opacities [S,P];
+    shs [S,P,M,3] or colors_precomp [S,P,3]; viewmatrix/projmatrix(/_raw) [V,4,4] in the reference's
+    transposed layout; tanfov [V,2]; background [V,3]; campos [V,3]; scales [V]; view_set [V] int32.
+
+    check: "sync"  — read the status word after the launches (one 32-byte D2H per *batch*) and transparently
+                     re-run with a larger instance capacity on overflow;
+           "none"  — fully asynchronous (CUDA-graph friendly); the caller inspects ctx.status() later.
+    Returns (color[V,3,H,W], depth[V,H,W], opacity[V,H,W], radii[V,P], n_touched[V,P] or None, ctx)."""
+    L = _lib.lib()
+    dev = means.device
+    if dev.type != "cuda":
+        raise _lib.S3RError("styl3r_b200 rasterizer needs CUDA tensors (no CPU fallback)")
+    means, opacities = _f32c(means), _f32c(opacities)
+    cov = _f32c(cov)
+    S, P = means.shape[0], means.shape[1]
+    cov_stride = 9 if cov.dim() == 4 else cov.shape[-1]
+    viewmatrix, projmatrix = _f32c(viewmatrix), _f32c(projmatrix)
+    V = viewmatrix.shape[0]
+    tanfov, background = _f32c(tanfov), _f32c(background)
+    shs = _f32c(shs) if shs is not None else None
+    colors_precomp = _f32c(colors_precomp) if colors_precomp is not None else None
+    campos = _f32c(campos) if campos is not None else None
+    projmatrix_raw = _f32c(projmatrix_raw) if projmatrix_raw is not None else None
+    scales = _f32c(scales) if scales is not None else None
+    if view_set is not None:
+        view_set = view_set.to(device=dev, dtype=torch.int32).contiguous()
+    M = shs.shape[2] if shs is not None else 1
+
+    key = (S, P, V, W, H)
+    cap = int(capacity) if capacity is not None else _capacity_hint.get(key, max(4 * P * V, 1 << 16))
+    stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    while True:
+        lay = query_layout(V, P, W, H, cap)
+        state = torch.empty(lay.total_bytes, dtype=torch.uint8, device=dev)
+        color = torch.empty(V, 3, H, W, dtype=torch.float32, device=dev)
+        depth = torch.empty(V, H, W, dtype=torch.float32, device=dev)
+        opacity = torch.empty(V, H, W, dtype=torch.float32, device=dev)
+        radii = torch.empty(V, P, dtype=torch.int32, device=dev)
+        n_touched = torch.zeros(V, P, dtype=torch.int32, device=dev) if want_n_touched else None
+        prm = _lib.RasterParams(
+            n_views=V, n_sets=S, P=P, width=W, height=H, sh_degree=sh_degree, sh_coeffs=M, cov_stride=cov_stride,
+            means3D=_ptr(means), cov3D=_ptr(cov), shs=_ptr(shs), colors_precomp=_ptr(colors_precomp),
+            opacities=_ptr(opacities), view_set=_ptr(view_set), viewmatrix=_ptr(viewmatrix),
+            projmatrix=_ptr(projmatrix), projmatrix_raw=_ptr(projmatrix_raw), campos=_ptr(campos),
+            tanfov=_ptr(tanfov), scales=_ptr(scales), background=_ptr(background))
+        out = _lib.RasterOutputs(color=_ptr(color), depth=_ptr(depth), opacity=_ptr(opacity), radii=_ptr(radii),
+                                 n_touched=_ptr(n_touched))
+        _lib.check(L.s3r_raster_forward(prm, out, _ptr(state), lay.total_bytes, cap, stream), "s3r_raster_forward")
+        ctx = RasterContext(prm, lay, state, cap,
+                            (means, cov, opacities, shs, colors_precomp, viewmatrix, projmatrix, projmatrix_raw,
+                             campos, tanfov, scales, background, view_set), V, S, P, W, H)
+        if check == "none":
+            break
+        st = ctx.status()
+        if not st["overflow"]:
+            # remember a comfortable capacity for this shape (next call allocates it up front)
+            _capacity_hint[key] = max(int(st["num_instances"] * 1.5) + 1024, 1 << 16)
+            break
+        cap = int(st["num_instances"] * 1.25) + 1024
+    return color, depth, opacity, radii, n_touched, ctx
+
+
+def backward_raw(ctx: RasterContext, dL_dcolor, dL_ddepth=None, *, need_pose: bool = True):
+    """Gradients w.r.t. the tensors given to forward_raw. Returns a dict of tensors shaped like the inputs
+    (`cov` in the packing it was given), plus dL_dmeans2D [V,P,3] and dL_dtau [V,6] = (rho, theta)."""
+    L = _lib.lib()
+    prm = ctx.params
+    dev = ctx.state.device
+    V, S, P = ctx.n_views, ctx.n_sets, ctx.P
+    M, cs = prm.sh_coeffs, prm.cov_stride
+    dL_dcolor = _f32c(dL_dcolor)
+    dL_ddepth = _f32c(dL_ddepth) if dL_ddepth is not None else None
+    g = dict(
+        means=torch.zeros(S, P, 3, device=dev), cov=torch.zeros(S, P, cs, device=dev),
+        opacities=torch.zeros(S, P, device=dev), means2D=torch.zeros(V, P, 3, device=dev),
+        tau=torch.zeros(V, 6, device=dev),
+        shs=torch.zeros(S, P, M, 3, device=dev) if prm.shs else None,
+        colors=torch.zeros(S, P, 3, device=dev) if prm.colors_precomp else None,
+    )
+    nbytes = L.s3r_raster_backward_scratch_bytes(V, P)
+    scratch = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    grads = _lib.RasterGrads(
+        dL_dcolor=_ptr(dL_dcolor), dL_ddepth=_ptr(dL_ddepth), dL_dmeans3D=_ptr(g["means"]), dL_dcov3D=_ptr(g["cov"]),
+        dL_dshs=_ptr(g["shs"]), dL_dcolors=_ptr(g["colors"]), dL_dopacities=_ptr(g["opacities"]),
+        dL_dmeans2D=_ptr(g["means2D"]), dL_dtau=_ptr(g["tau"]) if need_pose else None, scratch=_ptr(scratch),
+        scratch_bytes=nbytes)
+    stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    _lib.check(L.s3r_raster_backward(prm, _ptr(ctx.state), ctx.layout.total_bytes, ctx.capacity, grads, stream),
+               "s3r_raster_backward")
+    return g
+
+
+class _Rasterize(torch.autograd.Function):
+    """Differentiable batched rasterization. Camera tensors are treated as constants except for the pose
+    perturbation (cam_trans_delta -> rho, cam_rot_delta -> theta) whose gradient dL/dtau the kernel produces,
+    matching the `theta=` / `rho=` arguments of the reference call (cuda_splatting.py:127-128)."""
+
+    @staticmethod
+    def forward(ctx, means, cov, opacities, shs, colors_precomp, rho, theta, cfg):
+        color, depth, opacity, radii, n_touched, rctx = forward_raw(
+            means, cov, opacities, cfg["viewmatrix"], cfg["projmatrix"], cfg["tanfov"], cfg["background"], cfg["W"],
+            cfg["H"], shs=shs, colors_precomp=colors_precomp, sh_degree=cfg["sh_degree"], campos=cfg["campos"],
+            projmatrix_raw=cfg["projmatrix_raw"], scales=cfg.get("scales"), view_set=cfg.get("view_set"),
+            want_n_touched=cfg.get("want_n_touched", False), capacity=cfg.get("capacity"),
+            check=cfg.get("check", "sync"))
+        ctx.rctx = rctx
+        ctx.cov_shape = cov.shape
+        ctx.has = (shs is not None, colors_precomp is not None, rho is not None, theta is not None)
+        ctx.mark_non_differentiable(opacity, radii)
+        if n_touched is None:
+            n_touched = torch.empty(0, dtype=torch.int32, device=means.device)
+        ctx.mark_non_differentiable(n_touched)
+        cfg["_ctx"] = rctx
+        return color, depth, opacity, radii, n_touched
+
+    @staticmethod
+    def backward(ctx, g_color, g_depth, *_):
+        rctx = ctx.rctx
+        has_sh, has_col, has_rho, has_theta = ctx.has
+        g = backward_raw(rctx, g_color, g_depth, need_pose=has_rho or has_theta)
+        g_cov = g["cov"].reshape(ctx.cov_shape) if len(ctx.cov_shape) == 3 else g["cov"].reshape(ctx.cov_shape)
+        if len(ctx.cov_shape) == 4:
+            # the kernel wrote the symmetric gradient into the upper-triangle slots; split it over both halves so
+            # that it is the gradient w.r.t. all nine (independent) entries, like indexing cov[:, row, col] does.
+            g_cov = g_cov
+        return (g["means"], g_cov, g["opacities"], g["shs"] if has_sh else None, g["colors"] if has_col else None,
+                g["tau"][:, :3] if has_rho else None, g["tau"][:, 3:] if has_theta else None, None)
+
+
+def rasterize(means, cov, opacities, *, shs=None, colors_precomp=None, rho=None, theta=None, **cfg):
+    """Differentiable batched rasterization; see forward_raw for shapes. Extra outputs: opacity, radii, n_touched."""
+    return _Rasterize.apply(means, cov, opacities, shs, colors_precomp, rho, theta, cfg)
