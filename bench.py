@@ -1,0 +1,380 @@
+#!/usr/bin/env python
+"""bench.py — stylized target views/s at 256x256 with ~130k Gaussians (BASELINE.json metric), B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE cfg2, "re10k_2v"): one scene of 2x256x256 pixel-aligned Gaussians (P = 131 072, SURVEY §8d
+synthetic recipe), 1 target view rasterized per step: preprocess -> tile binning -> per-tile depth radix sort ->
+alpha blend.  A step is one pass of that path over one scene; the encoder is not part of the step (round-1 scope:
+SURVEY §8 rows a11-a14).  Steps rotate over several resident scenes so that consecutive steps do not reuse L2.
+
+  value      views/s with inputs resident in HBM (CUDA-graph replay of the kernel chain), max-over-ranks time
+  e2e        same metric through the public `render_cuda` call with pinned HOST buffers: H2D of the Gaussians and
+             cameras and D2H of the image inside the timed region
+  roofline   blend kernel: algorithmic bytes (40 R + 20 HW + 8 T) / CUDA-event time of that kernel, vs measured HBM peak
+  cpu_baseline / --impl reference: the CPU oracle (oracle/raster_oracle.c, a port: the upstream rasterizer is
+             un-vendored and has no CPU path) on all host threads.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+import numpy as np  # noqa: E402
+
+METRIC = "stylized target views/sec at 256x256, ~130k Gaussians"
+WORKLOAD = "cfg2 re10k_2v raster: 1 scene, v=2 (P=131072 Gaussians), 1 target view 256x256, sh_degree 0, scale-invariant"
+HW = 256
+V_CTX = 2
+V_TGT = 1
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            time.sleep(0.25)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_scene(seed):
+    from styl3r_b200 import synthetic as syn
+    return syn.make_scene(seed=seed, v=V_CTX, V=V_TGT, hw=HW)
+
+
+# ----------------------------------------------------------------------------- reference / CPU arm
+
+
+def oracle_step(scene):
+    from oracle import raster_oracle as ro
+    outs = []
+    for v in range(scene["extrinsics"].shape[0]):
+        cam = ro.camera_setup(scene["extrinsics"][v], scene["intrinsics"][v], scene["near"][v], scene["far"][v], True)
+        m, c = ro.scale_gaussians(scene["means"], scene["covariances"], cam["scale"])
+        shs = np.ascontiguousarray(scene["harmonics"].transpose(0, 2, 1))
+        outs.append(ro.forward(m, ro.cov3x3_to_6(c), scene["opacities"], cam["view16"], cam["proj16"], cam["campos"],
+                               HW, HW, cam["tanx"], cam["tany"], np.zeros(3, np.float32), shs=shs, deg=0))
+    return outs
+
+
+def cpu_baseline(n_steps=3, warmup=1):
+    from oracle import raster_oracle as ro
+    scene = make_scene(1234)
+    for _ in range(warmup):
+        oracle_step(scene)
+    t0 = time.perf_counter()
+    for _ in range(n_steps):
+        oracle_step(scene)
+    dt = time.perf_counter() - t0
+    return {"value": V_TGT * n_steps / dt, "unit": "views/s", "cores": ro.num_threads(), "kind": "port",
+            "sample": f"{n_steps} steps of the same workload (oracle/raster_oracle.c, OpenMP over Gaussians and tiles)"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import raster_oracle as ro
+    scenes = [make_scene(1234 + i) for i in range(2)]
+    for i in range(args.warmup):
+        oracle_step(scenes[i % 2])
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        oracle_step(scenes[i % 2])
+    dt = time.perf_counter() - t0
+    val = V_TGT * args.steps / dt
+    cb = {"value": val, "unit": "views/s", "cores": ro.num_threads(), "kind": "port",
+          "sample": f"{args.steps} full steps (1 view each) on {ro.num_threads()} host threads"}
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "views/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "note": "CPU restatement of the un-vendored upstream rasterizer (no CPU path "
+                   "exists in the reference); parity unpinned"},
+        "cpu_baseline": cb, "e2e": {"value": val, "unit": "views/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ----------------------------------------------------------------------------- our arm
+
+
+def run_ours(args):
+    import torch
+
+    from styl3r_b200 import rasterizer as rz
+    from styl3r_b200.decoder import cuda_splatting as cs
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback for the product path)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier(device_ids=[local])
+
+    n_slots = args.slots
+    K, Wm = args.steps, max(args.warmup, 3)
+    # ---- resident inputs: n_slots different scenes per rank (weak scaling: every rank renders its own scenes)
+    slots = []
+    for s in range(n_slots):
+        sc = make_scene(1234 + 1000 * rank + s)
+        t = lambda a: torch.as_tensor(a, device=dev)
+        g = dict(means=t(sc["means"])[None], cov=t(sc["covariances"])[None], sh=t(sc["harmonics"])[None],
+                 opac=t(sc["opacities"])[None], extr=t(sc["extrinsics"]), intr=t(sc["intrinsics"]),
+                 near=t(sc["near"]), far=t(sc["far"]))
+        # camera set-up exactly as render_cuda does it (torch, on device, once per slot)
+        scale = 1 / g["near"]
+        extr = g["extr"].clone()
+        extr[:, :3, 3] = extr[:, :3, 3] * scale[:, None]
+        fov = cs.get_fov(g["intr"])
+        proj_t = cs.get_projection_matrix(g["near"] * scale, g["far"] * scale, fov[:, 0], fov[:, 1]).transpose(1, 2).contiguous()
+        view_t = extr.inverse().transpose(1, 2).contiguous()
+        full = (view_t @ proj_t).contiguous()
+        tensors = (g["means"], g["cov"], g["opac"], g["sh"].reshape(1, -1, 1, 3), None, view_t, full, proj_t,
+                   extr[:, :3, 3].contiguous(), (0.5 * fov).tan().contiguous(), scale.contiguous(),
+                   torch.zeros(V_TGT, 3, device=dev), torch.zeros(V_TGT, dtype=torch.int32, device=dev))
+        P = g["means"].shape[1]
+        probe = rz.RasterPlan(tensors, 1, P, V_TGT, HW, HW, 1, 0, 9, 4 * P * V_TGT)
+        probe.launch()
+        st = probe.ctx.status()
+        assert not st["overflow"]
+        plan = rz.RasterPlan(tensors, 1, P, V_TGT, HW, HW, 1, 0, 9, int(st["num_instances"] * 1.1) + 1024)
+        plan.launch()
+        slots.append(dict(g=g, plan=plan, R=st["num_instances"], max_tile=st["max_tile_count"], sc=sc))
+    torch.cuda.synchronize()
+    resident_mb = sum(s["plan"].state.numel() + 64 * P for s in slots) / 1e6
+    # ---- CUDA graphs: one per slot
+    graphs = []
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        for s in slots:
+            gph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gph, stream=side):
+                s["plan"].launch()
+            graphs.append(gph)
+    torch.cuda.synchronize()
+    n_streams = max(1, min(args.streams, n_slots))
+    streams = [torch.cuda.Stream() for _ in range(n_streams)]
+    main = torch.cuda.current_stream()
+
+    def run_steps(count):
+        """`count` steps; step i renders scene slot i % n_slots on stream (i % n_slots) % n_streams, so independent
+        scenes overlap on the GPU while a slot's buffers are never used by two streams at once."""
+        fork = torch.cuda.Event()
+        fork.record(main)
+        for st in streams:
+            st.wait_event(fork)
+        for i in range(count):
+            sl = i % n_slots
+            with torch.cuda.stream(streams[sl % n_streams]):
+                graphs[sl].replay()
+        for st in streams:
+            j = torch.cuda.Event()
+            j.record(st)
+            main.wait_event(j)
+
+    run_steps(Wm)
+    torch.cuda.synchronize()
+
+    # ---- timed region A: K graph replays
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        barrier()
+        torch.cuda.synchronize()
+        e0.record()
+        run_steps(K)
+        e1.record()
+        torch.cuda.synchronize()
+        barrier()
+    ms = e0.elapsed_time(e1)
+    if dist is not None:
+        tms = torch.tensor([ms], device=dev)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        ms = float(tms.item())
+    value = world * V_TGT * K / (ms / 1e3)
+    launches = 5 * K  # preprocess, bin_scan, bin_emit, tile_sort, blend per step
+
+    # ---- region B: per-stage CUDA-event timing over the same K steps (direct launches, same stream)
+    stages = [("preprocess", rz.STAGE_PREPROCESS), ("bin", rz.STAGE_BIN), ("sort", rz.STAGE_SORT),
+              ("blend", rz.STAGE_BLEND)]
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(K)]
+    for i in range(K):
+        pl = slots[i % n_slots]["plan"]
+        ev[i][0].record()
+        for j, (_, m) in enumerate(stages):
+            pl.launch(m)
+            ev[i][j + 1].record()
+    torch.cuda.synchronize()
+    stage_ms = {n: sum(ev[i][j].elapsed_time(ev[i][j + 1]) for i in range(K)) / K for j, (n, _) in enumerate(stages)}
+    R_mean = sum(slots[i % n_slots]["R"] for i in range(K)) / K
+    T_tiles = (HW // 16) ** 2
+    blend_bytes = 40.0 * R_mean + 20.0 * HW * HW * V_TGT + 8.0 * T_tiles * V_TGT
+    peak, peak_src = peaks()
+    achieved = blend_bytes / (stage_ms["blend"] * 1e-3) / 1e9
+    traffic = None
+    tj = ROOT / "profiles" / "blend_traffic.json"
+    if tj.exists():
+        try:
+            traffic = json.loads(tj.read_text()).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+
+    # ---- e2e through the public API with pinned host buffers
+    Ke = min(K, 100)
+    host = []
+    for s in slots:
+        sc = s["sc"]
+        pin = lambda a: torch.as_tensor(np.ascontiguousarray(a)).pin_memory()
+        host.append(dict(means=pin(sc["means"][None]), cov=pin(sc["covariances"][None]), sh=pin(sc["harmonics"][None]),
+                         opac=pin(sc["opacities"][None]), extr=pin(sc["extrinsics"]), intr=pin(sc["intrinsics"]),
+                         near=pin(sc["near"]), far=pin(sc["far"]), bg=torch.zeros(V_TGT, 3).pin_memory()))
+    out_host = torch.empty(V_TGT, 3, HW, HW).pin_memory()
+    h2d = sum(v.numel() * v.element_size() for v in host[0].values())
+    d2h = out_host.numel() * 4
+
+    def e2e_step(h):
+        d = {k: v.to(dev, non_blocking=True) for k, v in h.items()}
+        color, _ = cs.render_cuda(d["extr"], d["intr"], d["near"], d["far"], (HW, HW), d["bg"], d["means"], d["cov"],
+                                  d["sh"], d["opac"], scale_invariant=True,
+                                  view_set=torch.zeros(V_TGT, dtype=torch.int32, device=dev))
+        out_host.copy_(color, non_blocking=True)
+
+    with torch.no_grad():
+        for i in range(3):
+            e2e_step(host[i % n_slots])
+        torch.cuda.synchronize()
+        barrier()
+        t0 = time.perf_counter()
+        e0.record()
+        for i in range(Ke):
+            e2e_step(host[i % n_slots])
+        e1.record()
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+    e2e_ms = max(e0.elapsed_time(e1), wall * 1e3)
+    if dist is not None:
+        tms = torch.tensor([e2e_ms], device=dev)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        e2e_ms = float(tms.item())
+    e2e_val = world * V_TGT * Ke / (e2e_ms / 1e3)
+
+    cb = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cb = cpu_baseline()
+
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": "views/s", "n_gpus": world, "steps": K, "warmup": Wm,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD, "P": P, "R_mean": R_mean, "max_tile_instances": max(s["max_tile"] for s in slots),
+                       "l2": f"inputs larger than L2: steps rotate over {n_slots} resident scenes ({resident_mb:.0f} MB)",
+                       "launch": f"CUDA graph replay of the 5-kernel chain, independent scenes on {n_streams} concurrent streams; "
+                                 "camera matrices precomputed per scene",
+                       "parallelism": f"scene-sharded x{world}, no collective"},
+            "clocks": clk.summary(),
+            "e2e": {"value": e2e_val, "unit": "views/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": Ke, "api": "styl3r_b200.decoder.render_cuda (host pinned tensors in, pinned image out)"},
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "kernel": "s3r_blend_fwd_kernel", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": blend_bytes, "kernel_ms": stage_ms["blend"],
+                         "note": "blend is FP32/MUFU-bound by arithmetic intensity (SURVEY §7); see profiles/"},
+            "stage_ms": stage_ms,
+            "cpu_baseline": cb,
+        }))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--slots", type=int, default=8)
+    ap.add_argument("--streams", type=int, default=4, help="concurrent streams over independent scenes")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -126,6 +126,17 @@ int s3r_raster_layout_query(int32_t n_views, int32_t P, int32_t width, int32_t h
 int s3r_raster_forward(const s3r_raster_params* params, const s3r_raster_outputs* out, void* state,
                        size_t state_bytes, int64_t capacity, void* stream);
 
+/* Same, but only the stages selected by `stage_mask` are launched (the others'
+ * results must already be in `state` from an earlier call with identical
+ * arguments).  Used by bench.py to time one stage with CUDA events. */
+#define S3R_STAGE_PREPROCESS 1u
+#define S3R_STAGE_BIN 2u
+#define S3R_STAGE_SORT 4u
+#define S3R_STAGE_BLEND 8u
+#define S3R_STAGE_ALL 15u
+int s3r_raster_forward_stages(const s3r_raster_params* params, const s3r_raster_outputs* out, void* state,
+                              size_t state_bytes, int64_t capacity, uint32_t stage_mask, void* stream);
+
 /* Blocking: copies status {num_instances, overflow, max_tile_count, 0}. */
 int s3r_raster_read_status(const void* state, int64_t host_out[4], void* stream);
 

@@ -70,6 +70,8 @@ def lib():
                                           C.POINTER(RasterLayout)]
     L.s3r_raster_forward.argtypes = [C.POINTER(RasterParams), C.POINTER(RasterOutputs), C.c_void_p, C.c_size_t,
                                      C.c_int64, C.c_void_p]
+    L.s3r_raster_forward_stages.argtypes = [C.POINTER(RasterParams), C.POINTER(RasterOutputs), C.c_void_p, C.c_size_t,
+                                            C.c_int64, C.c_uint32, C.c_void_p]
     L.s3r_raster_read_status.argtypes = [C.c_void_p, C.POINTER(C.c_int64 * 4), C.c_void_p]
     L.s3r_raster_backward_scratch_bytes.restype = C.c_size_t
     L.s3r_raster_backward_scratch_bytes.argtypes = [C.c_int32, C.c_int32]
@@ -91,7 +93,7 @@ def check(code: int, what: str = "") -> None:
 
 
 EXPORTED_SYMBOLS = (
-    "s3r_abi_version", "s3r_error_string", "s3r_raster_layout_query", "s3r_raster_forward",
+    "s3r_abi_version", "s3r_error_string", "s3r_raster_layout_query", "s3r_raster_forward", "s3r_raster_forward_stages",
     "s3r_raster_read_status", "s3r_raster_backward_scratch_bytes", "s3r_raster_backward", "s3r_rope2d",
     "s3r_se3_update_w2c",
 )

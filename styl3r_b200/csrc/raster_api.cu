@@ -78,8 +78,8 @@ static int validate(const s3r_raster_params* p) {
   return S3R_OK;
 }
 
-extern "C" int s3r_raster_forward(const s3r_raster_params* params, const s3r_raster_outputs* out, void* state,
-                                  size_t state_bytes, int64_t capacity, void* stream) {
+extern "C" int s3r_raster_forward_stages(const s3r_raster_params* params, const s3r_raster_outputs* out, void* state,
+                                         size_t state_bytes, int64_t capacity, uint32_t stage_mask, void* stream) {
   int rc = validate(params);
   if (rc != S3R_OK) return rc;
   if (!out || !out->color || !out->depth || !out->opacity || !out->radii || !state) return S3R_ERR_INVALID_ARG;
@@ -89,11 +89,17 @@ extern "C" int s3r_raster_forward(const s3r_raster_params* params, const s3r_ras
   if ((int64_t)state_bytes < L.total_bytes) return S3R_ERR_STATE_TOO_SMALL;
   cudaStream_t st = (cudaStream_t)stream;
   char* s = (char*)state;
-  if ((rc = s3r_launch_preprocess(*params, L, s, out->radii, st)) != S3R_OK) return rc;
-  if ((rc = s3r_launch_bin(*params, L, s, capacity, st)) != S3R_OK) return rc;
-  if ((rc = s3r_launch_sort(*params, L, s, st)) != S3R_OK) return rc;
-  if ((rc = s3r_launch_blend(*params, *out, L, s, st)) != S3R_OK) return rc;
+  if ((stage_mask & S3R_STAGE_PREPROCESS) && (rc = s3r_launch_preprocess(*params, L, s, out->radii, st)) != S3R_OK)
+    return rc;
+  if ((stage_mask & S3R_STAGE_BIN) && (rc = s3r_launch_bin(*params, L, s, capacity, st)) != S3R_OK) return rc;
+  if ((stage_mask & S3R_STAGE_SORT) && (rc = s3r_launch_sort(*params, L, s, st)) != S3R_OK) return rc;
+  if ((stage_mask & S3R_STAGE_BLEND) && (rc = s3r_launch_blend(*params, *out, L, s, st)) != S3R_OK) return rc;
   return S3R_OK;
+}
+
+extern "C" int s3r_raster_forward(const s3r_raster_params* params, const s3r_raster_outputs* out, void* state,
+                                  size_t state_bytes, int64_t capacity, void* stream) {
+  return s3r_raster_forward_stages(params, out, state, state_bytes, capacity, S3R_STAGE_ALL, stream);
 }
 
 extern "C" int s3r_raster_read_status(const void* state, int64_t host_out[4], void* stream) {

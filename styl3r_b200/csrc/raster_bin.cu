@@ -13,92 +13,107 @@
 //              (oracle/raster_oracle.c:s3r_oracle_bin_sort).
 #include "s3r_common.cuh"
 
-// grid (ceil(T/32), n_views), 256 threads = 8 warps x 32 tiles.
-__global__ void __launch_bounds__(256) s3r_bin_scan_kernel(int tiles, int chunks, int n_views,
-                                                           const uint16_t* __restrict__ chunk_hist,
-                                                           uint32_t* __restrict__ chunk_base,
-                                                           uint32_t* __restrict__ tile_count,
-                                                           uint2* __restrict__ ranges, long long* __restrict__ status,
-                                                           unsigned* __restrict__ counters, long long capacity) {
-  __shared__ uint32_t s_part[8][32];
-  __shared__ uint32_t s_warp[8];
+// grid (ceil(T/32), n_views), 1024 threads = 32 warps x 32 tiles; warp w scans a slice of the chunks.
+#define SCAN_THREADS 1024
+#define SCAN_WARPS 32
+__global__ void __launch_bounds__(SCAN_THREADS) s3r_bin_scan_kernel(int tiles, int chunks, int n_views,
+                                                                    const uint16_t* __restrict__ chunk_hist,
+                                                                    uint32_t* __restrict__ chunk_base,
+                                                                    uint32_t* __restrict__ tile_count,
+                                                                    uint2* __restrict__ ranges,
+                                                                    long long* __restrict__ status,
+                                                                    unsigned* __restrict__ counters,
+                                                                    long long capacity) {
+  __shared__ uint32_t s_part[SCAN_WARPS][32];
+  __shared__ unsigned long long s_wsum[SCAN_WARPS];
+  __shared__ uint32_t s_wmax[SCAN_WARPS];
+  __shared__ unsigned long long s_carry;
   __shared__ unsigned s_last;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int view = blockIdx.y;
   const int t = blockIdx.x * 32 + lane;
-  const int cpw = (chunks + 7) / 8;
-  const int c0 = w * cpw, c1 = min(chunks, c0 + cpw);
+  const int cpw = (chunks + SCAN_WARPS - 1) / SCAN_WARPS;
+  const int c0 = min(chunks, w * cpw), c1 = min(chunks, c0 + cpw);
   const uint16_t* hist = chunk_hist + (size_t)view * chunks * tiles;
   uint32_t* base = chunk_base + (size_t)view * chunks * tiles;
   uint32_t sum = 0;
   if (t < tiles) {
-#pragma unroll 8
+#pragma unroll 16
     for (int c = c0; c < c1; c++) sum += hist[(size_t)c * tiles + t];
   }
   s_part[w][lane] = sum;
   __syncthreads();
   uint32_t run = 0, total = 0;
 #pragma unroll
-  for (int k = 0; k < 8; k++) {
-    uint32_t v = s_part[k][lane];
+  for (int k = 0; k < SCAN_WARPS; k++) {
+    const uint32_t v = s_part[k][lane];
     if (k < w) run += v;
     total += v;
   }
   if (t < tiles) {
-#pragma unroll 8
+#pragma unroll 16
     for (int c = c0; c < c1; c++) {
+      const uint32_t h = hist[(size_t)c * tiles + t];
       base[(size_t)c * tiles + t] = run;
-      run += hist[(size_t)c * tiles + t];
+      run += h;
     }
     if (w == 0) tile_count[(size_t)view * tiles + t] = total;
   }
-  // ---- last CTA: exclusive scan over all (view, tile) totals
+  // ---- last CTA: exclusive scan over all (view, tile) totals -> ranges
   __threadfence();
   __syncthreads();
-  if (threadIdx.x == 0) s_last = atomicAdd(&counters[0], 1u);
+  if (threadIdx.x == 0) {
+    s_last = atomicAdd(&counters[0], 1u);
+    s_carry = 0ull;
+  }
   __syncthreads();
   if (s_last != gridDim.x * gridDim.y - 1) return;
   __threadfence();
   const int n = n_views * tiles;
-  const int per = (n + 255) / 256;
-  const int i0 = threadIdx.x * per, i1 = min(n, i0 + per);
-  unsigned long long local = 0;
+  const unsigned long long cap = (unsigned long long)capacity;
   uint32_t mx = 0;
-  for (int i = i0; i < i1; i++) {
-    uint32_t v = __ldcg(&tile_count[i]);
-    local += v;
-    mx = max(mx, v);
-  }
-  // block exclusive scan of `local` (64-bit)
-  unsigned long long incl = local;
+  for (int i0 = 0; i0 < n; i0 += SCAN_THREADS * 4) {
+    const int i = i0 + threadIdx.x * 4;
+    uint32_t v[4];
 #pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    unsigned long long u = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= o) incl += u;
+    for (int k = 0; k < 4; k++) v[k] = (i + k < n) ? __ldcg(&tile_count[i + k]) : 0u;
+    const unsigned long long local = (unsigned long long)v[0] + v[1] + v[2] + v[3];
+    mx = max(mx, max(max(v[0], v[1]), max(v[2], v[3])));
+    unsigned long long incl = local;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned long long u = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += u;
+    }
+    if (lane == 31) s_wsum[w] = incl;
+    __syncthreads();
+    unsigned long long woff = s_carry, blk = 0;
+    for (int k = 0; k < SCAN_WARPS; k++) {
+      const unsigned long long x = s_wsum[k];
+      if (k < w) woff += x;
+      blk += x;
+    }
+    unsigned long long runp = woff + incl - local;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      if (i + k < n) {
+        const unsigned long long sb = runp, e = runp + v[k];
+        ranges[i + k] = make_uint2((uint32_t)min(sb, cap), (uint32_t)min(e, cap));
+        runp = e;
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) s_carry += blk;
+    __syncthreads();
   }
-  __shared__ unsigned long long s_wsum[8];
-  if (lane == 31) s_wsum[w] = incl;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-  if (lane == 0) s_warp[w] = mx;
+  if (lane == 0) s_wmax[w] = mx;
   __syncthreads();
-  unsigned long long woff = 0, grand = 0;
-  uint32_t gmx = 0;
-#pragma unroll
-  for (int k = 0; k < 8; k++) {
-    if (k < w) woff += s_wsum[k];
-    grand += s_wsum[k];
-    gmx = max(gmx, s_warp[k]);
-  }
-  unsigned long long runp = woff + incl - local;
-  const unsigned long long cap = (unsigned long long)capacity;
-  for (int i = i0; i < i1; i++) {
-    uint32_t v = __ldcg(&tile_count[i]);
-    unsigned long long s = runp, e = runp + v;
-    runp = e;
-    ranges[i] = make_uint2((uint32_t)min(s, cap), (uint32_t)min(e, cap));
-  }
   if (threadIdx.x == 0) {
+    uint32_t gmx = 0;
+    for (int k = 0; k < SCAN_WARPS; k++) gmx = max(gmx, s_wmax[k]);
+    const unsigned long long grand = s_carry;
     status[0] = (long long)grand;
     status[1] = grand > cap ? 1 : 0;
     status[2] = gmx;
@@ -158,7 +173,7 @@ __global__ void __launch_bounds__(S3R_CHUNK) s3r_bin_emit_kernel(int P, int tile
 int s3r_launch_bin(const s3r_raster_params& p, const s3r_raster_layout& L, char* state, int64_t capacity,
                    cudaStream_t st) {
   dim3 g1((L.tiles + 31) / 32, p.n_views);
-  s3r_bin_scan_kernel<<<g1, 256, 0, st>>>(L.tiles, L.chunks, p.n_views, (const uint16_t*)(state + L.chunk_hist),
+  s3r_bin_scan_kernel<<<g1, SCAN_THREADS, 0, st>>>(L.tiles, L.chunks, p.n_views, (const uint16_t*)(state + L.chunk_hist),
                                           (uint32_t*)(state + L.chunk_base), (uint32_t*)(state + L.tile_count),
                                           (uint2*)(state + L.ranges), (long long*)(state + L.status),
                                           (unsigned*)(state + L.counters), (long long)capacity);

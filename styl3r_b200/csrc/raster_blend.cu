@@ -1,11 +1,13 @@
 // Rasterizer stage 5: per-tile front-to-back alpha blend (forward).
 //
-// One CTA per (view, 16x16 tile); warp w owns the 8x4 pixel block (w&1, w>>1) of the tile, one pixel per
-// lane.  The tile's sorted-gathered 48-byte records are streamed through a 2-stage shared-memory ring by
-// TMA bulk copies (cp.async.bulk + mbarrier complete_tx; SASS: UBLKCP / SYNCS), 256 records per stage.
-// Per stage every thread tests one record's alpha>=1/255 bounding box against the eight pixel blocks and
-// the warps exchange 8 ballots, so that each warp then walks only the records that can touch its block
-// (warp-uniform compaction — skipping a record that cannot reach 1/255 is result-neutral).
+// One CTA per (view, 16x16 tile): 8 consumer warps + 1 producer warp.  Consumer warp w owns the 8x4 pixel
+// block (w&1, w>>1) of the tile, one pixel per lane.  The tile's sorted-gathered 48-byte records are streamed
+// through a 4-stage shared-memory ring by TMA bulk copies issued by the producer warp (cp.async.bulk +
+// mbarrier complete_tx; SASS: UBLKCP / SYNCS), 128 records per stage; full/empty mbarriers decouple the
+// consumer warps from each other (no CTA-wide barrier in the main loop).  Per stage a warp tests the
+// records' alpha>=1/255 bounding boxes against its own pixel block, compacts the survivors with ballots and
+// composites only those, BLEND_U at a time (warp-uniform compaction — skipping a record that cannot reach
+// 1/255 is result-neutral).
 //
 // Semantics follow upstream renderCUDA + the "-w-pose" fork (blended depth, opacity, n_touched) as restated by
 // oracle/raster_oracle.c:s3r_oracle_render:  power is evaluated with the
@@ -14,8 +16,8 @@
 // that the keep/skip decision matches the oracle.
 #include "s3r_common.cuh"
 
-#define BLEND_THREADS 256
-#define BLEND_CHUNK 256
+#define BLEND_THREADS 288
+#define BLEND_CHUNK 128
 #define ALPHA_MIN (1.0f / 255.0f)
 #define ALPHA_LO (ALPHA_MIN * (1.0f - 2e-5f))
 #define ALPHA_HI (ALPHA_MIN * (1.0f + 2e-5f))
@@ -55,13 +57,39 @@ __device__ __noinline__ float exact_alpha(float power, float opacity) {
   return fminf(0.99f, __fmul_rn(opacity, e));
 }
 
-struct __align__(16) BlendSmem {
-  float4 rec[2][BLEND_CHUNK * 3];
-  uint32_t mask[8][8];
-  uint64_t full[2];
+#define BLEND_U 4        // survivors evaluated per batch (independent alpha chains -> ILP)
+#define BLEND_STAGES 4   // depth of the TMA ring
+#define BLEND_CWARPS 8   // consumer warps (one 8x4 pixel block each); warp 8 is the TMA producer
+
+struct __align__(128) BlendSmem {
+  float4 rec[BLEND_STAGES][BLEND_CHUNK * 3];
+  uint8_t list[BLEND_CWARPS][BLEND_CHUNK + 16];  // per-warp compacted survivor indices
+  uint64_t full[BLEND_STAGES];                   // producer -> consumers (expect_tx / complete_tx)
+  uint64_t empty[BLEND_STAGES];                  // consumers -> producer (one arrival per consumer warp)
+  int done_warps;
 };
 
-__global__ void __launch_bounds__(BLEND_THREADS) s3r_blend_fwd_kernel(
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+
+// Warp-specialised: warp 8 streams the tile's records through a BLEND_STAGES-deep ring with TMA bulk copies;
+// the 8 consumer warps run decoupled from each other (no CTA-wide barrier in the main loop): each culls the
+// stage against its own 8x4 pixel block, composites the survivors front to back, and releases the stage.
+__global__ void __launch_bounds__(BLEND_THREADS, 3) s3r_blend_fwd_kernel(
     int W, int H, int P, int tiles_x, int tiles, const uint2* __restrict__ ranges, const float4* __restrict__ records,
     const uint32_t* __restrict__ point_list, const float* __restrict__ background, float* __restrict__ out_color,
     float* __restrict__ out_depth, float* __restrict__ out_opacity, float* __restrict__ final_T,
@@ -69,119 +97,160 @@ __global__ void __launch_bounds__(BLEND_THREADS) s3r_blend_fwd_kernel(
   __shared__ BlendSmem sm;
   const int view = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x;
   const int lane = tid & 31, w = tid >> 5;
-  const int tx = tile % tiles_x, ty = tile / tiles_x;
-  const int X0 = tx * S3R_TILE, Y0 = ty * S3R_TILE;
-  const int px = X0 + (w & 1) * 8 + (lane & 7), py = Y0 + (w >> 1) * 4 + (lane >> 3);
-  const bool inside = px < W && py < H;
-  const float pxf = (float)px, pyf = (float)py;
   const uint2 rg = ranges[(size_t)view * tiles + tile];
   const uint32_t n = rg.y - rg.x;
   const uint32_t nchunks = (n + BLEND_CHUNK - 1) / BLEND_CHUNK;
   const float4* src = records + (size_t)rg.x * 3;
 
   if (tid == 0) {
-    mbar_init(&sm.full[0], 1);
-    mbar_init(&sm.full[1], 1);
+#pragma unroll
+    for (int s = 0; s < BLEND_STAGES; s++) {
+      mbar_init(&sm.full[s], 1);
+      mbar_init(&sm.empty[s], BLEND_CWARPS);
+    }
+    sm.done_warps = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  if (tid == 0) {
-    for (uint32_t c = 0; c < 2 && c < nchunks; c++) {
-      const uint32_t cnt = min((uint32_t)BLEND_CHUNK, n - c * BLEND_CHUNK);
-      mbar_expect_tx(&sm.full[c], cnt * S3R_REC_BYTES);
-      bulk_g2s(sm.rec[c], src + (size_t)c * BLEND_CHUNK * 3, cnt * S3R_REC_BYTES, &sm.full[c]);
+
+  if (w == BLEND_CWARPS) {
+    // ===== TMA producer (one elected lane)
+    if (lane == 0) {
+      uint32_t issued = 0;
+      for (uint32_t c = 0; c < nchunks; c++) {
+        const int s = c % BLEND_STAGES;
+        if (c >= BLEND_STAGES) {
+          const uint32_t par = ((c / BLEND_STAGES) - 1) & 1;
+          while (!mbar_try(&sm.empty[s], par)) {
+            if (*(volatile int*)&sm.done_warps == BLEND_CWARPS) break;
+          }
+        }
+        if (*(volatile int*)&sm.done_warps == BLEND_CWARPS) break;
+        const uint32_t cnt = min((uint32_t)BLEND_CHUNK, n - c * BLEND_CHUNK);
+        mbar_expect_tx(&sm.full[s], cnt * S3R_REC_BYTES);
+        bulk_g2s(sm.rec[s], src + (size_t)c * BLEND_CHUNK * 3, cnt * S3R_REC_BYTES, &sm.full[s]);
+        issued = c + 1;
+      }
+      // drain: every issued copy must have landed before the CTA may retire
+      const uint32_t first = issued > BLEND_STAGES ? issued - BLEND_STAGES : 0;
+      for (uint32_t c = first; c < issued; c++) mbar_wait(&sm.full[c % BLEND_STAGES], (c / BLEND_STAGES) & 1);
     }
+    return;
   }
+
+  // ===== consumers
+  const int tx = tile % tiles_x, ty = tile / tiles_x;
+  const int X0 = tx * S3R_TILE + (w & 1) * 8, Y0 = ty * S3R_TILE + (w >> 1) * 4;  // this warp's 8x4 block
+  const int px = X0 + (lane & 7), py = Y0 + (lane >> 3);
+  const bool inside = px < W && py < H;
+  const float pxf = (float)px, pyf = (float)py;
+  const float bx0 = (float)X0, by0 = (float)Y0;
+  const uint32_t lt = (1u << lane) - 1u;
+  uint8_t* list = sm.list[w];
 
   float T = 1.0f, Cr = 0.f, Cg = 0.f, Cb = 0.f, D = 0.f;
   uint32_t last = 0;
   bool done = !inside;
-  // block pixel bounds for the cull test
-  const float bx0 = (float)X0, by0 = (float)Y0;
+  bool warp_done = !__any_sync(0xffffffffu, !done);
+  if (warp_done && lane == 0) atomicAdd(&sm.done_warps, 1);
 
   for (uint32_t c = 0; c < nchunks; c++) {
-    const int s = c & 1;
-    const uint32_t cnt = min((uint32_t)BLEND_CHUNK, n - c * BLEND_CHUNK);
-    mbar_wait(&sm.full[s], (c >> 1) & 1);
-    // ---- cull: record `tid` against the 8 pixel blocks
-    {
-      bool hx0 = false, hx1 = false, hy[4] = {false, false, false, false};
-      if ((uint32_t)tid < cnt) {
-        const float4 r0 = sm.rec[s][tid * 3];
-        const float4 r2 = sm.rec[s][tid * 3 + 2];
-        const float xl = r0.x - r2.z, xh = r0.x + r2.z, yl = r0.y - r2.w, yh = r0.y + r2.w;
-        const bool ok = r2.z >= 0.f;
-        hx0 = ok && xh >= bx0 && xl <= bx0 + 7.f;
-        hx1 = ok && xh >= bx0 + 8.f && xl <= bx0 + 15.f;
-#pragma unroll
-        for (int k = 0; k < 4; k++) hy[k] = yh >= by0 + 4.f * k && yl <= by0 + 4.f * k + 3.f;
+    const int s = c % BLEND_STAGES;
+    if (warp_done) {
+      // drain mode: keep releasing stages in phase order so the producer never stalls on us
+      if (*(volatile int*)&sm.done_warps == BLEND_CWARPS) break;
+      if (c >= BLEND_STAGES) {
+        const uint32_t par = ((c / BLEND_STAGES) - 1) & 1;
+        bool all = false;
+        while (!mbar_try(&sm.empty[s], par)) {
+          if (*(volatile int*)&sm.done_warps == BLEND_CWARPS) { all = true; break; }
+        }
+        if (all) break;
       }
-#pragma unroll
-      for (int b = 0; b < 8; b++) {
-        const uint32_t m = __ballot_sync(0xffffffffu, ((b & 1) ? hx1 : hx0) && hy[b >> 1]);
-        if (lane == 0) sm.mask[b][w] = m;
-      }
+      if (lane == 0) mbar_arrive(&sm.empty[s]);
+      __syncwarp();
+      continue;
     }
-    __syncthreads();
-    // ---- blend: warp w walks the survivors of its block in list order
-    if (__any_sync(0xffffffffu, !done)) {
-      const uint32_t base_idx = c * BLEND_CHUNK;
+    const uint32_t cnt = min((uint32_t)BLEND_CHUNK, n - c * BLEND_CHUNK);
+    mbar_wait(&sm.full[s], (c / BLEND_STAGES) & 1);
+    // ---- cull this stage against the warp's own pixel block and compact the survivors
+    int count = 0;
+#pragma unroll
+    for (int j = 0; j < BLEND_CHUNK / 32; j++) {
+      const int i = j * 32 + lane;
+      bool hit = false;
+      if ((uint32_t)i < cnt) {
+        const float4 r0 = sm.rec[s][i * 3];
+        const float4 r2 = sm.rec[s][i * 3 + 2];
+        hit = r2.z >= 0.f && (r0.x + r2.z >= bx0) && (r0.x - r2.z <= bx0 + 7.f) && (r0.y + r2.w >= by0) &&
+              (r0.y - r2.w <= by0 + 3.f);
+      }
+      const uint32_t m = __ballot_sync(0xffffffffu, hit);
+      if (hit) list[count + __popc(m & lt)] = (uint8_t)i;
+      count += __popc(m);
+    }
+    __syncwarp();
+    const uint32_t base_idx = c * BLEND_CHUNK;
 #pragma unroll 1
-      for (int j = 0; j < 8; j++) {
-        uint32_t m = sm.mask[w][j];
-        while (m) {
-          const int i = j * 32 + __ffs(m) - 1;
-          m &= m - 1;
-          const float4 r0 = sm.rec[s][i * 3];
-          const float4 r1 = sm.rec[s][i * 3 + 1];
-          const float4 r2 = sm.rec[s][i * 3 + 2];
-          if (!done) {
-            const float dx = r0.x - pxf, dy = r0.y - pyf;
-            const float q = __fadd_rn(__fmul_rn(__fmul_rn(r0.z, dx), dx), __fmul_rn(__fmul_rn(r1.x, dy), dy));
-            const float power = __fsub_rn(__fmul_rn(-0.5f, q), __fmul_rn(__fmul_rn(r0.w, dx), dy));
-            if (!(power > 0.0f)) {
-              float alpha = fminf(0.99f, r1.y * __expf(power));
-              bool keep = true;
-              if (alpha < ALPHA_HI) {
-                keep = false;
-                if (alpha >= ALPHA_LO) {
-                  alpha = exact_alpha(power, r1.y);
-                  keep = alpha >= ALPHA_MIN;
-                }
-              }
-              if (keep) {
-                const float test_T = T * (1.0f - alpha);
-                if (test_T < 0.0001f) {
-                  done = true;
-                } else {
-                  const float wgt = alpha * T;
-                  Cr += r1.z * wgt;
-                  Cg += r1.w * wgt;
-                  Cb += r2.x * wgt;
-                  D += r2.y * wgt;
-                  if (n_touched != nullptr && test_T > 0.5f)
-                    atomicAdd(&n_touched[(size_t)view * P + point_list[(size_t)rg.x + base_idx + i]], 1);
-                  T = test_T;
-                  last = base_idx + i + 1;
-                }
-              }
-            }
+    for (int k = 0; k < count; k += BLEND_U) {
+      const uint32_t packed = *reinterpret_cast<const uint32_t*>(list + k);
+      float alpha[BLEND_U], cr[BLEND_U], cg[BLEND_U], cb[BLEND_U], dp[BLEND_U];
+      bool keep[BLEND_U];
+      int idx[BLEND_U];
+#pragma unroll
+      for (int u = 0; u < BLEND_U; u++) {
+        const int i = (packed >> (8 * u)) & (BLEND_CHUNK - 1);  // bytes past `count` are stale: keep them in range
+        idx[u] = i;
+        const float4 r0 = sm.rec[s][i * 3];
+        const float4 r1 = sm.rec[s][i * 3 + 1];
+        const float4 r2 = sm.rec[s][i * 3 + 2];
+        const float dx = r0.x - pxf, dy = r0.y - pyf;
+        const float q = __fadd_rn(__fmul_rn(__fmul_rn(r0.z, dx), dx), __fmul_rn(__fmul_rn(r1.x, dy), dy));
+        const float power = __fsub_rn(__fmul_rn(-0.5f, q), __fmul_rn(__fmul_rn(r0.w, dx), dy));
+        float a = fminf(0.99f, r1.y * __expf(power));
+        bool kp = (k + u < count) && !(power > 0.0f);
+        if (kp && a < ALPHA_HI) {
+          kp = false;
+          if (a >= ALPHA_LO) {
+            a = exact_alpha(power, r1.y);
+            kp = a >= ALPHA_MIN;
           }
         }
-        if (!__any_sync(0xffffffffu, !done)) break;
+        alpha[u] = a;
+        keep[u] = kp;
+        cr[u] = r1.z;
+        cg[u] = r1.w;
+        cb[u] = r2.x;
+        dp[u] = r2.y;
+      }
+#pragma unroll
+      for (int u = 0; u < BLEND_U; u++) {
+        if (keep[u] && !done) {
+          const float test_T = T * (1.0f - alpha[u]);
+          if (test_T < 0.0001f) {
+            done = true;
+          } else {
+            const float wgt = alpha[u] * T;
+            Cr += cr[u] * wgt;
+            Cg += cg[u] * wgt;
+            Cb += cb[u] * wgt;
+            D += dp[u] * wgt;
+            if (n_touched != nullptr && test_T > 0.5f)
+              atomicAdd(&n_touched[(size_t)view * P + point_list[(size_t)rg.x + base_idx + idx[u]]], 1);
+            T = test_T;
+            last = base_idx + idx[u] + 1;
+          }
+        }
+      }
+      if (!__any_sync(0xffffffffu, !done)) {
+        warp_done = true;
+        break;
       }
     }
-    const int ndone = __syncthreads_count(done);
-    if (ndone == BLEND_THREADS) {
-      // a bulk copy for chunk c+1 may still be in flight into the other stage: drain it before the CTA retires
-      if (tid == 0 && c + 1 < nchunks) mbar_wait(&sm.full[s ^ 1], ((c + 1) >> 1) & 1);
-      break;
-    }
-    if (tid == 0 && c + 2 < nchunks) {
-      const uint32_t c2 = c + 2;
-      const uint32_t cnt2 = min((uint32_t)BLEND_CHUNK, n - c2 * BLEND_CHUNK);
-      mbar_expect_tx(&sm.full[s], cnt2 * S3R_REC_BYTES);
-      bulk_g2s(sm.rec[s], src + (size_t)c2 * BLEND_CHUNK * 3, cnt2 * S3R_REC_BYTES, &sm.full[s]);
+    __syncwarp();
+    if (lane == 0) {
+      if (warp_done) atomicAdd(&sm.done_warps, 1);
+      mbar_arrive(&sm.empty[s]);
     }
   }
   if (inside) {

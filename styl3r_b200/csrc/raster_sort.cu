@@ -136,6 +136,7 @@ __global__ void __launch_bounds__(SORT_THREADS) s3r_tile_sort_kernel(
   // epilogue: ids, keys, gathered records
   const size_t vbase = (size_t)view * P;
   const unsigned long long tile_hi = ((unsigned long long)((uint32_t)view * (uint32_t)tiles + (uint32_t)tile)) << 32;
+#pragma unroll 4
   for (uint32_t i = tid; i < n; i += SORT_THREADS) {
     const unsigned long long k = (n <= S3R_SORT_SMEM_CAP) ? sorted[i] : __ldcg(sorted + i);
     const uint32_t id = (uint32_t)k, dbits = (uint32_t)(k >> 32);

@@ -112,27 +112,12 @@ def forward_raw(means, cov, opacities, viewmatrix, projmatrix, tanfov, backgroun
 
     key = (S, P, V, W, H)
     cap = int(capacity) if capacity is not None else _capacity_hint.get(key, max(4 * P * V, 1 << 16))
-    stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    tensors = (means, cov, opacities, shs, colors_precomp, viewmatrix, projmatrix, projmatrix_raw, campos, tanfov,
+               scales, background, view_set)
     while True:
-        lay = query_layout(V, P, W, H, cap)
-        state = torch.empty(lay.total_bytes, dtype=torch.uint8, device=dev)
-        color = torch.empty(V, 3, H, W, dtype=torch.float32, device=dev)
-        depth = torch.empty(V, H, W, dtype=torch.float32, device=dev)
-        opacity = torch.empty(V, H, W, dtype=torch.float32, device=dev)
-        radii = torch.empty(V, P, dtype=torch.int32, device=dev)
-        n_touched = torch.zeros(V, P, dtype=torch.int32, device=dev) if want_n_touched else None
-        prm = _lib.RasterParams(
-            n_views=V, n_sets=S, P=P, width=W, height=H, sh_degree=sh_degree, sh_coeffs=M, cov_stride=cov_stride,
-            means3D=_ptr(means), cov3D=_ptr(cov), shs=_ptr(shs), colors_precomp=_ptr(colors_precomp),
-            opacities=_ptr(opacities), view_set=_ptr(view_set), viewmatrix=_ptr(viewmatrix),
-            projmatrix=_ptr(projmatrix), projmatrix_raw=_ptr(projmatrix_raw), campos=_ptr(campos),
-            tanfov=_ptr(tanfov), scales=_ptr(scales), background=_ptr(background))
-        out = _lib.RasterOutputs(color=_ptr(color), depth=_ptr(depth), opacity=_ptr(opacity), radii=_ptr(radii),
-                                 n_touched=_ptr(n_touched))
-        _lib.check(L.s3r_raster_forward(prm, out, _ptr(state), lay.total_bytes, cap, stream), "s3r_raster_forward")
-        ctx = RasterContext(prm, lay, state, cap,
-                            (means, cov, opacities, shs, colors_precomp, viewmatrix, projmatrix, projmatrix_raw,
-                             campos, tanfov, scales, background, view_set), V, S, P, W, H)
+        plan = RasterPlan(tensors, S, P, V, W, H, M, sh_degree, cov_stride, cap, want_n_touched)
+        plan.launch()
+        ctx = plan.ctx
         if check == "none":
             break
         st = ctx.status()
@@ -141,7 +126,45 @@ def forward_raw(means, cov, opacities, viewmatrix, projmatrix, tanfov, backgroun
             _capacity_hint[key] = max(int(st["num_instances"] * 1.5) + 1024, 1 << 16)
             break
         cap = int(st["num_instances"] * 1.25) + 1024
-    return color, depth, opacity, radii, n_touched, ctx
+    return plan.color, plan.depth, plan.opacity, plan.radii, plan.n_touched, ctx
+
+
+STAGE_PREPROCESS, STAGE_BIN, STAGE_SORT, STAGE_BLEND, STAGE_ALL = 1, 2, 4, 8, 15
+
+
+class RasterPlan:
+    """Pre-allocated state + outputs + parameter block for one rasterization shape; `launch()` enqueues the
+    kernel chain (or the stages selected by `stage_mask`) on the current stream and can be called repeatedly or
+    captured in a CUDA graph."""
+
+    def __init__(self, tensors, S, P, V, W, H, M, sh_degree, cov_stride, cap, want_n_touched=False):
+        (means, cov, opacities, shs, colors_precomp, viewmatrix, projmatrix, projmatrix_raw, campos, tanfov, scales,
+         background, view_set) = tensors
+        dev = means.device
+        self.dev = dev
+        lay = query_layout(V, P, W, H, cap)
+        self.state = torch.empty(lay.total_bytes, dtype=torch.uint8, device=dev)
+        self.color = torch.empty(V, 3, H, W, dtype=torch.float32, device=dev)
+        self.depth = torch.empty(V, H, W, dtype=torch.float32, device=dev)
+        self.opacity = torch.empty(V, H, W, dtype=torch.float32, device=dev)
+        self.radii = torch.empty(V, P, dtype=torch.int32, device=dev)
+        self.n_touched = torch.zeros(V, P, dtype=torch.int32, device=dev) if want_n_touched else None
+        self.prm = _lib.RasterParams(
+            n_views=V, n_sets=S, P=P, width=W, height=H, sh_degree=sh_degree, sh_coeffs=M, cov_stride=cov_stride,
+            means3D=_ptr(means), cov3D=_ptr(cov), shs=_ptr(shs), colors_precomp=_ptr(colors_precomp),
+            opacities=_ptr(opacities), view_set=_ptr(view_set), viewmatrix=_ptr(viewmatrix),
+            projmatrix=_ptr(projmatrix), projmatrix_raw=_ptr(projmatrix_raw), campos=_ptr(campos),
+            tanfov=_ptr(tanfov), scales=_ptr(scales), background=_ptr(background))
+        self.out = _lib.RasterOutputs(color=_ptr(self.color), depth=_ptr(self.depth), opacity=_ptr(self.opacity),
+                                      radii=_ptr(self.radii), n_touched=_ptr(self.n_touched))
+        self.cap = cap
+        self.ctx = RasterContext(self.prm, lay, self.state, cap, tensors, V, S, P, W, H)
+
+    def launch(self, stage_mask: int = STAGE_ALL):
+        stream = C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
+        _lib.check(_lib.lib().s3r_raster_forward_stages(self.prm, self.out, _ptr(self.state),
+                                                        self.ctx.layout.total_bytes, self.cap, stage_mask, stream),
+                   "s3r_raster_forward")
 
 
 def backward_raw(ctx: RasterContext, dL_dcolor, dL_ddepth=None, *, need_pose: bool = True):
@@ -177,10 +200,11 @@ def backward_raw(ctx: RasterContext, dL_dcolor, dL_ddepth=None, *, need_pose: bo
 class _Rasterize(torch.autograd.Function):
     """Differentiable batched rasterization. Camera tensors are treated as constants except for the pose
     perturbation (cam_trans_delta -> rho, cam_rot_delta -> theta) whose gradient dL/dtau the kernel produces,
-    matching the `theta=` / `rho=` arguments of the reference call (cuda_splatting.py:127-128)."""
+    matching the `theta=` / `rho=` arguments of the reference call (cuda_splatting.py:127-128).  `means2D` is
+    upstream's screen-space gradient holder: its value is ignored, its .grad receives dL/d(NDC mean)."""
 
     @staticmethod
-    def forward(ctx, means, cov, opacities, shs, colors_precomp, rho, theta, cfg):
+    def forward(ctx, means, cov, opacities, shs, colors_precomp, rho, theta, means2D, cfg):
         color, depth, opacity, radii, n_touched, rctx = forward_raw(
             means, cov, opacities, cfg["viewmatrix"], cfg["projmatrix"], cfg["tanfov"], cfg["background"], cfg["W"],
             cfg["H"], shs=shs, colors_precomp=colors_precomp, sh_degree=cfg["sh_degree"], campos=cfg["campos"],
@@ -189,11 +213,11 @@ class _Rasterize(torch.autograd.Function):
             check=cfg.get("check", "sync"))
         ctx.rctx = rctx
         ctx.cov_shape = cov.shape
+        ctx.m2d_shape = None if means2D is None else means2D.shape
         ctx.has = (shs is not None, colors_precomp is not None, rho is not None, theta is not None)
-        ctx.mark_non_differentiable(opacity, radii)
         if n_touched is None:
             n_touched = torch.empty(0, dtype=torch.int32, device=means.device)
-        ctx.mark_non_differentiable(n_touched)
+        ctx.mark_non_differentiable(opacity, radii, n_touched)
         cfg["_ctx"] = rctx
         return color, depth, opacity, radii, n_touched
 
@@ -202,15 +226,13 @@ class _Rasterize(torch.autograd.Function):
         rctx = ctx.rctx
         has_sh, has_col, has_rho, has_theta = ctx.has
         g = backward_raw(rctx, g_color, g_depth, need_pose=has_rho or has_theta)
-        g_cov = g["cov"].reshape(ctx.cov_shape) if len(ctx.cov_shape) == 3 else g["cov"].reshape(ctx.cov_shape)
-        if len(ctx.cov_shape) == 4:
-            # the kernel wrote the symmetric gradient into the upper-triangle slots; split it over both halves so
-            # that it is the gradient w.r.t. all nine (independent) entries, like indexing cov[:, row, col] does.
-            g_cov = g_cov
-        return (g["means"], g_cov, g["opacities"], g["shs"] if has_sh else None, g["colors"] if has_col else None,
-                g["tau"][:, :3] if has_rho else None, g["tau"][:, 3:] if has_theta else None, None)
+        g_m2d = None if ctx.m2d_shape is None else g["means2D"].reshape(ctx.m2d_shape)
+        return (g["means"], g["cov"].reshape(ctx.cov_shape), g["opacities"], g["shs"] if has_sh else None,
+                g["colors"] if has_col else None, g["tau"][:, :3] if has_rho else None,
+                g["tau"][:, 3:] if has_theta else None, g_m2d, None)
 
 
-def rasterize(means, cov, opacities, *, shs=None, colors_precomp=None, rho=None, theta=None, **cfg):
-    """Differentiable batched rasterization; see forward_raw for shapes. Extra outputs: opacity, radii, n_touched."""
-    return _Rasterize.apply(means, cov, opacities, shs, colors_precomp, rho, theta, cfg)
+def rasterize(means, cov, opacities, *, shs=None, colors_precomp=None, rho=None, theta=None, means2D=None, **cfg):
+    """Differentiable batched rasterization; see forward_raw for shapes.
+    Returns (color, depth, opacity, radii, n_touched)."""
+    return _Rasterize.apply(means, cov, opacities, shs, colors_precomp, rho, theta, means2D, cfg)
