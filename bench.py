@@ -366,8 +366,8 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--slots", type=int, default=8)
-    ap.add_argument("--streams", type=int, default=4, help="concurrent streams over independent scenes")
+    ap.add_argument("--slots", type=int, default=16)
+    ap.add_argument("--streams", type=int, default=8, help="concurrent streams over independent scenes")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -57,7 +57,8 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         obj = OBJDIR / (src.stem + ".o")
         if not force and not _stale(obj, [src, *hdrs, Path(__file__)]):
             return obj, ""
-        cmd = [cc, *ccbin, *ARCH, *COMMON, *EXTRA.get(src.name, []), "-c", str(src), "-o", str(obj)]
+        cmd = [cc, *ccbin, *ARCH, *COMMON, *EXTRA.get(src.name, []), *os.environ.get("S3R_NVCC_FLAGS", "").split(),
+               "-c", str(src), "-o", str(obj)]
         if verbose:
             cmd += ["-Xptxas", "-v"]
         r = subprocess.run(cmd, capture_output=True, text=True, env=env)

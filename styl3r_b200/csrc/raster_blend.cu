@@ -57,8 +57,15 @@ __device__ __noinline__ float exact_alpha(float power, float opacity) {
   return fminf(0.99f, __fmul_rn(opacity, e));
 }
 
+#ifndef BLEND_U
 #define BLEND_U 4        // survivors evaluated per batch (independent alpha chains -> ILP)
+#endif
+#ifndef BLEND_STAGES
 #define BLEND_STAGES 4   // depth of the TMA ring
+#endif
+#ifndef BLEND_MINB
+#define BLEND_MINB 4
+#endif
 #define BLEND_CWARPS 8   // consumer warps (one 8x4 pixel block each); warp 8 is the TMA producer
 
 struct __align__(128) BlendSmem {
@@ -89,7 +96,7 @@ __device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
 // Warp-specialised: warp 8 streams the tile's records through a BLEND_STAGES-deep ring with TMA bulk copies;
 // the 8 consumer warps run decoupled from each other (no CTA-wide barrier in the main loop): each culls the
 // stage against its own 8x4 pixel block, composites the survivors front to back, and releases the stage.
-__global__ void __launch_bounds__(BLEND_THREADS, 3) s3r_blend_fwd_kernel(
+__global__ void __launch_bounds__(BLEND_THREADS, BLEND_MINB) s3r_blend_fwd_kernel(
     int W, int H, int P, int tiles_x, int tiles, const uint2* __restrict__ ranges, const float4* __restrict__ records,
     const uint32_t* __restrict__ point_list, const float* __restrict__ background, float* __restrict__ out_color,
     float* __restrict__ out_depth, float* __restrict__ out_opacity, float* __restrict__ final_T,
@@ -193,13 +200,15 @@ __global__ void __launch_bounds__(BLEND_THREADS, 3) s3r_blend_fwd_kernel(
     const uint32_t base_idx = c * BLEND_CHUNK;
 #pragma unroll 1
     for (int k = 0; k < count; k += BLEND_U) {
-      const uint32_t packed = *reinterpret_cast<const uint32_t*>(list + k);
+      uint32_t packed[(BLEND_U + 3) / 4];
+#pragma unroll
+      for (int q4 = 0; q4 < (BLEND_U + 3) / 4; q4++) packed[q4] = *reinterpret_cast<const uint32_t*>(list + k + 4 * q4);
       float alpha[BLEND_U], cr[BLEND_U], cg[BLEND_U], cb[BLEND_U], dp[BLEND_U];
       bool keep[BLEND_U];
       int idx[BLEND_U];
 #pragma unroll
       for (int u = 0; u < BLEND_U; u++) {
-        const int i = (packed >> (8 * u)) & (BLEND_CHUNK - 1);  // bytes past `count` are stale: keep them in range
+        const int i = (packed[u >> 2] >> (8 * (u & 3))) & (BLEND_CHUNK - 1);  // bytes past `count` are stale: keep them in range
         idx[u] = i;
         const float4 r0 = sm.rec[s][i * 3];
         const float4 r1 = sm.rec[s][i * 3 + 1];
