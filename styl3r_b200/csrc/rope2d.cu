@@ -92,9 +92,10 @@ static int dispatch_vec(void* tokens, const int64_t* pos, int B, int N, int H, i
 extern "C" int s3r_rope2d(void* tokens, const int64_t* pos, int32_t B, int32_t N, int32_t H, int32_t D,
                           int64_t stride_b, int64_t stride_n, int64_t stride_h, float base, float fwd, int32_t dtype,
                           void* stream) {
-  if (!tokens || !pos || B < 0 || N < 0 || H <= 0 || D <= 0) return S3R_ERR_INVALID_ARG;
+  if (B < 0 || N < 0 || H < 0 || D <= 0) return S3R_ERR_INVALID_ARG;
   if (D % 4 != 0) return S3R_ERR_INVALID_ARG;  // same contract as curope.cpp:58
-  if (B == 0 || N == 0) return S3R_OK;
+  if (B == 0 || N == 0 || H == 0) return S3R_OK;
+  if (!tokens || !pos) return S3R_ERR_INVALID_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   switch (dtype) {
     case 0: return dispatch_vec<float, 4>(tokens, pos, B, N, H, D, stride_b, stride_n, stride_h, base, fwd, st);

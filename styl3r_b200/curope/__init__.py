@@ -42,6 +42,8 @@ def rope_2d(tokens: torch.Tensor, positions: torch.Tensor, base: float, fwd: flo
     if positions.dtype != torch.int64:
         raise RuntimeError("positions must be int64")
     B, N, H, D = tokens.shape
+    if tokens.numel() == 0:
+        return
     stream = C.c_void_p(torch.cuda.current_stream(tokens.device).cuda_stream)
     _lib.check(_lib.lib().s3r_rope2d(C.c_void_p(tokens.data_ptr()), C.c_void_p(positions.data_ptr()), B, N, H, D,
                                      tokens.stride(0), tokens.stride(1), tokens.stride(2), float(base), float(fwd),
