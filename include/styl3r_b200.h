@@ -165,6 +165,17 @@ int s3r_raster_backward(const s3r_raster_params* params, const void* state, size
                         int64_t capacity, const s3r_raster_grads* grads, void* stream);
 
 /* ------------------------------------------------------------------------
+ * Camera set-up of render_cuda (cuda_splatting.py:65-72,81-88; projection.py:
+ * 247-261) for n views in one launch: extrinsics [n,4,4] camera-to-world
+ * (row-major), intrinsics [n,3,3] normalised, near/far [n].  Outputs are the
+ * tensors s3r_raster_params expects: viewmatrix / projmatrix / projmatrix_raw
+ * [n,16] (transposed layout), campos [n,3], tanfov [n,2], scales [n].
+ * ------------------------------------------------------------------------ */
+int s3r_camera_setup(const float* extrinsics, const float* intrinsics, const float* near_, const float* far_,
+                     int32_t scale_invariant, int32_t n, float* viewmatrix, float* projmatrix,
+                     float* projmatrix_raw, float* campos, float* tanfov, float* scales, void* stream);
+
+/* ------------------------------------------------------------------------
  * RoPE-2D (curope replacement). tokens[B,N,H,D] modified in place.
  * dtype: 0 = fp32, 1 = fp16, 2 = bf16.  pos is int64 [B,N,2] (y,x).
  * ------------------------------------------------------------------------ */

@@ -19,6 +19,9 @@ from typing import Literal, Optional
 import torch
 from torch import Tensor
 
+import ctypes as _C
+
+from .. import _lib
 from .. import rasterizer as _rz
 
 DepthRenderingMode = Literal["depth", "disparity", "relative_disparity", "log"]
@@ -50,6 +53,29 @@ def get_projection_matrix(near: Tensor, far: Tensor, fov_x: Tensor, fov_y: Tenso
     m[:, 2, 2] = far / (far - near)
     m[:, 2, 3] = -(far * near) / (far - near)
     return m
+
+
+def camera_setup(extrinsics: Tensor, intrinsics: Tensor, near: Tensor, far: Tensor, scale_invariant: bool):
+    """All per-view camera tensors of `render_cuda` in ONE kernel launch (s3r_camera_setup): returns
+    (viewmatrix_T [B,4,4], full_projection_T [B,4,4], projection_T [B,4,4], campos [B,3], tan_fov [B,2], scale [B])
+    in the transposed layout the rasterizer expects (reference lines 65-72, 81-88).  Camera tensors are treated
+    as constants (no autograd), as everywhere in Styl3R — pose optimisation goes through the cam deltas."""
+    if extrinsics.device.type != "cuda":
+        raise _lib.S3RError("styl3r_b200 render_cuda needs CUDA tensors (no CPU fallback)")
+    b = extrinsics.shape[0]
+    dev = extrinsics.device
+    f = lambda t: t.detach().to(torch.float32).contiguous()
+    e, k, n_, f_ = f(extrinsics), f(intrinsics), f(near), f(far)
+    buf = torch.empty(b * 54, dtype=torch.float32, device=dev)
+    view_t, full, proj_t = (buf[16 * b * i:16 * b * (i + 1)].view(b, 4, 4) for i in range(3))
+    campos = buf[48 * b:51 * b].view(b, 3)
+    tan_fov = buf[51 * b:53 * b].view(b, 2)
+    scale = buf[53 * b:54 * b]
+    p = lambda t: _C.c_void_p(t.data_ptr())
+    _lib.check(_lib.lib().s3r_camera_setup(p(e), p(k), p(n_), p(f_), int(bool(scale_invariant)), b, p(view_t), p(full),
+                                           p(proj_t), p(campos), p(tan_fov), p(scale),
+                                           _C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), "s3r_camera_setup")
+    return view_t, full, proj_t, campos, tan_fov, scale
 
 
 def _sh_layout(sh: Tensor) -> Tensor:
@@ -97,19 +123,17 @@ def render_cuda(
     """Returns (color [B,3,h,w], depth [B,h,w]); differentiable w.r.t. means, covariances, SH, opacities and the
     camera deltas, like the reference."""
     assert use_sh or gaussian_sh_coefficients.shape[-1] == 1
-    near_scale = None
-    if scale_invariant:
-        near_scale = 1 / near
-        extrinsics = extrinsics.clone()
-        extrinsics[..., :3, 3] = extrinsics[..., :3, 3] * near_scale[:, None]
-        far = far * near_scale
-        near = near * near_scale
-    fov = get_fov(intrinsics)
-    tan_fov = (0.5 * fov).tan()
-    projection = get_projection_matrix(near, far, fov[:, 0], fov[:, 1])
-    color, depth, _, _, _ = _render(extrinsics, tan_fov, projection, near_scale, image_shape, background_color,
-                                    gaussian_means, gaussian_covariances, gaussian_sh_coefficients,
-                                    gaussian_opacities, use_sh, cam_rot_delta, cam_trans_delta, view_set, check=check)
+    h, w = image_shape
+    view_t, full, proj_t, campos, tan_fov, scale = camera_setup(extrinsics, intrinsics, near, far, scale_invariant)
+    sh = gaussian_sh_coefficients
+    degree = isqrt(sh.shape[-1]) - 1
+    shs = _sh_layout(sh)
+    kw = dict(shs=shs) if use_sh else dict(colors_precomp=shs[:, :, 0, :])
+    color, depth, _, _, _ = _rz.rasterize(
+        gaussian_means, gaussian_covariances, gaussian_opacities, rho=cam_trans_delta, theta=cam_rot_delta,
+        viewmatrix=view_t, projmatrix=full, projmatrix_raw=proj_t, campos=campos, tanfov=tan_fov,
+        background=background_color, W=w, H=h, sh_degree=degree, scales=scale if scale_invariant else None,
+        view_set=view_set, check=check, **kw)
     return color, depth
 
 

@@ -77,6 +77,29 @@ class RasterContext:
 
 
 _capacity_hint: dict = {}
+_pending: list = []  # deferred overflow checks: (event, pinned status copy, shape key)
+
+
+def validate_pending(block: bool = False) -> None:
+    """Resolve deferred overflow checks (check="deferred").  Raises S3RError if an earlier asynchronous render
+    dropped instances because its capacity was too small (the capacity hint is raised so a retry succeeds)."""
+    bad = None
+    keep = []
+    for ev, host, key in _pending:
+        if block:
+            ev.synchronize()
+        if ev.query():
+            r_total, overflow = int(host[0]), bool(host[1])
+            _capacity_hint[key] = max(_capacity_hint.get(key, 0), int(r_total * 1.5) + 1024, 1 << 16)
+            if overflow:
+                bad = (key, r_total)
+        else:
+            keep.append((ev, host, key))
+    _pending[:] = keep
+    if bad is not None:
+        raise _lib.S3RError(f"a deferred-check render (S,P,V,W,H)={bad[0]} overflowed its instance capacity "
+                            f"(needed {bad[1]}); its image is incomplete — re-render (capacity hint updated)")
+
 
 
 def forward_raw(means, cov, opacities, viewmatrix, projmatrix, tanfov, background, W: int, H: int, *, shs=None,
@@ -86,9 +109,12 @@ def forward_raw(means, cov, opacities, viewmatrix, projmatrix, tanfov, backgroun
     shs [S,P,M,3] or colors_precomp [S,P,3]; viewmatrix/projmatrix(/_raw) [V,4,4] in the reference's
     transposed layout; tanfov [V,2]; background [V,3]; campos [V,3]; scales [V]; view_set [V] int32.
 
-    check: "sync"  — read the status word after the launches (one 32-byte D2H per *batch*) and transparently
-                     re-run with a larger instance capacity on overflow;
-           "none"  — fully asynchronous (CUDA-graph friendly); the caller inspects ctx.status() later.
+    check: "sync"     — read the status word after the launches (one 32-byte D2H per *batch*) and transparently
+                        re-run with a larger instance capacity on overflow;
+           "deferred" — asynchronous once a capacity hint exists for this shape (first call syncs): the status word
+                        is copied to pinned memory and inspected by a later call / validate_pending(), which raises
+                        if the render had overflowed (capacity = 1.5x the largest R seen, so this is rare);
+           "none"     — fully asynchronous (CUDA-graph friendly); the caller inspects ctx.status() later.
     Returns (color[V,3,H,W], depth[V,H,W], opacity[V,H,W], radii[V,P], n_touched[V,P] or None, ctx)."""
     L = _lib.lib()
     dev = means.device
@@ -111,6 +137,10 @@ def forward_raw(means, cov, opacities, viewmatrix, projmatrix, tanfov, backgroun
     M = shs.shape[2] if shs is not None else 1
 
     key = (S, P, V, W, H)
+    if _pending:
+        validate_pending()
+    if check == "deferred" and capacity is None and key not in _capacity_hint:
+        check = "sync"  # establish a capacity for this shape first
     cap = int(capacity) if capacity is not None else _capacity_hint.get(key, max(4 * P * V, 1 << 16))
     tensors = (means, cov, opacities, shs, colors_precomp, viewmatrix, projmatrix, projmatrix_raw, campos, tanfov,
                scales, background, view_set)
@@ -119,6 +149,13 @@ def forward_raw(means, cov, opacities, viewmatrix, projmatrix, tanfov, backgroun
         plan.launch()
         ctx = plan.ctx
         if check == "none":
+            break
+        if check == "deferred":
+            host = torch.empty(4, dtype=torch.int64).pin_memory()
+            host.copy_(ctx.view("status"), non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            _pending.append((ev, host, key))
             break
         st = ctx.status()
         if not st["overflow"]:
