@@ -184,6 +184,20 @@ int s3r_rope2d(void* tokens, const int64_t* pos, int32_t B, int32_t N, int32_t H
                int32_t dtype, void* stream);
 
 /* ------------------------------------------------------------------------
+ * Fused head epilogue -> Gaussians for one context view of a batch
+ * (encoder_noposplat_multi_token_style.py:178-251, postprocess.py:45-61,
+ * gaussian_adapter.py:122-153, gaussians.py:8-44).  Planar inputs pts_raw
+ * [B,3,HW], params [B,8,HW], app [B,3*d_sh,HW]; outputs are written at
+ * Gaussian index view*HW + pixel of the scene buffers means [B,G,3], cov
+ * [B,G,3,3], harmonics [B,G,3,d_sh], opacities [B,G] (scales [B,G,3] and
+ * rotations [B,G,4] optional).  exponent = 2^x of map_pdf_to_opacity.
+ * ------------------------------------------------------------------------ */
+int s3r_gaussian_adapter(const float* pts_raw, const float* params, const float* app, const float* sh_mask,
+                         int32_t B, int32_t HW, int32_t d_sh, int32_t view, int32_t G, float exponent,
+                         float* means, float* cov, float* harmonics, float* opacities, float* scales,
+                         float* rotations, void* stream);
+
+/* ------------------------------------------------------------------------
  * Pose update: w2c_out[i] = SE3_exp([rho_i, theta_i]) @ w2c_in[i] (row-major
  * 4x4, fp32).  Mirrors cam_utils.py:103-137 without the per-view host loop.
  * ------------------------------------------------------------------------ */

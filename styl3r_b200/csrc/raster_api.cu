@@ -70,8 +70,7 @@ static int validate(const s3r_raster_params* p) {
   if (p->cov_stride != 6 && p->cov_stride != 9) return S3R_ERR_INVALID_ARG;
   if (p->shs) {
     if (p->sh_degree < 0 || p->sh_degree > 3) return S3R_ERR_UNSUPPORTED;
-    if (p->sh_coeffs < (p->sh_degree + 1) * (p->sh_degree + 1) || p->sh_coeffs > S3R_MAX_SH_COEFFS)
-      return S3R_ERR_INVALID_ARG;
+    if (p->sh_coeffs < (p->sh_degree + 1) * (p->sh_degree + 1)) return S3R_ERR_INVALID_ARG;
     if (p->sh_degree > 0 && !p->campos) return S3R_ERR_INVALID_ARG;
   }
   if (!p->view_set && p->n_sets != p->n_views) return S3R_ERR_INVALID_ARG;

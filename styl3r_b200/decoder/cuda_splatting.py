@@ -126,7 +126,8 @@ def render_cuda(
     h, w = image_shape
     view_t, full, proj_t, campos, tan_fov, scale = camera_setup(extrinsics, intrinsics, near, far, scale_invariant)
     sh = gaussian_sh_coefficients
-    degree = isqrt(sh.shape[-1]) - 1
+    # like upstream, coefficients beyond degree 3 are stored but not evaluated (config default sh_degree 4)
+    degree = min(isqrt(sh.shape[-1]) - 1, 3)
     shs = _sh_layout(sh)
     kw = dict(shs=shs) if use_sh else dict(colors_precomp=shs[:, :, 0, :])
     color, depth, _, _, _ = _rz.rasterize(

@@ -1,0 +1,269 @@
+"""`EncoderNoPoSplatMultiTokenStyle` — the production Styl3R encoder (backbone `croco_multi` + token stylizer + DPT
+heads + unified Gaussian adapter) behind the reference's module surface
+(src/model/encoder/encoder_noposplat_multi_token_style.py:46-263, src/model/encoder/__init__.py:20-25):
+
+    encoder, _ = get_encoder(cfg)
+    gaussians  = encoder(context, style, global_step=0, visualization_dump=None)   # -> Gaussians
+
+with `context = {"image": [b,v,3,h,w] in [-1,1], "intrinsics": [b,v,3,3] normalised, ...}` and
+`style = {"image": [b,3,h,w]}`.  The parameter registry equals the reference's (SURVEY.md Appendix C;
+tests/golden/encoder_state_manifest.json), so `load_state_dict(strict=True)` works with existing checkpoints.
+
+B200 path: RoPE-2D (in place on the packed qkv) and the fused head-epilogue -> Gaussians kernel are ours; GEMMs,
+convolutions and the attention contraction are library calls in round 1 (DESIGN.md §7 lists the tcgen05 kernels as
+the next rows).  CUDA only — there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Any, List, Literal, Optional
+
+import torch
+from torch import Tensor, nn
+
+from .. import _lib
+from .dpt import PixelwiseDPT
+from .vit import CroCoTrunk
+
+
+@dataclass
+class Gaussians:  # src/model/types.py:7-12
+    means: Tensor         # [batch, gaussian, 3]
+    covariances: Tensor   # [batch, gaussian, 3, 3]
+    harmonics: Tensor     # [batch, gaussian, 3, d_sh]
+    opacities: Tensor     # [batch, gaussian]
+
+
+@dataclass
+class OpacityMappingCfg:
+    initial: float = 0.0
+    final: float = 0.0
+    warm_up: int = 1
+
+
+@dataclass
+class GaussianAdapterCfg:
+    gaussian_scale_min: float = 0.5
+    gaussian_scale_max: float = 15.0
+    sh_degree: int = 0
+
+
+@dataclass
+class BackboneCrocoCfg:
+    name: Literal["croco", "croco_multi"] = "croco_multi"
+    model: str = "ViTLarge_BaseDecoder"
+    patch_embed_cls: str = "PatchEmbedDust3R"
+    asymmetry_decoder: bool = True
+    intrinsics_embed_loc: str = "encoder"
+    intrinsics_embed_degree: int = 4
+    intrinsics_embed_type: str = "token"
+
+
+@dataclass
+class TokenStylizerCfg:
+    model: str = "ViTLarge_BaseDecoder"
+    patch_embed_cls: str = "PatchEmbedDust3R"
+    pretrained_weights: str = ""
+
+
+@dataclass
+class EncoderNoPoSplatTokenStyleCfg:
+    name: str = "noposplat_multi_token_style"
+    d_feature: int = 128
+    num_monocular_samples: int = 32
+    backbone: BackboneCrocoCfg = field(default_factory=BackboneCrocoCfg)
+    token_stylizer: TokenStylizerCfg = field(default_factory=TokenStylizerCfg)
+    structure_builder: Any = None
+    visualizer: Any = None
+    gaussian_adapter: GaussianAdapterCfg = field(default_factory=GaussianAdapterCfg)
+    apply_bounds_shim: bool = True
+    opacity_mapping: OpacityMappingCfg = field(default_factory=OpacityMappingCfg)
+    gaussians_per_pixel: int = 1
+    num_surfaces: int = 1
+    gs_params_head_type: str = "dpt_gs"
+    gs_sh_head_type: str = "dpt"
+    input_mean: tuple = (0.5, 0.5, 0.5)
+    input_std: tuple = (0.5, 0.5, 0.5)
+    pretrained_weights: str = ""
+    pose_free: bool = True
+    stylized: bool = False
+
+
+class AsymmetricCroCoMulti(CroCoTrunk):
+    """Backbone: shared ViT-L encoder over all context views (+ intrinsics token) and two cross-view decoders —
+    `dec_blocks` for view 0, `dec_blocks2` for views 1..v-1 (backbone_croco_multiview.py:51-227)."""
+
+    def __init__(self, cfg: BackboneCrocoCfg):
+        if cfg.model != "ViTLarge_BaseDecoder" or cfg.intrinsics_embed_loc != "encoder" or cfg.intrinsics_embed_type != "token":
+            raise NotImplementedError("production configuration only: ViTLarge_BaseDecoder + intrinsics token in the encoder")
+        super().__init__(second_decoder=cfg.asymmetry_decoder, intrinsics_token=True)
+        self.asymmetric = cfg.asymmetry_decoder
+
+    def load_state_dict(self, ckpt, **kw):
+        """Like the reference (…multiview.py:94-101): duplicate `dec_blocks` into `dec_blocks2` when absent."""
+        ckpt = dict(ckpt)
+        if self.asymmetric and not any(k.startswith("dec_blocks2") for k in ckpt):
+            for k, v in list(ckpt.items()):
+                if k.startswith("dec_blocks"):
+                    ckpt[k.replace("dec_blocks", "dec_blocks2")] = v
+        return super().load_state_dict(ckpt, **kw)
+
+    @staticmethod
+    def _others(x: Tensor) -> Tensor:
+        """[b,v,l,c] -> [b,v,(v-1)*l,c]: for every view the tokens of all *other* views, in view order."""
+        b, v, l, c = x.shape
+        idx = torch.tensor([[j for j in range(v) if j != i] for i in range(v)], device=x.device)  # [v, v-1]
+        return x[:, idx].reshape(b, v, (v - 1) * l, c)
+
+    def forward(self, context: dict):
+        img = context["image"]
+        b, v, _, h, w = img.shape
+        tok = self.intrinsic_encoder(context["intrinsics"].flatten(2)).reshape(b * v, 1, -1)
+        feat, pos = self.encode(img.reshape(b * v, *img.shape[2:]), tok)
+        feat, pos = feat.reshape(b, v, *feat.shape[1:]), pos.reshape(b, v, *pos.shape[1:])
+        outs = [feat]
+        cur = self.decoder_embed(feat)
+        pos_ctx = self._others(pos)
+        blocks2 = self.dec_blocks2 if self.asymmetric else self.dec_blocks
+        for blk1, blk2 in zip(self.dec_blocks, blocks2):
+            ctx = self._others(cur)
+            f1 = blk1(cur[:, 0], ctx[:, 0], pos[:, 0], pos_ctx[:, 0])
+            parts = [f1[:, None]]
+            if v > 1:
+                f2 = blk2(cur[:, 1:].reshape(b * (v - 1), *cur.shape[2:]), ctx[:, 1:].reshape(b * (v - 1), *ctx.shape[2:]),
+                          pos[:, 1:].reshape(b * (v - 1), *pos.shape[2:]), pos_ctx[:, 1:].reshape(b * (v - 1), *pos_ctx.shape[2:]))
+                parts.append(f2.reshape(b, v - 1, *f2.shape[1:]))
+            cur = torch.cat(parts, dim=1)
+            outs.append(cur)
+        outs[-1] = self.dec_norm(outs[-1])
+        dec_feat = [o[:, :, :-1] for o in outs]  # drop the intrinsics token
+        return feat, pos, dec_feat, (h, w), img
+
+
+class TokenStylizer(CroCoTrunk):
+    """Second ViT-L on the style image; 12 DecoderBlocks where all content tokens of a scene self-attend jointly and
+    cross-attend to the 256 style tokens (token_stylizer/token_stylizer.py:36-154)."""
+
+    def __init__(self, cfg: TokenStylizerCfg):
+        super().__init__(second_decoder=False, intrinsics_token=False)
+
+    def forward(self, style: dict, content_feat: Tensor, content_pos: Tensor) -> List[Tensor]:
+        b, v, l, _ = content_feat.shape
+        sfeat, spos = self.encode(style["image"])
+        outs = [content_feat]
+        x = self.decoder_embed(content_feat.reshape(b, v * l, -1))
+        xpos = content_pos.reshape(b, v * l, 2)
+        y = self.decoder_embed(sfeat)
+        for blk in self.dec_blocks:
+            x = blk(x, y, xpos, spos)
+            outs.append(x.reshape(b, v, l, -1))
+        outs[-1] = self.dec_norm(x).reshape(b, v, l, -1)
+        return [o[:, :, :-1] for o in outs]
+
+
+class UnifiedGaussianAdapter(nn.Module):
+    """Parameter-free; `sh_mask` is a non-persistent buffer as in the reference (gaussian_adapter.py:35-48)."""
+
+    def __init__(self, cfg: GaussianAdapterCfg):
+        super().__init__()
+        self.cfg = cfg
+        mask = torch.ones((self.d_sh,), dtype=torch.float32)
+        for degree in range(1, cfg.sh_degree + 1):
+            mask[degree ** 2:(degree + 1) ** 2] = 0.1 * 0.25 ** degree
+        self.register_buffer("sh_mask", mask, persistent=False)
+
+    @property
+    def d_sh(self) -> int:
+        return (self.cfg.sh_degree + 1) ** 2
+
+    @property
+    def d_in(self) -> int:
+        return 7 + 3 * self.d_sh
+
+
+class EncoderNoPoSplatMultiTokenStyle(nn.Module):
+    def __init__(self, cfg: EncoderNoPoSplatTokenStyleCfg):
+        super().__init__()
+        if not cfg.pose_free or cfg.gs_params_head_type != "dpt_gs" or cfg.num_surfaces != 1:
+            raise NotImplementedError("production configuration only: pose_free, dpt_gs heads, 1 surface")
+        self.cfg = cfg
+        self.backbone = AsymmetricCroCoMulti(cfg.backbone)
+        self.gaussian_adapter = UnifiedGaussianAdapter(cfg.gaussian_adapter)
+        self.pose_free = True
+        self.patch_size = self.backbone.patch_embed.patch_size[0]
+        d_sh = self.gaussian_adapter.d_sh
+        self.raw_gs_dim = 1 + self.gaussian_adapter.d_in
+        self.gs_params_head_type = cfg.gs_params_head_type
+        self.downstream_head1 = PixelwiseDPT("pts3d", 3)
+        self.downstream_head2 = PixelwiseDPT("pts3d", 3)
+        self.gaussian_param_head = PixelwiseDPT("gs_params", self.raw_gs_dim - 3 * d_sh)
+        self.gaussian_param_head2 = PixelwiseDPT("gs_params", self.raw_gs_dim - 3 * d_sh)
+        self.stylized = cfg.stylized
+        self.token_stylizer = TokenStylizer(cfg.token_stylizer)
+        self.gaussian_appearance_head = PixelwiseDPT("gs_sh", 3 * d_sh)
+
+    def opacity_exponent(self, global_step: int) -> float:
+        m = self.cfg.opacity_mapping
+        return 2.0 ** (m.initial + min(global_step / m.warm_up, 1) * (m.final - m.initial))
+
+    def forward(self, context: dict, style: dict, global_step: int = 0,
+                visualization_dump: Optional[dict] = None) -> Gaussians:
+        img = context["image"]
+        if img.device.type != "cuda":
+            raise _lib.S3RError("styl3r_b200 encoder needs CUDA tensors (no CPU fallback)")
+        b, v, _, h, w = img.shape
+        if w < h:
+            raise NotImplementedError("portrait inputs: transpose to landscape first (reference transpose_to_landscape)")
+        enc_feat, enc_pos, dec_feat, shape, images = self.backbone(context)
+        sty_feat = self.token_stylizer(style, enc_feat, enc_pos)
+        HW, G, d_sh = h * w, v * h * w, self.gaussian_adapter.d_sh
+        dev = img.device
+        means = torch.empty(b, G, 3, device=dev)
+        cov = torch.empty(b, G, 3, 3, device=dev)
+        harm = torch.empty(b, G, 3, d_sh, device=dev)
+        opac = torch.empty(b, G, device=dev)
+        scales = torch.empty(b, G, 3, device=dev) if visualization_dump is not None else None
+        rots = torch.empty(b, G, 4, device=dev) if visualization_dump is not None else None
+        L = _lib.lib()
+        p = lambda t: None if t is None else C.c_void_p(t.data_ptr())
+        with torch.autocast("cuda", enabled=False):
+            for i in range(v):
+                toks = [t[:, i].float() for t in dec_feat]
+                pts_raw = (self.downstream_head1 if i == 0 else self.downstream_head2)(toks, shape).contiguous()
+                prm = (self.gaussian_param_head if i == 0 else self.gaussian_param_head2)(
+                    toks, shape, images[:, i, :3].float()).contiguous()
+                app = self.gaussian_appearance_head([t[:, i].float() for t in sty_feat], shape).contiguous()
+                _lib.check(L.s3r_gaussian_adapter(p(pts_raw), p(prm), p(app), p(self.gaussian_adapter.sh_mask), b, HW, d_sh,
+                                                  i, G, float(self.opacity_exponent(global_step)), p(means), p(cov),
+                                                  p(harm), p(opac), p(scales), p(rots),
+                                                  C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)),
+                           "s3r_gaussian_adapter")
+        if visualization_dump is not None:  # keys consumed by export_ply (infer_model_re10k.py:542-557)
+            visualization_dump["depth"] = means[..., 2].reshape(b, v, h, w, 1, 1)
+            visualization_dump["scales"] = scales
+            visualization_dump["rotations"] = rots
+            visualization_dump["means"] = means.reshape(b, v, h, w, 1, 3)
+            visualization_dump["opacities"] = opac.reshape(b, v, h, w, 1, 1)
+        return Gaussians(means, cov, harm, opac)
+
+    def get_data_shim(self):
+        mean, std = self.cfg.input_mean, self.cfg.input_std
+
+        def data_shim(batch):
+            """apply_normalize_shim (src/dataset/shims/normalize_shim.py:21-27): context images -> (x - mean) / std."""
+            ctx = dict(batch["context"])
+            m = torch.tensor(mean, device=ctx["image"].device).view(1, 1, 3, 1, 1)
+            s = torch.tensor(std, device=ctx["image"].device).view(1, 1, 3, 1, 1)
+            ctx["image"] = (ctx["image"] - m) / s
+            return {**batch, "context": ctx}
+
+        return data_shim
+
+
+ENCODERS = {"noposplat_multi_token_style": (EncoderNoPoSplatMultiTokenStyle, None)}
+
+
+def get_encoder(cfg):
+    encoder, visualizer = ENCODERS[cfg.name]
+    return encoder(cfg), visualizer

@@ -1,0 +1,171 @@
+"""Transformer pieces of the CroCo / MASt3R ViT used by Styl3R, with the reference's parameter registry
+ so that checkpoints load strictly:
+
+  Block           norm1, attn.{qkv, proj}, norm2, mlp.{fc1, fc2}                 croco/blocks.py:136-152
+  DecoderBlock    + cross_attn.{projq, projk, projv, proj}, norm3, norm_y          croco/blocks.py:202-222
+  PatchEmbed      proj (Conv2d k16 s16), integer (y, x) positions                  croco/patch_embed.py:19-29
+
+Differences from the reference implementation (results are the same): RoPE is applied in place on the q / k
+slices of the packed qkv tensor by our CUDA kernel (no transposes / copies), attention goes through
+styl3r_b200.ops.memory_efficient_attention, and the context K/V projections are computed once per layer.
+"""
+from __future__ import annotations
+
+import torch
+from torch import Tensor, nn
+
+from ..curope import cuRoPE2D_func
+from ..ops import memory_efficient_attention
+
+LN_EPS = 1e-6  # croco.py:34
+
+
+def _rope(t_bnhd: Tensor, pos: Tensor, base: float) -> Tensor:
+    """In-place RoPE-2D on a [B,N,H,D] (possibly strided) tensor."""
+    return cuRoPE2D_func.apply(t_bnhd, pos, base, 1.0)
+
+
+class Mlp(nn.Module):
+    def __init__(self, dim: int, hidden: int):
+        super().__init__()
+        self.fc1 = nn.Linear(dim, hidden)
+        self.act = nn.GELU()
+        self.fc2 = nn.Linear(hidden, dim)
+
+    def forward(self, x: Tensor) -> Tensor:
+        return self.fc2(self.act(self.fc1(x)))
+
+
+class Attention(nn.Module):
+    def __init__(self, dim: int, num_heads: int, rope_base: float):
+        super().__init__()
+        self.num_heads, self.scale, self.rope_base = num_heads, (dim // num_heads) ** -0.5, rope_base
+        self.qkv = nn.Linear(dim, dim * 3, bias=True)
+        self.proj = nn.Linear(dim, dim)
+
+    def forward(self, x: Tensor, xpos: Tensor) -> Tensor:
+        B, N, C = x.shape
+        qkv = self.qkv(x).view(B, N, 3, self.num_heads, C // self.num_heads)
+        q, k, v = qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2]          # [B,N,H,D] views, stride(2) == D
+        q, k = _rope(q, xpos, self.rope_base), _rope(k, xpos, self.rope_base)
+        o = memory_efficient_attention(q, k, v, scale=self.scale)
+        return self.proj(o.reshape(B, N, C))
+
+
+class CrossAttention(nn.Module):
+    def __init__(self, dim: int, num_heads: int, rope_base: float):
+        super().__init__()
+        self.num_heads, self.scale, self.rope_base = num_heads, (dim // num_heads) ** -0.5, rope_base
+        self.projq = nn.Linear(dim, dim, bias=True)
+        self.projk = nn.Linear(dim, dim, bias=True)
+        self.projv = nn.Linear(dim, dim, bias=True)
+        self.proj = nn.Linear(dim, dim)
+
+    def forward(self, query: Tensor, key: Tensor, value: Tensor, qpos: Tensor, kpos: Tensor) -> Tensor:
+        B, Nq, C = query.shape
+        H, D = self.num_heads, C // self.num_heads
+        q = _rope(self.projq(query).view(B, Nq, H, D), qpos, self.rope_base)
+        k = _rope(self.projk(key).view(B, key.shape[1], H, D), kpos, self.rope_base)
+        v = self.projv(value).view(B, value.shape[1], H, D)
+        o = memory_efficient_attention(q, k, v, scale=self.scale)
+        return self.proj(o.reshape(B, Nq, C))
+
+
+class Block(nn.Module):
+    def __init__(self, dim: int, num_heads: int, rope_base: float, mlp_ratio: float = 4.0):
+        super().__init__()
+        self.norm1 = nn.LayerNorm(dim, eps=LN_EPS)
+        self.attn = Attention(dim, num_heads, rope_base)
+        self.norm2 = nn.LayerNorm(dim, eps=LN_EPS)
+        self.mlp = Mlp(dim, int(dim * mlp_ratio))
+
+    def forward(self, x: Tensor, xpos: Tensor) -> Tensor:
+        x = x + self.attn(self.norm1(x), xpos)
+        return x + self.mlp(self.norm2(x))
+
+
+class DecoderBlock(nn.Module):
+    def __init__(self, dim: int, num_heads: int, rope_base: float, mlp_ratio: float = 4.0):
+        super().__init__()
+        self.norm1 = nn.LayerNorm(dim, eps=LN_EPS)
+        self.attn = Attention(dim, num_heads, rope_base)
+        self.cross_attn = CrossAttention(dim, num_heads, rope_base)
+        self.norm2 = nn.LayerNorm(dim, eps=LN_EPS)
+        self.norm3 = nn.LayerNorm(dim, eps=LN_EPS)
+        self.mlp = Mlp(dim, int(dim * mlp_ratio))
+        self.norm_y = nn.LayerNorm(dim, eps=LN_EPS)
+
+    def forward(self, x: Tensor, y: Tensor, xpos: Tensor, ypos: Tensor) -> Tensor:
+        x = x + self.attn(self.norm1(x), xpos)
+        y_ = self.norm_y(y)
+        x = x + self.cross_attn(self.norm2(x), y_, y_, xpos, ypos)
+        return x + self.mlp(self.norm3(x))
+
+
+class PatchEmbed(nn.Module):
+    """Conv2d(3 -> dim, k = s = patch) + flatten; positions are the integer (y, x) patch coordinates."""
+
+    def __init__(self, patch_size: int, in_chans: int, dim: int):
+        super().__init__()
+        self.patch_size = (patch_size, patch_size)
+        self.proj = nn.Conv2d(in_chans, dim, kernel_size=patch_size, stride=patch_size)
+
+    def forward(self, img: Tensor):
+        B, _, H, W = img.shape
+        ph, pw = self.patch_size
+        assert H % ph == 0, f"Input image height ({H}) is not a multiple of patch size ({ph})."
+        assert W % pw == 0, f"Input image width ({W}) is not a multiple of patch size ({pw})."
+        x = self.proj(img)
+        gh, gw = x.shape[2], x.shape[3]
+        ys, xs = torch.meshgrid(torch.arange(gh, device=img.device), torch.arange(gw, device=img.device), indexing="ij")
+        pos = torch.stack((ys.reshape(-1), xs.reshape(-1)), dim=-1)[None].expand(B, -1, -1).contiguous()
+        return x.flatten(2).transpose(1, 2), pos
+
+
+class CroCoTrunk(nn.Module):
+    """ViT-L/16 encoder (24 x 1024 x 16 heads) + decoder_embed + 12 x 768 x 12-head DecoderBlocks, RoPE base 100
+    (`croco_params['ViTLarge_BaseDecoder']`, backbone_croco_multiview.py:21-32; croco.py:21-84).  Holds exactly the
+    parameters of the reference's CroCoNet subclasses, including the unused `mask_token`."""
+
+    enc_depth, dec_depth, enc_embed_dim, dec_embed_dim, enc_heads, dec_heads, rope_base = 24, 12, 1024, 768, 16, 12, 100.0
+
+    def __init__(self, second_decoder: bool, intrinsics_token: bool):
+        super().__init__()
+        E, Dd = self.enc_embed_dim, self.dec_embed_dim
+        self.patch_embed = PatchEmbed(16, 3, E)
+        self.enc_blocks = nn.ModuleList([Block(E, self.enc_heads, self.rope_base) for _ in range(self.enc_depth)])
+        self.enc_norm = nn.LayerNorm(E, eps=LN_EPS)
+        self.mask_token = nn.Parameter(torch.zeros(1, 1, Dd))
+        self.decoder_embed = nn.Linear(E, Dd, bias=True)
+        self.dec_blocks = nn.ModuleList([DecoderBlock(Dd, self.dec_heads, self.rope_base) for _ in range(self.dec_depth)])
+        self.dec_norm = nn.LayerNorm(Dd, eps=LN_EPS)
+        if second_decoder:
+            self.dec_blocks2 = nn.ModuleList([DecoderBlock(Dd, self.dec_heads, self.rope_base) for _ in range(self.dec_depth)])
+        if intrinsics_token:
+            self.intrinsic_encoder = nn.Linear(9, E)
+        self._init_weights()
+
+    def _init_weights(self):
+        # croco.py:112-127: xavier-uniform linears, unit LayerNorms, N(0, .02) mask token, xavier patch projection
+        w = self.patch_embed.proj.weight.data
+        nn.init.xavier_uniform_(w.view(w.shape[0], -1))
+        nn.init.normal_(self.mask_token, std=0.02)
+        for m in self.modules():
+            if isinstance(m, nn.Linear):
+                nn.init.xavier_uniform_(m.weight)
+                if m.bias is not None:
+                    nn.init.constant_(m.bias, 0)
+            elif isinstance(m, nn.LayerNorm):
+                nn.init.constant_(m.bias, 0)
+                nn.init.constant_(m.weight, 1.0)
+
+    def encode(self, img: Tensor, extra_token: Tensor | None = None):
+        x, pos = self.patch_embed(img)
+        if extra_token is not None:  # intrinsics token appended at position (grid_h, 0)  (…multiview.py:131-135)
+            x = torch.cat((x, extra_token), dim=1)
+            tok_pos = pos[:, :1].clone()
+            tok_pos[:, :, 0] += pos[:, -1:, 0] + 1
+            pos = torch.cat((pos, tok_pos), dim=1)
+        for blk in self.enc_blocks:
+            x = blk(x, pos)
+        return self.enc_norm(x), pos

@@ -98,3 +98,18 @@ def test_decoder_surface():
     d = get_decoder(DecoderSplattingCUDACfg("splatting_cuda", [0.0, 0.0, 0.0], True))
     assert isinstance(d, DecoderSplattingCUDA) and d.make_scale_invariant
     assert "background_color" not in d.state_dict()  # non-persistent, like the reference
+
+
+def test_encoder_state_dict_matches_reference_manifest():
+    """Checkpoint contract: same keys, order and shapes as the reference encoder's state_dict
+    (tests/golden/encoder_state_manifest.json, dumped from the reference by make_encoder_golden.py)."""
+    import json
+    from styl3r_b200.encoder import EncoderNoPoSplatTokenStyleCfg, get_encoder
+    with torch.device("meta"):
+        enc, vis = get_encoder(EncoderNoPoSplatTokenStyleCfg())
+    assert vis is None
+    mine = {k: list(v.shape) for k, v in enc.state_dict().items()}
+    ref = json.loads((ROOT / "tests" / "golden" / "encoder_state_manifest.json").read_text())
+    assert list(mine) == list(ref)
+    assert mine == ref
+    assert enc.stylized is False and enc.backbone.patch_embed.patch_size == (16, 16) and enc.gaussian_adapter.d_sh == 1

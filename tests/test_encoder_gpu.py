@@ -1,0 +1,67 @@
+"""GPU parity: our encoder (styl3r_b200.encoder) vs golden vectors produced by the REFERENCE encoder on CPU
+(tests/golden/make_encoder_golden.py).  Both models get the same name-derived weights and seeded inputs.
+Tolerance (fp32 on both sides, ~60 layers, different GEMM/conv reduction orders; `means` amplify head error through
+expm1): max |err| <= 2e-3 * scale and mean |err| <= 2e-4 * scale, scale = the golden tensor's std."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+GOLD = Path(__file__).parent / "golden"
+
+
+def sample(t, n=4096):
+    import torch
+    f = t.detach().reshape(-1)
+    idx = torch.linspace(0, f.numel() - 1, min(n, f.numel())).long().to(f.device)
+    return f[idx].float().cpu().numpy()
+
+
+@pytest.fixture(scope="module")
+def encoder():
+    import torch
+    from styl3r_b200.encoder import EncoderNoPoSplatTokenStyleCfg, get_encoder
+    from tests.encoder_weights import fill_named_weights
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    enc, _ = get_encoder(EncoderNoPoSplatTokenStyleCfg(stylized=True))
+    fill_named_weights(enc)
+    return enc.cuda().eval()
+
+
+@pytest.mark.parametrize("tag,b,v", [("b1v2", 1, 2), ("b1v3", 1, 3)])
+def test_encoder_matches_reference_golden(encoder, tag, b, v):
+    import torch
+    from tests.encoder_weights import make_inputs
+    g = np.load(GOLD / "encoder_golden.npz")
+    context, style = make_inputs(b, v, 256, seed=1234, device="cuda")
+    dump = {}
+    with torch.no_grad():
+        out = encoder(context, style, visualization_dump=dump)
+    assert out.means.shape == (b, v * 65536, 3) and out.covariances.shape == (b, v * 65536, 3, 3)
+    assert out.harmonics.shape == (b, v * 65536, 3, 1) and out.opacities.shape == (b, v * 65536)
+    for name, t in [("means", out.means), ("covariances", out.covariances), ("harmonics", out.harmonics),
+                    ("opacities", out.opacities), ("scales", dump["scales"]), ("rotations", dump["rotations"])]:
+        ref, scale = g[f"{tag}_{name}"], float(g[f"{tag}_{name}_stats"][2])
+        err = np.abs(sample(t) - ref)
+        assert err.max() <= 2e-3 * scale and err.mean() <= 2e-4 * scale, \
+            f"{tag} {name}: max {err.max():.3e} mean {err.mean():.3e} scale {scale:.3e}"
+
+
+def test_encoder_feeds_decoder(encoder):
+    """Encoder -> DecoderSplattingCUDA end to end (BASELINE cfg2 shapes), strict state-dict round trip."""
+    import torch
+    from styl3r_b200 import synthetic as syn
+    from styl3r_b200.decoder import DecoderSplattingCUDA, DecoderSplattingCUDACfg
+    from tests.encoder_weights import make_inputs
+    context, style = make_inputs(1, 2, 256, seed=7, device="cuda")
+    with torch.no_grad():
+        g = encoder(context, style)
+        sc = syn.make_scene(seed=1, v=2, V=1, hw=256)
+        t = lambda a: torch.as_tensor(a).cuda()[None]
+        dec = DecoderSplattingCUDA(DecoderSplattingCUDACfg("splatting_cuda", [0.0, 0.0, 0.0], True)).cuda()
+        out = dec(g, t(sc["extrinsics"]), t(sc["intrinsics"]), t(sc["near"]), t(sc["far"]), (256, 256))
+    assert out.color.shape == (1, 1, 3, 256, 256) and torch.isfinite(out.color).all()
+    sd = encoder.state_dict()
+    encoder.load_state_dict(sd, strict=True)
