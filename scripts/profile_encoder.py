@@ -1,0 +1,26 @@
+import sys
+from pathlib import Path
+sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+import torch
+from torch.profiler import profile, ProfilerActivity
+from styl3r_b200.encoder import EncoderNoPoSplatTokenStyleCfg, get_encoder
+from tests.encoder_weights import make_inputs
+mode = sys.argv[1] if len(sys.argv) > 1 else "bf16"
+enc, _ = get_encoder(EncoderNoPoSplatTokenStyleCfg(stylized=True)); enc = enc.cuda().eval()
+torch.backends.cuda.matmul.allow_tf32 = True; torch.backends.cudnn.allow_tf32 = True
+if mode == "inf":
+    enc.to_inference(torch.bfloat16)
+context, style = make_inputs(1, 2, 256, seed=1, device="cuda")
+def step():
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=(mode == "bf16")):
+        return enc(context, style)
+for _ in range(2): step()
+torch.cuda.synchronize()
+with profile(activities=[ProfilerActivity.CUDA]) as prof:
+    step(); torch.cuda.synchronize()
+ev = prof.key_averages()
+rows = sorted(ev, key=lambda e: -e.device_time_total)[:28]
+tot = sum(e.device_time_total for e in ev)
+print(f"total device time {tot/1000:.2f} ms")
+for e in rows:
+    print(f"{e.device_time_total/1000:8.3f} ms {100*e.device_time_total/tot:5.1f}% n={e.count:4d}  {e.key[:110]}")

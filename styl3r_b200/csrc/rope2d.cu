@@ -4,8 +4,9 @@
 // position, [D/2, D) with the x position; inside a half the pairs are (d, d + D/4) and the angle is
 // pos * fwd * base^(-d/(D/4)).  fwd = -1 applies the inverse rotation (= the backward pass).
 //
-// One thread owns VEC consecutive pair-lanes of one token-half and loops over the heads, so sin/cos are
-// computed once per (token, d) instead of once per head, and every access is a 16-byte vector.
+// One thread owns VEC consecutive pair-lanes of one token-half and a slice of `hpt` heads (blockIdx.y), so
+// sin/cos are shared by the heads of the slice and every access is a 16-byte vector; the head slices keep
+// the grid large enough (>= ~64k threads) for the 257..4112-token shapes of the ViT.
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
@@ -32,7 +33,8 @@ struct alignas(sizeof(T) * VEC) Pack { T v[VEC]; };
 template <typename T, int VEC>
 __global__ void __launch_bounds__(256) s3r_rope2d_kernel(T* __restrict__ tok, const long long* __restrict__ pos,
                                                         long long n_tokens, int N, int H, int Q, long long stride_b,
-                                                        long long stride_n, long long stride_h, float base, float fwd) {
+                                                        long long stride_n, long long stride_h, float base, float fwd,
+                                                        int hpt) {
   const int gph = Q / VEC;  // groups per half
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long token = gid / (2 * gph);
@@ -50,7 +52,9 @@ __global__ void __launch_bounds__(256) s3r_rope2d_kernel(T* __restrict__ tok, co
   }
   T* t0 = tok + b * stride_b + n * stride_n + (long long)half * 2 * Q + (long long)grp * VEC;
   using P = Pack<T, VEC>;
-  for (int h = 0; h < H; h++) {
+  const int h0 = blockIdx.y * hpt, h1 = min(H, h0 + hpt);
+#pragma unroll 2
+  for (int h = h0; h < h1; h++) {
     T* th = t0 + (long long)h * stride_h;
     P u = *reinterpret_cast<const P*>(th);
     P v = *reinterpret_cast<const P*>(th + Q);
@@ -73,8 +77,11 @@ static int launch(void* tokens, const int64_t* pos, int B, int N, int H, int Q, 
   const long long threads = n_tokens * 2 * (Q / VEC);
   const int block = 256;
   const long long grid = (threads + block - 1) / block;
-  s3r_rope2d_kernel<T, VEC><<<(unsigned)grid, block, 0, st>>>((T*)tokens, (const long long*)pos, n_tokens, N, H, Q, sb,
-                                                              sn, sh, base, fwd);
+  int hpt = H;  // heads per thread: shrink until the grid has >= 64k threads (or one head per thread)
+  while (hpt > 1 && threads * ((H + hpt - 1) / hpt) < 65536) hpt = (hpt + 1) / 2;
+  dim3 g((unsigned)grid, (unsigned)((H + hpt - 1) / hpt));
+  s3r_rope2d_kernel<T, VEC><<<g, block, 0, st>>>((T*)tokens, (const long long*)pos, n_tokens, N, H, Q, sb, sn, sh, base,
+                                                 fwd, hpt);
   S3R_CUDA_CHECK(cudaGetLastError());
   return S3R_OK;
 }

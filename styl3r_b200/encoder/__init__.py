@@ -1,2 +1,2 @@
 from .encoder import (BackboneCrocoCfg, EncoderNoPoSplatMultiTokenStyle, EncoderNoPoSplatTokenStyleCfg,  # noqa: F401
-                      GaussianAdapterCfg, Gaussians, OpacityMappingCfg, TokenStylizerCfg, get_encoder)
+                      GaussianAdapterCfg, Gaussians, GraphedEncoder, OpacityMappingCfg, TokenStylizerCfg, get_encoder)

@@ -93,7 +93,8 @@ class DPTAdapter(nn.Module):
         feats = []
         for i, hook in enumerate(HOOKS):
             t = tokens[hook]
-            x = t.transpose(1, 2).reshape(t.shape[0], t.shape[2], nh, nw)
+            # [B, nh*nw, C] tokens viewed as NCHW are already a channels_last tensor: no copy
+            x = t.contiguous().view(t.shape[0], nh, nw, t.shape[2]).permute(0, 3, 1, 2)
             feats.append(self.scratch.layer_rn[i](self.act_postprocess[i](x)))
         p = self.scratch.refinenet4(feats[3])[:, :, :feats[2].shape[2], :feats[2].shape[3]]
         p = self.scratch.refinenet3(p, feats[2])

@@ -109,12 +109,16 @@ class AsymmetricCroCoMulti(CroCoTrunk):
                     ckpt[k.replace("dec_blocks", "dec_blocks2")] = v
         return super().load_state_dict(ckpt, **kw)
 
-    @staticmethod
-    def _others(x: Tensor) -> Tensor:
+    _others_idx: dict = {}
+
+    @classmethod
+    def _others(cls, x: Tensor) -> Tensor:
         """[b,v,l,c] -> [b,v,(v-1)*l,c]: for every view the tokens of all *other* views, in view order."""
         b, v, l, c = x.shape
-        idx = torch.tensor([[j for j in range(v) if j != i] for i in range(v)], device=x.device)  # [v, v-1]
-        return x[:, idx].reshape(b, v, (v - 1) * l, c)
+        key = (v, x.device)
+        if key not in cls._others_idx:  # built once per (v, device): no host->device copy inside a CUDA-graph capture
+            cls._others_idx[key] = torch.tensor([[j for j in range(v) if j != i] for i in range(v)], device=x.device)
+        return x[:, cls._others_idx[key]].reshape(b, v, (v - 1) * l, c)
 
     def forward(self, context: dict):
         img = context["image"]
@@ -203,6 +207,18 @@ class EncoderNoPoSplatMultiTokenStyle(nn.Module):
         self.token_stylizer = TokenStylizer(cfg.token_stylizer)
         self.gaussian_appearance_head = PixelwiseDPT("gs_sh", 3 * d_sh)
 
+    def to_inference(self, vit_dtype: torch.dtype = torch.bfloat16):
+        """Inference layout for B200: ViT trunks (backbone, token stylizer) hold `vit_dtype` weights (bf16 operands,
+        fp32 accumulation in the GEMMs / attention; no per-call autocast weight casts), DPT heads stay fp32 (TF32
+        convolutions — the reference disables autocast there, encoder…style.py:150) in channels_last so cuDNN runs
+        NHWC kernels without layout transposes.  Checkpoints still load strictly (load_state_dict casts)."""
+        self.backbone.to(vit_dtype)
+        self.token_stylizer.to(vit_dtype)
+        for head in (self.downstream_head1, self.downstream_head2, self.gaussian_param_head, self.gaussian_param_head2,
+                     self.gaussian_appearance_head):
+            head.to(memory_format=torch.channels_last)
+        return self
+
     def opacity_exponent(self, global_step: int) -> float:
         m = self.cfg.opacity_mapping
         return 2.0 ** (m.initial + min(global_step / m.warm_up, 1) * (m.final - m.initial))
@@ -215,6 +231,10 @@ class EncoderNoPoSplatMultiTokenStyle(nn.Module):
         b, v, _, h, w = img.shape
         if w < h:
             raise NotImplementedError("portrait inputs: transpose to landscape first (reference transpose_to_landscape)")
+        vit_dtype = self.backbone.patch_embed.proj.weight.dtype
+        if img.dtype != vit_dtype:  # to_inference(): bf16 trunks
+            context = {**context, "image": img.to(vit_dtype), "intrinsics": context["intrinsics"].to(vit_dtype)}
+            style = {**style, "image": style["image"].to(vit_dtype)}
         enc_feat, enc_pos, dec_feat, shape, images = self.backbone(context)
         sty_feat = self.token_stylizer(style, enc_feat, enc_pos)
         HW, G, d_sh = h * w, v * h * w, self.gaussian_adapter.d_sh
@@ -232,7 +252,7 @@ class EncoderNoPoSplatMultiTokenStyle(nn.Module):
                 toks = [t[:, i].float() for t in dec_feat]
                 pts_raw = (self.downstream_head1 if i == 0 else self.downstream_head2)(toks, shape).contiguous()
                 prm = (self.gaussian_param_head if i == 0 else self.gaussian_param_head2)(
-                    toks, shape, images[:, i, :3].float()).contiguous()
+                    toks, shape, img[:, i, :3].float()).contiguous()
                 app = self.gaussian_appearance_head([t[:, i].float() for t in sty_feat], shape).contiguous()
                 _lib.check(L.s3r_gaussian_adapter(p(pts_raw), p(prm), p(app), p(self.gaussian_adapter.sh_mask), b, HW, d_sh,
                                                   i, G, float(self.opacity_exponent(global_step)), p(means), p(cov),
@@ -259,6 +279,51 @@ class EncoderNoPoSplatMultiTokenStyle(nn.Module):
             return {**batch, "context": ctx}
 
         return data_shim
+
+
+class GraphedEncoder:
+    """CUDA-graph replay of `encoder(context, style)` for inference: the ~3000 small launches of one forward
+    (84 self- and 36 cross-attention modules, 5 DPT pyramids per view) are captured once per input shape and
+    replayed with a single launch, which removes the Python / launch overhead that dominates at b=1.
+
+        fast = GraphedEncoder(encoder, autocast_dtype=torch.bfloat16)
+        gaussians = fast(context, style)           # tensors are copied into static buffers, outputs are static
+
+    Outputs are views of static buffers: they are overwritten by the next call with the same shape."""
+
+    def __init__(self, encoder: EncoderNoPoSplatMultiTokenStyle, autocast_dtype: Optional[torch.dtype] = None,
+                 global_step: int = 0):
+        self.encoder, self.autocast_dtype, self.global_step = encoder, autocast_dtype, global_step
+        self._graphs: dict = {}
+
+    def _run(self, context, style):
+        with torch.no_grad(), torch.autocast("cuda", dtype=self.autocast_dtype or torch.bfloat16,
+                                            enabled=self.autocast_dtype is not None):
+            return self.encoder(context, style, self.global_step)
+
+    def __call__(self, context: dict, style: dict) -> Gaussians:
+        img, K, sty = context["image"], context["intrinsics"], style["image"]
+        key = (tuple(img.shape), tuple(sty.shape), img.device)
+        if key not in self._graphs:
+            static = dict(img=img.clone(), K=K.clone(), sty=sty.clone())
+            ctx, st = {"image": static["img"], "intrinsics": static["K"]}, {"image": static["sty"]}
+            side = torch.cuda.Stream(device=img.device)
+            side.wait_stream(torch.cuda.current_stream(img.device))
+            with torch.cuda.stream(side):
+                for _ in range(2):  # warm-up outside capture: lazy inits, cuDNN/cuBLAS plan selection, index caches
+                    self._run(ctx, st)
+            torch.cuda.current_stream(img.device).wait_stream(side)
+            torch.cuda.synchronize(img.device)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                out = self._run(ctx, st)
+            self._graphs[key] = (graph, static, out)
+        graph, static, out = self._graphs[key]
+        static["img"].copy_(img, non_blocking=True)
+        static["K"].copy_(K, non_blocking=True)
+        static["sty"].copy_(sty, non_blocking=True)
+        graph.replay()
+        return out
 
 
 ENCODERS = {"noposplat_multi_token_style": (EncoderNoPoSplatMultiTokenStyle, None)}

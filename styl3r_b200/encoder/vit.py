@@ -22,7 +22,7 @@ LN_EPS = 1e-6  # croco.py:34
 
 def _rope(t_bnhd: Tensor, pos: Tensor, base: float) -> Tensor:
     """In-place RoPE-2D on a [B,N,H,D] (possibly strided) tensor."""
-    return cuRoPE2D_func.apply(t_bnhd, pos, base, 1.0)
+    return cuRoPE2D_func.apply(t_bnhd, pos if pos.is_contiguous() else pos.contiguous(), base, 1.0)
 
 
 class Mlp(nn.Module):
