@@ -184,6 +184,22 @@ int s3r_rope2d(void* tokens, const int64_t* pos, int32_t B, int32_t N, int32_t H
                int32_t dtype, void* stream);
 
 /* ------------------------------------------------------------------------
+ * bf16 GEMM with fused epilogue on tcgen05/TMEM (the encoder's nn.Linear:
+ * croco/blocks.py:70-73,91-93,162-166):
+ *   C[M,N] = act(A[M,K] . W[N,K]^T + bias[N]) + residual[M,N]
+ * A, W, bias, residual bf16 (row pitches lda/ldw/ldr in elements), C bf16 or
+ * fp32 (S3R_EPI_OUT_F32), fp32 accumulation.  flags: S3R_EPI_*.
+ * Requires K, lda, ldw, ldc, ldr multiples of 8 and 16-byte aligned pointers.
+ * ------------------------------------------------------------------------ */
+#define S3R_EPI_BIAS 1
+#define S3R_EPI_GELU 2
+#define S3R_EPI_RESIDUAL 4
+#define S3R_EPI_OUT_F32 8
+int s3r_gemm_bf16(const void* A, const void* W, const void* bias, const void* residual, void* C, int32_t M,
+                  int32_t N, int32_t K, int32_t lda, int32_t ldw, int32_t ldc, int32_t ldr, int32_t flags,
+                  void* stream);
+
+/* ------------------------------------------------------------------------
  * Fused head epilogue -> Gaussians for one context view of a batch
  * (encoder_noposplat_multi_token_style.py:178-251, postprocess.py:45-61,
  * gaussian_adapter.py:122-153, gaussians.py:8-44).  Planar inputs pts_raw

@@ -1,0 +1,320 @@
+// bf16 GEMM with fused epilogue on the 5th-generation tensor cores (tcgen05 + TMEM + TMA), sm_100a.
+//
+//   C[M,N] = act( A[M,K] . W[N,K]^T + bias[N] ) + residual[M,N]        (bf16 operands, fp32 accumulation in TMEM)
+//
+// This is the dense-contraction kernel behind the encoder's nn.Linear layers (qkv / proj / fc1(+GELU) / fc2 /
+// projq,k,v / decoder_embed: src/model/encoder/backbone/croco/blocks.py:70-73,91-93,162-166), where the reference
+// calls cuBLAS through torch (TF32).  Both operands are K-major (row-major activations, row-major [out,in] weights),
+// i.e. the "TN" GEMM.
+//
+// Structure (one 128 x BN output tile per CTA, 6 warps, warp-specialised):
+//   warp 0   TMA producer: cp.async.bulk.tensor.2d of a 128x64 A tile and a BNx64 W tile per k-block into a 4-stage
+//            SWIZZLE_128B shared-memory ring, completion on `full` mbarriers (expect_tx)
+//   warp 1   allocates BN TMEM columns; one elected lane issues 4 x tcgen05.mma (M=128, N=BN, K=16) per k-block from
+//            shared-memory matrix descriptors, releases ring slots with tcgen05.commit -> `empty` mbarriers and signals
+//            the epilogue with a final commit
+//   warps 2-5 epilogue: tcgen05.ld (32 lanes x 32 columns per instruction) TMEM -> registers, + bias, exact GELU,
+//            + residual, -> bf16 (or fp32), 16-byte global stores
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "s3r_common.cuh"
+
+#define GEMM_BM 128
+#define GEMM_BK 64
+#define GEMM_STAGES 4
+#define GEMM_THREADS 192
+
+__device__ __forceinline__ uint32_t g_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void g_mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(g_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void g_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(g_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void g_mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(g_smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void g_tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+          g_smem_u32(dst)),
+      "l"(map), "r"(c0), "r"(c1), "r"(g_smem_u32(bar))
+      : "memory");
+}
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+//   [0,14) start>>4 | [16,30) LBO>>4 = 1 | [32,46) SBO>>4 = 1024>>4 | [46,48) version = 1 | [61,64) layout = 2 (SW128)
+__device__ __forceinline__ uint64_t g_make_desc(const void* smem_ptr) {
+  const uint32_t addr = g_smem_u32(smem_ptr);
+  uint64_t d = 0;
+  d |= (uint64_t)((addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// kind::f16 instruction descriptor: c=F32 (1<<4), a=b=BF16 (1<<7, 1<<10), both K-major, N>>3 at [17,23), M>>4 at [24,29)
+__device__ __forceinline__ uint32_t g_make_idesc(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+__device__ __forceinline__ void g_umma(uint32_t tmem_c, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_c),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void g_umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(g_smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void g_tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, "
+      "%24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+template <int BN>
+struct GemmSmem {
+  static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
+  static constexpr int B_BYTES = BN * GEMM_BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int TOTAL = GEMM_STAGES * STAGE_BYTES + 256 + 1024;  // + barriers + alignment slack
+};
+
+template <int BN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+s3r_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                     const __nv_bfloat16* __restrict__ bias, const __nv_bfloat16* __restrict__ residual, void* __restrict__ Cout,
+                     int M, int N, int K, int ldc, int ldr, int flags) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);  // SWIZZLE_128B atoms need 1024-B alignment
+  using S = GemmSmem<BN>;
+  uint64_t* full = (uint64_t*)(smem + GEMM_STAGES * S::STAGE_BYTES);
+  uint64_t* empty = full + GEMM_STAGES;
+  uint64_t* tmem_full = empty + GEMM_STAGES;
+  uint32_t* tmem_slot = (uint32_t*)(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * GEMM_BM, n0 = blockIdx.y * BN;
+  const int num_kb = (K + GEMM_BK - 1) / GEMM_BK;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    for (int s = 0; s < GEMM_STAGES; s++) {
+      g_mbar_init(&full[s], 1);
+      g_mbar_init(&empty[s], 1);
+    }
+    g_mbar_init(tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(g_smem_u32(tmem_slot)), "r"(BN)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < num_kb; kb++) {
+        const int s = kb % GEMM_STAGES;
+        g_mbar_wait(&empty[s], ((kb / GEMM_STAGES) & 1) ^ 1);
+        uint8_t* a_dst = smem + s * S::STAGE_BYTES;
+        uint8_t* b_dst = a_dst + S::A_BYTES;
+        g_mbar_expect_tx(&full[s], S::STAGE_BYTES);
+        g_tma_load_2d(a_dst, &tmA, kb * GEMM_BK, m0, &full[s]);
+        g_tma_load_2d(b_dst, &tmB, kb * GEMM_BK, n0, &full[s]);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = g_make_idesc(GEMM_BM, BN);
+      for (int kb = 0; kb < num_kb; kb++) {
+        const int s = kb % GEMM_STAGES;
+        g_mbar_wait(&full[s], (kb / GEMM_STAGES) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint64_t adesc = g_make_desc(smem + s * S::STAGE_BYTES);
+        const uint64_t bdesc = g_make_desc(smem + s * S::STAGE_BYTES + S::A_BYTES);
+#pragma unroll
+        for (int k = 0; k < GEMM_BK / 16; k++)  // advance 16 bf16 = 32 B inside the 128-B swizzle atom: +2 in >>4 units
+          g_umma(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+        g_umma_commit(&empty[s]);  // frees the ring slot once these MMAs have read it
+      }
+      g_umma_commit(tmem_full);  // accumulator complete
+    }
+  } else {
+    // ===== epilogue warps: TMEM lane quarter = warp % 4
+    const int q = warp & 3;
+    g_mbar_wait(tmem_full, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int row = m0 + q * 32 + lane;
+    const bool has_bias = flags & S3R_EPI_BIAS, gelu = flags & S3R_EPI_GELU, has_res = flags & S3R_EPI_RESIDUAL,
+               out_f32 = flags & S3R_EPI_OUT_F32;
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; c++) {
+      uint32_t v[32];
+      g_tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+      const int col0 = n0 + c * 32;
+      if (row < M && col0 < N) {
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; j++) f[j] = __uint_as_float(v[j]);
+        if (has_bias) {
+#pragma unroll
+          for (int j = 0; j < 32; j++)
+            if (col0 + j < N) f[j] += __bfloat162float(bias[col0 + j]);
+        }
+        if (gelu) {
+#pragma unroll
+          for (int j = 0; j < 32; j++) f[j] = 0.5f * f[j] * (1.0f + erff(f[j] * 0.70710678118654752f));
+        }
+        if (has_res) {
+          const __nv_bfloat16* rp = residual + (size_t)row * ldr + col0;
+          if (col0 + 32 <= N) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              const uint4 u = *reinterpret_cast<const uint4*>(rp + j);
+              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+              for (int t = 0; t < 4; t++) {
+                const float2 r2 = __bfloat1622float2(h[t]);
+                f[j + 2 * t] += r2.x;
+                f[j + 2 * t + 1] += r2.y;
+              }
+            }
+          } else {
+            for (int j = 0; j < 32 && col0 + j < N; j++) f[j] += __bfloat162float(rp[j]);
+          }
+        }
+        if (out_f32) {
+          float* op = (float*)Cout + (size_t)row * ldc + col0;
+          if (col0 + 32 <= N) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(op + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+          } else {
+            for (int j = 0; j < 32 && col0 + j < N; j++) op[j] = f[j];
+          }
+        } else {
+          __nv_bfloat16* op = (__nv_bfloat16*)Cout + (size_t)row * ldc + col0;
+          if (col0 + 32 <= N) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              uint4 u;
+              __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+              for (int t = 0; t < 4; t++) h[t] = __floats2bfloat162_rn(f[j + 2 * t], f[j + 2 * t + 1]);
+              *reinterpret_cast<uint4*>(op + j) = u;
+            }
+          } else {
+            for (int j = 0; j < 32 && col0 + j < N; j++) op[j] = __float2bfloat16_rn(f[j]);
+          }
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(BN) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------- host
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      return nullptr;
+    fn = (PFN_encodeTiled)p;
+  }
+  return fn;
+}
+
+// 2-D bf16 row-major [rows, cols] (ld elements per row), box = [box_rows, 64 cols], SWIZZLE_128B, zero OOB fill
+static int make_map(CUtensorMap* map, const void* ptr, int rows, int cols, int ld, int box_rows) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return S3R_ERR_CUDA;
+  const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  const cuuint32_t box[2] = {GEMM_BK, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? S3R_OK : S3R_ERR_CUDA;
+}
+
+template <int BN>
+static int launch_gemm(const CUtensorMap& a, const CUtensorMap& b, const void* bias, const void* residual, void* C, int M,
+                       int N, int K, int ldc, int ldr, int flags, cudaStream_t st) {
+  static bool configured = false;
+  const int smem = GemmSmem<BN>::TOTAL;
+  if (!configured) {
+    S3R_CUDA_CHECK(cudaFuncSetAttribute(s3r_gemm_bf16_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  dim3 grid((M + GEMM_BM - 1) / GEMM_BM, (N + BN - 1) / BN);
+  s3r_gemm_bf16_kernel<BN><<<grid, GEMM_THREADS, smem, st>>>(a, b, (const __nv_bfloat16*)bias, (const __nv_bfloat16*)residual, C,
+                                                             M, N, K, ldc, ldr, flags);
+  S3R_CUDA_CHECK(cudaGetLastError());
+  return S3R_OK;
+}
+
+extern "C" int s3r_gemm_bf16(const void* A, const void* W, const void* bias, const void* residual, void* C, int32_t M,
+                             int32_t N, int32_t K, int32_t lda, int32_t ldw, int32_t ldc, int32_t ldr, int32_t flags,
+                             void* stream) {
+  if (M < 0 || N <= 0 || K <= 0) return S3R_ERR_INVALID_ARG;
+  if (M == 0) return S3R_OK;
+  if (!A || !W || !C) return S3R_ERR_INVALID_ARG;
+  if ((flags & S3R_EPI_BIAS) && !bias) return S3R_ERR_INVALID_ARG;
+  if ((flags & S3R_EPI_RESIDUAL) && !residual) return S3R_ERR_INVALID_ARG;
+  // TMA: 16-byte aligned base and row pitch; vector epilogue: 16-byte aligned output rows
+  if (K % 8 || lda % 8 || ldw % 8 || ldc % 8 || ((flags & S3R_EPI_RESIDUAL) && ldr % 8)) return S3R_ERR_UNSUPPORTED;
+  if (((uintptr_t)A | (uintptr_t)W | (uintptr_t)C) & 15) return S3R_ERR_UNSUPPORTED;
+  CUtensorMap ta, tb;
+  int rc;
+  // fewer than ~1 wave of 128x128 tiles: use 128x64 tiles to fill the 148 SMs
+  const long tiles128 = (long)((M + 127) / 128) * ((N + 127) / 128);
+  const int BN = tiles128 < 120 ? 64 : 128;
+  if ((rc = make_map(&ta, A, M, K, lda, GEMM_BM)) != S3R_OK) return rc;
+  if ((rc = make_map(&tb, W, N, K, ldw, BN)) != S3R_OK) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (BN == 64) return launch_gemm<64>(ta, tb, bias, residual, C, M, N, K, ldc, ldr, flags, st);
+  return launch_gemm<128>(ta, tb, bias, residual, C, M, N, K, ldc, ldr, flags, st);
+}

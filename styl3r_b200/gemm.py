@@ -1,0 +1,57 @@
+"""bf16 linear layers on the tcgen05 GEMM (styl3r_b200/csrc/gemm_tcgen05.cu) — the dense-contraction path of the
+ViT trunks in the B200 inference layout (`EncoderNoPoSplatMultiTokenStyle.to_inference`).
+
+    y = linear(x, weight, bias=None, residual=None, gelu=False)      # y = act(x W^T + b) + residual
+
+replaces `nn.Linear` (+ `nn.GELU`, + the residual add of the transformer block) of
+src/model/encoder/backbone/croco/blocks.py:61-82,97-134,149-152 with one kernel."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib
+
+EPI_BIAS, EPI_GELU, EPI_RESIDUAL, EPI_OUT_F32 = 1, 2, 4, 8
+
+
+def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None,
+           residual: Optional[torch.Tensor] = None, gelu: bool = False, out_dtype: torch.dtype = torch.bfloat16):
+    if x.device.type != "cuda":
+        raise _lib.S3RError("styl3r_b200.gemm.linear needs CUDA tensors (no CPU fallback)")
+    if x.dtype != torch.bfloat16 or weight.dtype != torch.bfloat16:
+        raise _lib.S3RError("styl3r_b200.gemm.linear expects bf16 activations and weights")
+    N, K = weight.shape
+    lead = x.shape[:-1]
+    x2 = x.reshape(-1, K)
+    if x2.stride(1) != 1:
+        x2 = x2.contiguous()
+    w = weight if weight.stride(1) == 1 else weight.contiguous()
+    M = x2.shape[0]
+    out = torch.empty((M, N), dtype=out_dtype, device=x.device)
+    flags = 0
+    bp = rp = None
+    ldr = 0
+    if bias is not None:
+        flags |= EPI_BIAS
+        bias = bias if bias.dtype == torch.bfloat16 else bias.to(torch.bfloat16)
+        bp = C.c_void_p(bias.data_ptr())
+    if gelu:
+        flags |= EPI_GELU
+    if residual is not None:
+        flags |= EPI_RESIDUAL
+        r2 = residual.reshape(-1, N)
+        if r2.stride(1) != 1 or r2.dtype != torch.bfloat16:
+            r2 = r2.to(torch.bfloat16).contiguous()
+        rp, ldr = C.c_void_p(r2.data_ptr()), r2.stride(0)
+    if out_dtype == torch.float32:
+        flags |= EPI_OUT_F32
+    elif out_dtype != torch.bfloat16:
+        raise _lib.S3RError("out_dtype must be bf16 or fp32")
+    _lib.check(_lib.lib().s3r_gemm_bf16(C.c_void_p(x2.data_ptr()), C.c_void_p(w.data_ptr()), bp, rp,
+                                        C.c_void_p(out.data_ptr()), M, N, K, x2.stride(0), w.stride(0), out.stride(0),
+                                        ldr, flags, C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)),
+               "s3r_gemm_bf16")
+    return out.reshape(*lead, N)

@@ -1,0 +1,50 @@
+"""GPU numerics: tcgen05 bf16 GEMM + fused epilogue vs a plain PyTorch fp32 reference of the same op on the same
+bf16-rounded operands.  Tolerance: fp32 accumulation on both sides, so the difference is the final bf16 rounding of
+the output (2^-8 relative) plus summation order: |err| <= 1e-2 * max|ref| for bf16 output, 2e-3 for fp32 output."""
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def ref(x, w, b, r, gelu):
+    import torch
+    y = x.float() @ w.float().t()
+    if b is not None:
+        y = y + b.float()
+    if gelu:
+        y = torch.nn.functional.gelu(y)
+    if r is not None:
+        y = y + r.float()
+    return y
+
+
+@pytest.mark.parametrize("M,N,K", [(514, 3072, 1024), (514, 1024, 4096), (128, 128, 64), (257, 768, 768), (1, 64, 72),
+                                   (4112, 4096, 1024), (771, 2304, 768), (300, 200, 136)])
+@pytest.mark.parametrize("epi", ["none", "bias", "bias_gelu", "bias_res", "bias_gelu_res_f32"])
+def test_gemm_matches_fp32_reference(M, N, K, epi):
+    import torch
+    from styl3r_b200.gemm import linear
+    torch.manual_seed(M * 7 + N * 3 + K)
+    x = (torch.randn(M, K, device="cuda") * 0.5).to(torch.bfloat16)
+    w = (torch.randn(N, K, device="cuda") * K ** -0.5).to(torch.bfloat16)
+    b = (torch.randn(N, device="cuda") * 0.1).to(torch.bfloat16) if "bias" in epi else None
+    r = torch.randn(M, N, device="cuda").to(torch.bfloat16) if "res" in epi else None
+    out_dtype = torch.float32 if "f32" in epi else torch.bfloat16
+    y = linear(x, w, b, r, gelu="gelu" in epi, out_dtype=out_dtype)
+    torch.cuda.synchronize()
+    expect = ref(x, w, b, r, "gelu" in epi)
+    err = (y.float() - expect).abs().max().item()
+    tol = (2e-3 if out_dtype == torch.float32 else 1e-2) * expect.abs().max().item()
+    assert y.shape == (M, N) and y.dtype == out_dtype
+    assert err <= tol, f"max err {err:.4e} > {tol:.4e}"
+
+
+def test_gemm_batched_leading_dims_and_strided_rows():
+    import torch
+    from styl3r_b200.gemm import linear
+    x = torch.randn(2, 257, 2048, device="cuda").to(torch.bfloat16)[..., :1024]  # row pitch 2048
+    w = (torch.randn(768, 1024, device="cuda") / 32).to(torch.bfloat16)
+    y = linear(x, w)
+    expect = x.float() @ w.float().t()
+    assert y.shape == (2, 257, 768)
+    assert (y.float() - expect).abs().max() <= 1e-2 * expect.abs().max()
