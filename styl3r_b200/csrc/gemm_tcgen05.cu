@@ -8,7 +8,7 @@
 // i.e. the "TN" GEMM.
 //
 // Structure (one 128 x BN output tile per CTA, 6 warps, warp-specialised):
-//   warp 0   TMA producer: cp.async.bulk.tensor.2d of a 128x64 A tile and a BNx64 W tile per k-block into a 4-stage
+//   warp 0   TMA producer: cp.async.bulk.tensor.2d of a 128x64 A tile and a BNx64 W tile per k-block into a deep (6-10 stage)
 //            SWIZZLE_128B shared-memory ring, completion on `full` mbarriers (expect_tx)
 //   warp 1   allocates BN TMEM columns; one elected lane issues 4 x tcgen05.mma (M=128, N=BN, K=16) per k-block from
 //            shared-memory matrix descriptors, releases ring slots with tcgen05.commit -> `empty` mbarriers and signals
@@ -22,8 +22,10 @@
 
 #define GEMM_BM 128
 #define GEMM_BK 64
-#define GEMM_STAGES 4
 #define GEMM_THREADS 192
+#ifndef GEMM_SMEM_KB
+#define GEMM_SMEM_KB 100
+#endif
 
 __device__ __forceinline__ uint32_t g_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -102,17 +104,25 @@ struct GemmSmem {
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
   static constexpr int B_BYTES = BN * GEMM_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int TOTAL = GEMM_STAGES * STAGE_BYTES + 256 + 1024;  // + barriers + alignment slack
+  // ring depth: ~100 KB per CTA so that TWO CTAs are resident per SM — the epilogue of one tile (TMEM -> registers,
+  // bias / erf-GELU / residual, stores) then overlaps the TMA + MMA main loop of the other (measured: better than one
+  // CTA with a 200 KB ring, whose tensor pipe idles during its own epilogue)
+#ifndef GEMM_SMEM_KB
+#define GEMM_SMEM_KB 100
+#endif
+  static constexpr int STAGES = (GEMM_SMEM_KB * 1024) / STAGE_BYTES;
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + 256 + 1024;  // + barriers + alignment slack
 };
 
 template <int BN>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(GEMM_THREADS, GEMM_SMEM_KB <= 100 ? 2 : 1)
 s3r_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const __nv_bfloat16* __restrict__ bias, const __nv_bfloat16* __restrict__ residual, void* __restrict__ Cout,
                      int M, int N, int K, int ldc, int ldr, int flags) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);  // SWIZZLE_128B atoms need 1024-B alignment
   using S = GemmSmem<BN>;
+  constexpr int GEMM_STAGES = S::STAGES;
   uint64_t* full = (uint64_t*)(smem + GEMM_STAGES * S::STAGE_BYTES);
   uint64_t* empty = full + GEMM_STAGES;
   uint64_t* tmem_full = empty + GEMM_STAGES;
@@ -310,11 +320,14 @@ extern "C" int s3r_gemm_bf16(const void* A, const void* W, const void* bias, con
   CUtensorMap ta, tb;
   int rc;
   // fewer than ~1 wave of 128x128 tiles: use 128x64 tiles to fill the 148 SMs
-  const long tiles128 = (long)((M + 127) / 128) * ((N + 127) / 128);
-  const int BN = tiles128 < 120 ? 64 : 128;
+  const long mt = (M + 127) / 128;
+  const long tiles128 = mt * ((N + 127) / 128), tiles64 = mt * ((N + 63) / 64);
+  (void)tiles64;
+  const int BN = tiles128 >= 120 ? 128 : 64;  // (BN=32 measured slower: every N-tile re-reads the A tile from L2)
   if ((rc = make_map(&ta, A, M, K, lda, GEMM_BM)) != S3R_OK) return rc;
   if ((rc = make_map(&tb, W, N, K, ldw, BN)) != S3R_OK) return rc;
   cudaStream_t st = (cudaStream_t)stream;
+  if (BN == 32) return launch_gemm<32>(ta, tb, bias, residual, C, M, N, K, ldc, ldr, flags, st);
   if (BN == 64) return launch_gemm<64>(ta, tb, bias, residual, C, M, N, K, ldc, ldr, flags, st);
   return launch_gemm<128>(ta, tb, bias, residual, C, M, N, K, ldc, ldr, flags, st);
 }

@@ -24,7 +24,7 @@ from torch import Tensor, nn
 
 from .. import _lib
 from .dpt import PixelwiseDPT
-from .vit import CroCoTrunk
+from .vit import CroCoTrunk, _lin
 
 
 @dataclass
@@ -127,7 +127,7 @@ class AsymmetricCroCoMulti(CroCoTrunk):
         feat, pos = self.encode(img.reshape(b * v, *img.shape[2:]), tok)
         feat, pos = feat.reshape(b, v, *feat.shape[1:]), pos.reshape(b, v, *pos.shape[1:])
         outs = [feat]
-        cur = self.decoder_embed(feat)
+        cur = _lin(self.decoder_embed, feat)
         pos_ctx = self._others(pos)
         blocks2 = self.dec_blocks2 if self.asymmetric else self.dec_blocks
         for blk1, blk2 in zip(self.dec_blocks, blocks2):
@@ -156,9 +156,9 @@ class TokenStylizer(CroCoTrunk):
         b, v, l, _ = content_feat.shape
         sfeat, spos = self.encode(style["image"])
         outs = [content_feat]
-        x = self.decoder_embed(content_feat.reshape(b, v * l, -1))
+        x = _lin(self.decoder_embed, content_feat.reshape(b, v * l, -1))
         xpos = content_pos.reshape(b, v * l, 2)
-        y = self.decoder_embed(sfeat)
+        y = _lin(self.decoder_embed, sfeat)
         for blk in self.dec_blocks:
             x = blk(x, y, xpos, spos)
             outs.append(x.reshape(b, v, l, -1))

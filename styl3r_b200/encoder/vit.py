@@ -14,6 +14,7 @@ from __future__ import annotations
 import torch
 from torch import Tensor, nn
 
+from .. import gemm as _gemm
 from ..curope import cuRoPE2D_func
 from ..ops import memory_efficient_attention
 
@@ -25,6 +26,17 @@ def _rope(t_bnhd: Tensor, pos: Tensor, base: float) -> Tensor:
     return cuRoPE2D_func.apply(t_bnhd, pos if pos.is_contiguous() else pos.contiguous(), base, 1.0)
 
 
+def _lin(layer: nn.Linear, x: Tensor, residual: Tensor | None = None, gelu: bool = False) -> Tensor:
+    """y = act(layer(x)) + residual.  bf16 inference layout (to_inference): one tcgen05 GEMM with the bias, exact
+    GELU and residual add fused in its epilogue; otherwise (fp32 / training) the torch ops of the reference."""
+    if x.dtype == torch.bfloat16 and layer.weight.dtype == torch.bfloat16 and not torch.is_grad_enabled():
+        return _gemm.linear(x, layer.weight, layer.bias, residual=residual, gelu=gelu)
+    y = layer(x)
+    if gelu:
+        y = torch.nn.functional.gelu(y)
+    return y if residual is None else residual + y
+
+
 class Mlp(nn.Module):
     def __init__(self, dim: int, hidden: int):
         super().__init__()
@@ -32,8 +44,8 @@ class Mlp(nn.Module):
         self.act = nn.GELU()
         self.fc2 = nn.Linear(hidden, dim)
 
-    def forward(self, x: Tensor) -> Tensor:
-        return self.fc2(self.act(self.fc1(x)))
+    def forward(self, x: Tensor, residual: Tensor | None = None) -> Tensor:
+        return _lin(self.fc2, _lin(self.fc1, x, gelu=True), residual=residual)
 
 
 class Attention(nn.Module):
@@ -43,13 +55,13 @@ class Attention(nn.Module):
         self.qkv = nn.Linear(dim, dim * 3, bias=True)
         self.proj = nn.Linear(dim, dim)
 
-    def forward(self, x: Tensor, xpos: Tensor) -> Tensor:
+    def forward(self, x: Tensor, xpos: Tensor, residual: Tensor | None = None) -> Tensor:
         B, N, C = x.shape
-        qkv = self.qkv(x).view(B, N, 3, self.num_heads, C // self.num_heads)
+        qkv = _lin(self.qkv, x).view(B, N, 3, self.num_heads, C // self.num_heads)
         q, k, v = qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2]          # [B,N,H,D] views, stride(2) == D
         q, k = _rope(q, xpos, self.rope_base), _rope(k, xpos, self.rope_base)
         o = memory_efficient_attention(q, k, v, scale=self.scale)
-        return self.proj(o.reshape(B, N, C))
+        return _lin(self.proj, o.reshape(B, N, C), residual=residual)
 
 
 class CrossAttention(nn.Module):
@@ -61,14 +73,15 @@ class CrossAttention(nn.Module):
         self.projv = nn.Linear(dim, dim, bias=True)
         self.proj = nn.Linear(dim, dim)
 
-    def forward(self, query: Tensor, key: Tensor, value: Tensor, qpos: Tensor, kpos: Tensor) -> Tensor:
+    def forward(self, query: Tensor, key: Tensor, value: Tensor, qpos: Tensor, kpos: Tensor,
+                residual: Tensor | None = None) -> Tensor:
         B, Nq, C = query.shape
         H, D = self.num_heads, C // self.num_heads
-        q = _rope(self.projq(query).view(B, Nq, H, D), qpos, self.rope_base)
-        k = _rope(self.projk(key).view(B, key.shape[1], H, D), kpos, self.rope_base)
-        v = self.projv(value).view(B, value.shape[1], H, D)
+        q = _rope(_lin(self.projq, query).view(B, Nq, H, D), qpos, self.rope_base)
+        k = _rope(_lin(self.projk, key).view(B, key.shape[1], H, D), kpos, self.rope_base)
+        v = _lin(self.projv, value).view(B, value.shape[1], H, D)
         o = memory_efficient_attention(q, k, v, scale=self.scale)
-        return self.proj(o.reshape(B, Nq, C))
+        return _lin(self.proj, o.reshape(B, Nq, C), residual=residual)
 
 
 class Block(nn.Module):
@@ -80,8 +93,8 @@ class Block(nn.Module):
         self.mlp = Mlp(dim, int(dim * mlp_ratio))
 
     def forward(self, x: Tensor, xpos: Tensor) -> Tensor:
-        x = x + self.attn(self.norm1(x), xpos)
-        return x + self.mlp(self.norm2(x))
+        x = self.attn(self.norm1(x), xpos, residual=x)
+        return self.mlp(self.norm2(x), residual=x)
 
 
 class DecoderBlock(nn.Module):
@@ -96,10 +109,10 @@ class DecoderBlock(nn.Module):
         self.norm_y = nn.LayerNorm(dim, eps=LN_EPS)
 
     def forward(self, x: Tensor, y: Tensor, xpos: Tensor, ypos: Tensor) -> Tensor:
-        x = x + self.attn(self.norm1(x), xpos)
+        x = self.attn(self.norm1(x), xpos, residual=x)
         y_ = self.norm_y(y)
-        x = x + self.cross_attn(self.norm2(x), y_, y_, xpos, ypos)
-        return x + self.mlp(self.norm3(x))
+        x = self.cross_attn(self.norm2(x), y_, y_, xpos, ypos, residual=x)
+        return self.mlp(self.norm3(x), residual=x)
 
 
 class PatchEmbed(nn.Module):
