@@ -4,3 +4,4 @@ from .cuda_splatting import (DepthRenderingMode, get_fov, get_projection_matrix,
                              render_cuda_orthographic)
 from .decoder_splatting_cuda import (DecoderOutput, DecoderSplattingCUDA, DecoderSplattingCUDACfg,  # noqa: F401
                                      get_decoder)
+from .session import RenderSession  # noqa: F401,E402

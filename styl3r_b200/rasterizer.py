@@ -31,9 +31,18 @@ def _f32c(t: torch.Tensor) -> torch.Tensor:
     return t.contiguous()
 
 
+_layout_cache: dict = {}
+
+
 def query_layout(n_views: int, P: int, W: int, H: int, capacity: int) -> _lib.RasterLayout:
-    lay = _lib.RasterLayout()
-    _lib.check(_lib.lib().s3r_raster_layout_query(n_views, P, W, H, capacity, lay), "s3r_raster_layout_query")
+    key = (n_views, P, W, H, capacity)
+    lay = _layout_cache.get(key)
+    if lay is None:
+        lay = _lib.RasterLayout()
+        _lib.check(_lib.lib().s3r_raster_layout_query(n_views, P, W, H, capacity, lay), "s3r_raster_layout_query")
+        if len(_layout_cache) > 256:
+            _layout_cache.clear()
+        _layout_cache[key] = lay
     return lay
 
 
@@ -78,6 +87,12 @@ class RasterContext:
 
 _capacity_hint: dict = {}
 _pending: list = []  # deferred overflow checks: (event, pinned status copy, shape key)
+_pinned_pool: list = []  # recycled pinned int64[4] buffers (cudaHostAlloc per call would cost ~100 us)
+
+
+def _pinned_status() -> torch.Tensor:
+    return _pinned_pool.pop() if _pinned_pool else torch.empty(4, dtype=torch.int64).pin_memory()
+
 
 
 def validate_pending(block: bool = False) -> None:
@@ -93,6 +108,7 @@ def validate_pending(block: bool = False) -> None:
             _capacity_hint[key] = max(_capacity_hint.get(key, 0), int(r_total * 1.5) + 1024, 1 << 16)
             if overflow:
                 bad = (key, r_total)
+            _pinned_pool.append(host)
         else:
             keep.append((ev, host, key))
     _pending[:] = keep
@@ -151,7 +167,7 @@ def forward_raw(means, cov, opacities, viewmatrix, projmatrix, tanfov, backgroun
         if check == "none":
             break
         if check == "deferred":
-            host = torch.empty(4, dtype=torch.int64).pin_memory()
+            host = _pinned_status()
             host.copy_(ctx.view("status"), non_blocking=True)
             ev = torch.cuda.Event()
             ev.record()

@@ -134,3 +134,35 @@ def test_render_cuda_end_to_end_vs_oracle():
     for v, o in enumerate(outs):
         err = np.abs(out.color[0, v].cpu().numpy() - o["color"])
         assert np.mean(err > 1e-4) < 2e-3 and np.median(err) < 1e-6
+
+
+def test_render_session_matches_render_cuda_and_detects_overflow():
+    import torch
+    from styl3r_b200 import synthetic as syn
+    from styl3r_b200._lib import S3RError
+    from styl3r_b200.decoder import RenderSession, render_cuda
+    sc = syn.make_scene(seed=3, v=2, V=2, hw=64)
+    pin = lambda a: torch.as_tensor(np.ascontiguousarray(a)).pin_memory()
+    host = dict(extrinsics=pin(sc["extrinsics"]), intrinsics=pin(sc["intrinsics"]), near=pin(sc["near"]), far=pin(sc["far"]),
+                background=torch.zeros(2, 3).pin_memory(), means=pin(sc["means"][None]), covariances=pin(sc["covariances"][None]),
+                harmonics=pin(sc["harmonics"][None]), opacities=pin(sc["opacities"][None]))
+    sess = RenderSession(host, (64, 64), want_depth=True)
+    d = {k: v.cuda() for k, v in host.items()}
+    vs = torch.zeros(2, dtype=torch.int32, device="cuda")
+    for it in range(2):
+        if it == 1:  # refill the bound host buffers: a new request through the same graph
+            host["opacities"].mul_(0.5)
+            host["extrinsics"][:, 0, 3] += 0.05
+            d = {k: v.cuda() for k, v in host.items()}
+        sess.run()
+        torch.cuda.synchronize()
+        sess.check()
+        color, depth = render_cuda(d["extrinsics"], d["intrinsics"], d["near"], d["far"], (64, 64), d["background"],
+                                   d["means"], d["covariances"], d["harmonics"], d["opacities"], view_set=vs)
+        assert torch.allclose(sess.color_host.cuda(), color, atol=1e-6)
+        assert torch.allclose(sess.depth_host.cuda(), depth, atol=1e-5)
+    small = RenderSession(host, (64, 64), capacity=100)
+    small.run()
+    torch.cuda.synchronize()
+    with pytest.raises(S3RError):
+        small.check()
