@@ -170,9 +170,11 @@ int s3r_raster_backward(const s3r_raster_params* params, const void* state, size
  * (row-major), intrinsics [n,3,3] normalised, near/far [n].  Outputs are the
  * tensors s3r_raster_params expects: viewmatrix / projmatrix / projmatrix_raw
  * [n,16] (transposed layout), campos [n,3], tanfov [n,2], scales [n].
+ * input_is_w2c != 0: `extrinsics` already holds world-to-camera matrices (the
+ * pose-align loop carries w2c, cam_utils.py:126-137) and no inverse is taken.
  * ------------------------------------------------------------------------ */
 int s3r_camera_setup(const float* extrinsics, const float* intrinsics, const float* near_, const float* far_,
-                     int32_t scale_invariant, int32_t n, float* viewmatrix, float* projmatrix,
+                     int32_t scale_invariant, int32_t input_is_w2c, int32_t n, float* viewmatrix, float* projmatrix,
                      float* projmatrix_raw, float* campos, float* tanfov, float* scales, void* stream);
 
 /* ------------------------------------------------------------------------

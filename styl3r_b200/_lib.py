@@ -79,7 +79,7 @@ def lib():
                                       C.POINTER(RasterGrads), C.c_void_p]
     L.s3r_rope2d.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int64,
                              C.c_int64, C.c_float, C.c_float, C.c_int32, C.c_void_p]
-    L.s3r_camera_setup.argtypes = [C.c_void_p] * 4 + [C.c_int32, C.c_int32] + [C.c_void_p] * 7
+    L.s3r_camera_setup.argtypes = [C.c_void_p] * 4 + [C.c_int32, C.c_int32, C.c_int32] + [C.c_void_p] * 7
     L.s3r_gaussian_adapter.argtypes = [C.c_void_p] * 4 + [C.c_int32] * 5 + [C.c_float] + [C.c_void_p] * 7
     L.s3r_gemm_bf16.argtypes = [C.c_void_p] * 5 + [C.c_int32] * 8 + [C.c_void_p]
     L.s3r_se3_update_w2c.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]

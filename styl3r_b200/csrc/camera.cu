@@ -42,7 +42,7 @@ __device__ static bool inv4(const double* m, double* out) {
 
 __global__ void s3r_camera_setup_kernel(const float* __restrict__ extr, const float* __restrict__ intr,
                                         const float* __restrict__ near_, const float* __restrict__ far_,
-                                        int scale_invariant, int n, float* __restrict__ viewmatrix,
+                                        int scale_invariant, int input_is_w2c, int n, float* __restrict__ viewmatrix,
                                         float* __restrict__ projmatrix, float* __restrict__ projraw,
                                         float* __restrict__ campos, float* __restrict__ tanfov,
                                         float* __restrict__ scales) {
@@ -50,12 +50,20 @@ __global__ void s3r_camera_setup_kernel(const float* __restrict__ extr, const fl
   if (i >= n) return;
   const float s = scale_invariant ? 1.0f / near_[i] : 1.0f;
   const double nr = (double)(near_[i] * s), fr = (double)(far_[i] * s);
-  double e[16];
-  for (int k = 0; k < 16; k++) e[k] = extr[16 * i + k];
-  for (int r = 0; r < 3; r++) e[4 * r + 3] = (double)(extr[16 * i + 4 * r + 3] * s);
-  double w2c[16];
-  if (!inv4(e, w2c))
-    for (int k = 0; k < 16; k++) w2c[k] = nan("");
+  double e[16], w2c[16];
+  if (input_is_w2c) {
+    // pose-align loop: the world->camera matrix is carried directly.  Scaling the camera-to-world translation by s
+    // equals scaling the world->camera translation by s; the camera centre is -R^T t.
+    for (int k = 0; k < 16; k++) w2c[k] = extr[16 * i + k];
+    for (int r = 0; r < 3; r++) w2c[4 * r + 3] = (double)(extr[16 * i + 4 * r + 3] * s);
+    for (int r = 0; r < 3; r++)
+      e[4 * r + 3] = -(w2c[0 + r] * w2c[3] + w2c[4 + r] * w2c[7] + w2c[8 + r] * w2c[11]);
+  } else {
+    for (int k = 0; k < 16; k++) e[k] = extr[16 * i + k];
+    for (int r = 0; r < 3; r++) e[4 * r + 3] = (double)(extr[16 * i + 4 * r + 3] * s);
+    if (!inv4(e, w2c))
+      for (int k = 0; k < 16; k++) w2c[k] = nan("");
+  }
   // K^-1 (3x3 adjugate)
   const float* K = intr + 9 * i;
   const double a = K[0], b = K[1], c = K[2], d = K[3], ee = K[4], f = K[5], g = K[6], h = K[7], k9 = K[8];
@@ -108,7 +116,7 @@ __global__ void s3r_camera_setup_kernel(const float* __restrict__ extr, const fl
 }
 
 extern "C" int s3r_camera_setup(const float* extrinsics, const float* intrinsics, const float* near_, const float* far_,
-                                int32_t scale_invariant, int32_t n, float* viewmatrix, float* projmatrix,
+                                int32_t scale_invariant, int32_t input_is_w2c, int32_t n, float* viewmatrix, float* projmatrix,
                                 float* projmatrix_raw, float* campos, float* tanfov, float* scales, void* stream) {
   if (n < 0) return S3R_ERR_INVALID_ARG;
   if (n == 0) return S3R_OK;
@@ -116,7 +124,7 @@ extern "C" int s3r_camera_setup(const float* extrinsics, const float* intrinsics
       !tanfov || !scales)
     return S3R_ERR_INVALID_ARG;
   s3r_camera_setup_kernel<<<(n + 31) / 32, 32, 0, (cudaStream_t)stream>>>(
-      extrinsics, intrinsics, near_, far_, scale_invariant, n, viewmatrix, projmatrix, projmatrix_raw, campos, tanfov,
+      extrinsics, intrinsics, near_, far_, scale_invariant, input_is_w2c, n, viewmatrix, projmatrix, projmatrix_raw, campos, tanfov,
       scales);
   S3R_CUDA_CHECK(cudaGetLastError());
   return S3R_OK;

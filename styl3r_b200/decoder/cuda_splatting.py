@@ -55,7 +55,8 @@ def get_projection_matrix(near: Tensor, far: Tensor, fov_x: Tensor, fov_y: Tenso
     return m
 
 
-def camera_setup(extrinsics: Tensor, intrinsics: Tensor, near: Tensor, far: Tensor, scale_invariant: bool):
+def camera_setup(extrinsics: Tensor, intrinsics: Tensor, near: Tensor, far: Tensor, scale_invariant: bool,
+                 input_is_w2c: bool = False):
     """All per-view camera tensors of `render_cuda` in ONE kernel launch (s3r_camera_setup): returns
     (viewmatrix_T [B,4,4], full_projection_T [B,4,4], projection_T [B,4,4], campos [B,3], tan_fov [B,2], scale [B])
     in the transposed layout the rasterizer expects (reference lines 65-72, 81-88).  Camera tensors are treated
@@ -72,7 +73,8 @@ def camera_setup(extrinsics: Tensor, intrinsics: Tensor, near: Tensor, far: Tens
     tan_fov = buf[51 * b:53 * b].view(b, 2)
     scale = buf[53 * b:54 * b]
     p = lambda t: _C.c_void_p(t.data_ptr())
-    _lib.check(_lib.lib().s3r_camera_setup(p(e), p(k), p(n_), p(f_), int(bool(scale_invariant)), b, p(view_t), p(full),
+    _lib.check(_lib.lib().s3r_camera_setup(p(e), p(k), p(n_), p(f_), int(bool(scale_invariant)), int(bool(input_is_w2c)), b,
+                                           p(view_t), p(full),
                                            p(proj_t), p(campos), p(tan_fov), p(scale),
                                            _C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), "s3r_camera_setup")
     return view_t, full, proj_t, campos, tan_fov, scale

@@ -220,9 +220,10 @@ class RasterPlan:
                    "s3r_raster_forward")
 
 
-def backward_raw(ctx: RasterContext, dL_dcolor, dL_ddepth=None, *, need_pose: bool = True):
+def backward_raw(ctx: RasterContext, dL_dcolor, dL_ddepth=None, *, need_pose: bool = True, only_pose: bool = False):
     """Gradients w.r.t. the tensors given to forward_raw. Returns a dict of tensors shaped like the inputs
-    (`cov` in the packing it was given), plus dL_dmeans2D [V,P,3] and dL_dtau [V,6] = (rho, theta)."""
+    (`cov` in the packing it was given), plus dL_dmeans2D [V,P,3] and dL_dtau [V,6] = (rho, theta).
+    only_pose: the pose-align loop needs dL/dtau only — no Gaussian gradient buffers are allocated or written."""
     L = _lib.lib()
     prm = ctx.params
     dev = ctx.state.device
@@ -230,12 +231,12 @@ def backward_raw(ctx: RasterContext, dL_dcolor, dL_ddepth=None, *, need_pose: bo
     M, cs = prm.sh_coeffs, prm.cov_stride
     dL_dcolor = _f32c(dL_dcolor)
     dL_ddepth = _f32c(dL_ddepth) if dL_ddepth is not None else None
+    z = (lambda *shape: None) if only_pose else (lambda *shape: torch.zeros(*shape, device=dev))
     g = dict(
-        means=torch.zeros(S, P, 3, device=dev), cov=torch.zeros(S, P, cs, device=dev),
-        opacities=torch.zeros(S, P, device=dev), means2D=torch.zeros(V, P, 3, device=dev),
+        means=z(S, P, 3), cov=z(S, P, cs), opacities=z(S, P), means2D=z(V, P, 3),
         tau=torch.zeros(V, 6, device=dev),
-        shs=torch.zeros(S, P, M, 3, device=dev) if prm.shs else None,
-        colors=torch.zeros(S, P, 3, device=dev) if prm.colors_precomp else None,
+        shs=z(S, P, M, 3) if prm.shs else None,
+        colors=z(S, P, 3) if prm.colors_precomp else None,
     )
     nbytes = L.s3r_raster_backward_scratch_bytes(V, P)
     scratch = torch.empty(nbytes, dtype=torch.uint8, device=dev)
