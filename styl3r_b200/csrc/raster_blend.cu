@@ -64,7 +64,7 @@ __device__ __noinline__ float exact_alpha(float power, float opacity) {
 #define BLEND_STAGES 4   // depth of the TMA ring
 #endif
 #ifndef BLEND_MINB
-#define BLEND_MINB 4
+#define BLEND_MINB 3
 #endif
 #define BLEND_CWARPS 8   // consumer warps (one 8x4 pixel block each); warp 8 is the TMA producer
 
@@ -96,6 +96,13 @@ __device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
 // Warp-specialised: warp 8 streams the tile's records through a BLEND_STAGES-deep ring with TMA bulk copies;
 // the 8 consumer warps run decoupled from each other (no CTA-wide barrier in the main loop): each culls the
 // stage against its own 8x4 pixel block, composites the survivors front to back, and releases the stage.
+__device__ __forceinline__ float fast_exp(float x) {  // MUFU.EX2 (flush-to-zero): |rel err| ~2^-21 * |x|
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
+  return y;
+}
+
+template <bool kHasNT>
 __global__ void __launch_bounds__(BLEND_THREADS, BLEND_MINB) s3r_blend_fwd_kernel(
     int W, int H, int P, int tiles_x, int tiles, const uint2* __restrict__ ranges, const float4* __restrict__ records,
     const uint32_t* __restrict__ point_list, const float* __restrict__ background, float* __restrict__ out_color,
@@ -206,50 +213,68 @@ __global__ void __launch_bounds__(BLEND_THREADS, BLEND_MINB) s3r_blend_fwd_kerne
       float alpha[BLEND_U], cr[BLEND_U], cg[BLEND_U], cb[BLEND_U], dp[BLEND_U];
       bool keep[BLEND_U];
       int idx[BLEND_U];
+      bool near_thr = false;
+      // ---- BLEND_U independent alpha chains (branch-free)
 #pragma unroll
       for (int u = 0; u < BLEND_U; u++) {
-        const int i = (packed[u >> 2] >> (8 * (u & 3))) & (BLEND_CHUNK - 1);  // bytes past `count` are stale: keep them in range
+        // bytes past `count` are stale: mask them into range, `valid` discards them
+        const int i = (packed[u >> 2] >> (8 * (u & 3))) & (BLEND_CHUNK - 1);
         idx[u] = i;
         const float4 r0 = sm.rec[s][i * 3];
         const float4 r1 = sm.rec[s][i * 3 + 1];
-        const float4 r2 = sm.rec[s][i * 3 + 2];
+        const float2 r2 = *reinterpret_cast<const float2*>(&sm.rec[s][i * 3 + 2]);
         const float dx = r0.x - pxf, dy = r0.y - pyf;
         const float q = __fadd_rn(__fmul_rn(__fmul_rn(r0.z, dx), dx), __fmul_rn(__fmul_rn(r1.x, dy), dy));
         const float power = __fsub_rn(__fmul_rn(-0.5f, q), __fmul_rn(__fmul_rn(r0.w, dx), dy));
-        float a = fminf(0.99f, r1.y * __expf(power));
-        bool kp = (k + u < count) && !(power > 0.0f);
-        if (kp && a < ALPHA_HI) {
-          kp = false;
-          if (a >= ALPHA_LO) {
-            a = exact_alpha(power, r1.y);
-            kp = a >= ALPHA_MIN;
-          }
-        }
+        const float a = fminf(0.99f, r1.y * fast_exp(power));
+        const bool valid = (k + u < count) && !(power > 0.0f);
+        keep[u] = valid && a >= ALPHA_HI;
+        near_thr |= valid && a >= ALPHA_LO && a < ALPHA_HI;
         alpha[u] = a;
-        keep[u] = kp;
         cr[u] = r1.z;
         cg[u] = r1.w;
         cb[u] = r2.x;
         dp[u] = r2.y;
       }
+      // ---- rare: some evaluation landed within 2e-5 of the 1/255 threshold -> decide it with the exact exp
+      if (__any_sync(0xffffffffu, near_thr)) {
 #pragma unroll
-      for (int u = 0; u < BLEND_U; u++) {
-        if (keep[u] && !done) {
-          const float test_T = T * (1.0f - alpha[u]);
-          if (test_T < 0.0001f) {
-            done = true;
-          } else {
-            const float wgt = alpha[u] * T;
-            Cr += cr[u] * wgt;
-            Cg += cg[u] * wgt;
-            Cb += cb[u] * wgt;
-            D += dp[u] * wgt;
-            if (n_touched != nullptr && test_T > 0.5f)
-              atomicAdd(&n_touched[(size_t)view * P + point_list[(size_t)rg.x + base_idx + idx[u]]], 1);
-            T = test_T;
-            last = base_idx + idx[u] + 1;
+        for (int u = 0; u < BLEND_U; u++) {
+          const float a = alpha[u];
+          if ((k + u < count) && a >= ALPHA_LO && a < ALPHA_HI) {
+            const int i = idx[u];
+            const float4 r0 = sm.rec[s][i * 3];
+            const float4 r1 = sm.rec[s][i * 3 + 1];
+            const float dx = r0.x - pxf, dy = r0.y - pyf;
+            const float q = __fadd_rn(__fmul_rn(__fmul_rn(r0.z, dx), dx), __fmul_rn(__fmul_rn(r1.x, dy), dy));
+            const float power = __fsub_rn(__fmul_rn(-0.5f, q), __fmul_rn(__fmul_rn(r0.w, dx), dy));
+            if (!(power > 0.0f)) {
+              const float ax = exact_alpha(power, r1.y);
+              alpha[u] = ax;
+              keep[u] = ax >= ALPHA_MIN;
+            }
           }
         }
+      }
+      // ---- sequential front-to-back compositing, predicated (no divergent branches)
+#pragma unroll
+      for (int u = 0; u < BLEND_U; u++) {
+        const bool active = keep[u] && !done;
+        const float test_T = T * (1.0f - alpha[u]);
+        const bool term = active && (test_T < 0.0001f);
+        const bool acc = active && !term;
+        const float wgt = acc ? alpha[u] * T : 0.0f;
+        Cr = fmaf(cr[u], wgt, Cr);
+        Cg = fmaf(cg[u], wgt, Cg);
+        Cb = fmaf(cb[u], wgt, Cb);
+        D = fmaf(dp[u], wgt, D);
+        if (kHasNT) {
+          if (acc && test_T > 0.5f)
+            atomicAdd(&n_touched[(size_t)view * P + point_list[(size_t)rg.x + base_idx + idx[u]]], 1);
+        }
+        T = acc ? test_T : T;
+        last = acc ? (base_idx + idx[u] + 1) : last;
+        done = done || term;
       }
       if (!__any_sync(0xffffffffu, !done)) {
         warp_done = true;
@@ -280,7 +305,8 @@ __global__ void __launch_bounds__(BLEND_THREADS, BLEND_MINB) s3r_blend_fwd_kerne
 int s3r_launch_blend(const s3r_raster_params& p, const s3r_raster_outputs& o, const s3r_raster_layout& L,
                      char* state, cudaStream_t st) {
   dim3 grid(L.tiles, p.n_views);
-  s3r_blend_fwd_kernel<<<grid, BLEND_THREADS, 0, st>>>(
+  auto kern = o.n_touched ? s3r_blend_fwd_kernel<true> : s3r_blend_fwd_kernel<false>;
+  kern<<<grid, BLEND_THREADS, 0, st>>>(
       p.width, p.height, p.P, L.tiles_x, L.tiles, (const uint2*)(state + L.ranges),
       (const float4*)(state + L.records), (const uint32_t*)(state + L.point_list), p.background, o.color, o.depth,
       o.opacity, (float*)(state + L.final_T), (uint32_t*)(state + L.n_contrib), o.n_touched);
