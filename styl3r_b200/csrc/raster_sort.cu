@@ -33,13 +33,9 @@ __device__ bool radix_pass(const unsigned long long* src, unsigned long long* ds
   uint32_t per = (n + SORT_WARPS - 1) / SORT_WARPS;
   per = (per + 31u) & ~31u;
   const uint32_t b0 = min(n, w * per), b1 = min(n, b0 + per);
-  for (uint32_t i = b0 + lane; (i - lane) < b1; i += 32) {
-    const bool valid = i < b1;
-    const uint32_t d = valid ? (uint32_t)((ld_key<kGlobal>(src + i) >> shift) & 255ull) : 0xffffffffu;
-    const uint32_t peers = __match_any_sync(0xffffffffu, d);
-    if (valid && lane == (__ffs(peers) - 1)) hist[w][d] += __popc(peers);
-    __syncwarp();
-  }
+  // count: fire-and-forget shared-memory reductions into the warp's private histogram (no dependency chain)
+  for (uint32_t i = b0 + lane; i < b1; i += 32)
+    atomicAdd(&hist[w][(uint32_t)((ld_key<kGlobal>(src + i) >> shift) & 255ull)], 1u);
   __syncthreads();
   // thread d owns digit d: total over warps -> exclusive scan over digits -> per-warp bases
   uint32_t tot = 0;
@@ -68,22 +64,31 @@ __device__ bool radix_pass(const unsigned long long* src, unsigned long long* ds
     base += c;
   }
   __syncthreads();
+  // scatter: stable ranks inside the warp from 8 independent ballots on the digit bits (fixed latency; MATCH.ANY's
+  // latency grows with the number of distinct digits in the warp, which is ~32 for mantissa bytes)
   for (uint32_t i = b0 + lane; (i - lane) < b1; i += 32) {
     const bool valid = i < b1;
     unsigned long long key = 0;
-    uint32_t d = 0xffffffffu;
+    uint32_t d = 0;
     if (valid) {
       key = ld_key<kGlobal>(src + i);
       d = (uint32_t)((key >> shift) & 255ull);
     }
-    const uint32_t peers = __match_any_sync(0xffffffffu, d);
+    uint32_t peers = __ballot_sync(0xffffffffu, valid);
+#pragma unroll
+    for (int bit = 0; bit < 8; bit++) {
+      const bool set = (d >> bit) & 1u;
+      const uint32_t m = __ballot_sync(0xffffffffu, set);
+      peers &= set ? m : ~m;
+    }
+    uint32_t base_d = 0;
+    if (valid) base_d = hist[w][d];
+    __syncwarp();
     if (valid) {
       const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
-      const uint32_t pos = hist[w][d] + rank;
-      dst[pos] = key;
+      dst[base_d + rank] = key;
+      if (rank == 0) hist[w][d] = base_d + __popc(peers);
     }
-    __syncwarp();
-    if (valid && lane == (__ffs(peers) - 1)) hist[w][d] += __popc(peers);
     __syncwarp();
   }
   __syncthreads();
