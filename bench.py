@@ -361,6 +361,34 @@ def run_ours(args):
     if rank == 0 and world == 1 and not args.no_cpu:
         cb = cpu_baseline()
 
+    # ---- supplementary (not part of `value`): the encoder that produces the Gaussians, cfg2 shapes, random weights
+    enc_info = None
+    if rank == 0 and world == 1 and args.with_encoder:
+        try:
+            from styl3r_b200.encoder import EncoderNoPoSplatTokenStyleCfg, GraphedEncoder, get_encoder
+            torch.manual_seed(0)
+            enc, _ = get_encoder(EncoderNoPoSplatTokenStyleCfg(stylized=True))
+            enc = enc.to(dev).eval().to_inference(torch.bfloat16)
+            gsel = torch.Generator().manual_seed(1234)
+            ctx = {"image": (torch.rand(1, V_CTX, 3, HW, HW, generator=gsel) * 2 - 1).to(dev),
+                   "intrinsics": torch.tensor([[0.8, 0, 0.5], [0, 0.8, 0.5], [0, 0, 1.0]]).expand(1, V_CTX, 3, 3).contiguous().to(dev)}
+            sty = {"image": (torch.rand(1, 3, HW, HW, generator=gsel) * 2 - 1).to(dev)}
+            fast = GraphedEncoder(enc)
+            fast(ctx, sty)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(10):
+                fast(ctx, sty)
+            e1.record()
+            torch.cuda.synchronize()
+            enc_ms = e0.elapsed_time(e1) / 10
+            enc_info = {"ms_per_scene": enc_ms, "tflops": 1270.8 / enc_ms, "config": "b=1, v=2, 256x256 + style image; bf16 ViT "
+                        "trunks on the tcgen05 GEMM, fp32 channels_last DPT heads, CUDA-graph replay; random weights",
+                        "reference_cpu_s_per_scene_survey_probe": 2.72}
+            del enc, fast
+        except Exception as e:  # supplementary only
+            enc_info = {"error": repr(e)[:200]}
+
     if rank == 0:
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": "views/s", "n_gpus": world, "steps": K, "warmup": Wm,
@@ -382,6 +410,7 @@ def run_ours(args):
                          "note": "blend is FP32/MUFU-bound by arithmetic intensity (SURVEY §7); see profiles/"},
             "stage_ms": stage_ms,
             "cpu_baseline": cb,
+            "encoder": enc_info,
         }))
     if dist is not None:
         dist.destroy_process_group()
@@ -397,6 +426,7 @@ def main():
     ap.add_argument("--e2e-streams", type=int, default=4, help="streams pipelining independent e2e requests")
     ap.add_argument("--streams", type=int, default=8, help="concurrent streams over independent scenes")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--with-encoder", action="store_true", help="also time the encoder (supplementary key)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

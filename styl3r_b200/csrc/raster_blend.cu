@@ -16,7 +16,6 @@
 // that the keep/skip decision matches the oracle.
 #include "s3r_common.cuh"
 
-#define BLEND_THREADS 288
 #define BLEND_CHUNK 128
 #define ALPHA_MIN (1.0f / 255.0f)
 #define ALPHA_LO (ALPHA_MIN * (1.0f - 2e-5f))
@@ -66,7 +65,11 @@ __device__ __noinline__ float exact_alpha(float power, float opacity) {
 #ifndef BLEND_MINB
 #define BLEND_MINB 3
 #endif
-#define BLEND_CWARPS 8   // consumer warps (one 8x4 pixel block each); warp 8 is the TMA producer
+#ifndef BLEND_SPLIT
+#define BLEND_SPLIT 1     // CTAs per 16x16 tile (1: 8 consumer warps, 2: half tiles of 16x8 px with 4 consumer warps)
+#endif
+#define BLEND_CWARPS (8 / BLEND_SPLIT)  // consumer warps (one 8x4 pixel block each); the last warp is the TMA producer
+#define BLEND_THREADS (32 * (BLEND_CWARPS + 1))
 
 struct __align__(128) BlendSmem {
   float4 rec[BLEND_STAGES][BLEND_CHUNK * 3];
@@ -109,7 +112,7 @@ __global__ void __launch_bounds__(BLEND_THREADS, BLEND_MINB) s3r_blend_fwd_kerne
     float* __restrict__ out_depth, float* __restrict__ out_opacity, float* __restrict__ final_T,
     uint32_t* __restrict__ n_contrib, int32_t* __restrict__ n_touched) {
   __shared__ BlendSmem sm;
-  const int view = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x;
+  const int view = blockIdx.y, tile = blockIdx.x / BLEND_SPLIT, part = blockIdx.x % BLEND_SPLIT, tid = threadIdx.x;
   const int lane = tid & 31, w = tid >> 5;
   const uint2 rg = ranges[(size_t)view * tiles + tile];
   const uint32_t n = rg.y - rg.x;
@@ -154,7 +157,8 @@ __global__ void __launch_bounds__(BLEND_THREADS, BLEND_MINB) s3r_blend_fwd_kerne
 
   // ===== consumers
   const int tx = tile % tiles_x, ty = tile / tiles_x;
-  const int X0 = tx * S3R_TILE + (w & 1) * 8, Y0 = ty * S3R_TILE + (w >> 1) * 4;  // this warp's 8x4 block
+  const int wt = part * BLEND_CWARPS + w;                                            // warp index inside the tile
+  const int X0 = tx * S3R_TILE + (wt & 1) * 8, Y0 = ty * S3R_TILE + (wt >> 1) * 4;  // this warp's 8x4 block
   const int px = X0 + (lane & 7), py = Y0 + (lane >> 3);
   const bool inside = px < W && py < H;
   const float pxf = (float)px, pyf = (float)py;
@@ -304,7 +308,7 @@ __global__ void __launch_bounds__(BLEND_THREADS, BLEND_MINB) s3r_blend_fwd_kerne
 
 int s3r_launch_blend(const s3r_raster_params& p, const s3r_raster_outputs& o, const s3r_raster_layout& L,
                      char* state, cudaStream_t st) {
-  dim3 grid(L.tiles, p.n_views);
+  dim3 grid(L.tiles * BLEND_SPLIT, p.n_views);
   auto kern = o.n_touched ? s3r_blend_fwd_kernel<true> : s3r_blend_fwd_kernel<false>;
   kern<<<grid, BLEND_THREADS, 0, st>>>(
       p.width, p.height, p.P, L.tiles_x, L.tiles, (const uint2*)(state + L.ranges),

@@ -8,7 +8,9 @@
 #define S3R_CHUNK 256          // Gaussians per preprocess / emit CTA (= one bit-mask row of 8 words)
 #define S3R_REC_FLOATS 12      // blend record: x y A B | C o r g | b depth ex ey
 #define S3R_REC_BYTES 48
+#ifndef S3R_SORT_SMEM_CAP
 #define S3R_SORT_SMEM_CAP 4096 // per-tile instances sorted entirely in shared memory
+#endif
 
 #define S3R_CUDA_CHECK(x)                    \
   do {                                       \
