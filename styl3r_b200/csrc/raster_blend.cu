@@ -200,6 +200,8 @@ __global__ void __launch_bounds__(BLEND_THREADS, BLEND_MINB) s3r_blend_fwd_kerne
       if ((uint32_t)i < cnt) {
         const float4 r0 = sm.rec[s][i * 3];
         const float4 r2 = sm.rec[s][i * 3 + 2];
+        // axis-aligned box of { alpha >= 1/255 } against the block (a tighter corner-cut test and skipping all-dead
+        // batches were measured and cost more than they save)
         hit = r2.z >= 0.f && (r0.x + r2.z >= bx0) && (r0.x - r2.z <= bx0 + 7.f) && (r0.y + r2.w >= by0) &&
               (r0.y - r2.w <= by0 + 3.f);
       }
