@@ -202,6 +202,17 @@ int s3r_gemm_bf16(const void* A, const void* W, const void* bias, const void* re
                   void* stream);
 
 /* ------------------------------------------------------------------------
+ * Attention softmax(q k^T * scale) v on tcgen05/TMEM, head_dim 64, bf16 —
+ * replaces xformers.ops.memory_efficient_attention (croco/blocks.py:126-130,
+ * 192-196).  q [B,Nq,H,64], k/v [B,Nk,H,64], o [B,Nq,H,64]; *_strides are the
+ * element strides of dims (B, N, H) (unit stride on the last dim; multiples of
+ * 8); no mask, no dropout.
+ * ------------------------------------------------------------------------ */
+int s3r_attention_bf16(const void* q, const void* k, const void* v, void* o, int32_t B, int32_t H, int32_t Nq,
+                       int32_t Nk, int32_t D, const int64_t* q_strides, const int64_t* k_strides,
+                       const int64_t* v_strides, const int64_t* o_strides, float scale, void* stream);
+
+/* ------------------------------------------------------------------------
  * Fused head epilogue -> Gaussians for one context view of a batch
  * (encoder_noposplat_multi_token_style.py:178-251, postprocess.py:45-61,
  * gaussian_adapter.py:122-153, gaussians.py:8-44).  Planar inputs pts_raw
