@@ -197,9 +197,21 @@ int s3r_rope2d(void* tokens, const int64_t* pos, int32_t B, int32_t N, int32_t H
 #define S3R_EPI_GELU 2
 #define S3R_EPI_RESIDUAL 4
 #define S3R_EPI_OUT_F32 8
+#define S3R_EPI_ROPE 16
 int s3r_gemm_bf16(const void* A, const void* W, const void* bias, const void* residual, void* C, int32_t M,
                   int32_t N, int32_t K, int32_t lda, int32_t ldw, int32_t ldc, int32_t ldr, int32_t flags,
                   void* stream);
+
+/* Same GEMM with RoPE-2D (curope.cpp:11-47 semantics, head_dim 64) applied to
+ * output columns [0, rope_cols) in the epilogue, after the bias: rope_pos is
+ * the int64 [M, 2] (y, x) position of every output row, rope_table the
+ * (cos, sin) table filled by s3r_rope_table for positions 0..rope_max_pos.
+ * Used for the qkv / projq / projk projections (blocks.py:97-106,176-182). */
+int s3r_gemm_bf16_rope(const void* A, const void* W, const void* bias, const void* residual, void* C, int32_t M,
+                       int32_t N, int32_t K, int32_t lda, int32_t ldw, int32_t ldc, int32_t ldr, int32_t flags,
+                       const int64_t* rope_pos, const float* rope_table, int32_t rope_cols, int32_t rope_max_pos,
+                       void* stream);
+int s3r_rope_table(float* table /* [(max_pos+1)*16*2] */, int32_t max_pos, float base, void* stream);
 
 /* ------------------------------------------------------------------------
  * Attention softmax(q k^T * scale) v on tcgen05/TMEM, head_dim 64, bf16 —

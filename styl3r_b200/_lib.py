@@ -82,6 +82,9 @@ def lib():
     L.s3r_camera_setup.argtypes = [C.c_void_p] * 4 + [C.c_int32, C.c_int32, C.c_int32] + [C.c_void_p] * 7
     L.s3r_gaussian_adapter.argtypes = [C.c_void_p] * 4 + [C.c_int32] * 5 + [C.c_float] + [C.c_void_p] * 7
     L.s3r_gemm_bf16.argtypes = [C.c_void_p] * 5 + [C.c_int32] * 8 + [C.c_void_p]
+    L.s3r_gemm_bf16_rope.argtypes = [C.c_void_p] * 5 + [C.c_int32] * 8 + [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
+                                                                          C.c_void_p]
+    L.s3r_rope_table.argtypes = [C.c_void_p, C.c_int32, C.c_float, C.c_void_p]
     L.s3r_attention_bf16.argtypes = [C.c_void_p] * 4 + [C.c_int32] * 5 + [C.POINTER(C.c_int64)] * 4 + [C.c_float, C.c_void_p]
     L.s3r_se3_update_w2c.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
     if L.s3r_abi_version() != ABI_VERSION:
@@ -99,5 +102,5 @@ def check(code: int, what: str = "") -> None:
 EXPORTED_SYMBOLS = (
     "s3r_abi_version", "s3r_error_string", "s3r_raster_layout_query", "s3r_raster_forward", "s3r_raster_forward_stages",
     "s3r_raster_read_status", "s3r_raster_backward_scratch_bytes", "s3r_raster_backward", "s3r_rope2d",
-    "s3r_se3_update_w2c", "s3r_camera_setup", "s3r_gaussian_adapter", "s3r_gemm_bf16", "s3r_attention_bf16",
+    "s3r_se3_update_w2c", "s3r_camera_setup", "s3r_gaussian_adapter", "s3r_gemm_bf16", "s3r_gemm_bf16_rope", "s3r_rope_table", "s3r_attention_bf16",
 )

@@ -23,9 +23,6 @@
 #define GEMM_BM 128
 #define GEMM_BK 64
 #define GEMM_THREADS 192
-#ifndef GEMM_SMEM_KB
-#define GEMM_SMEM_KB 100
-#endif
 
 __device__ __forceinline__ uint32_t g_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -99,29 +96,35 @@ __device__ __forceinline__ void g_tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-template <int BN>
+template <int BN, int STAGES_>
 struct GemmSmem {
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
   static constexpr int B_BYTES = BN * GEMM_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  // ring depth: ~100 KB per CTA so that TWO CTAs are resident per SM — the epilogue of one tile (TMEM -> registers,
-  // bias / erf-GELU / residual, stores) then overlaps the TMA + MMA main loop of the other (measured: better than one
-  // CTA with a 200 KB ring, whose tensor pipe idles during its own epilogue)
-#ifndef GEMM_SMEM_KB
-#define GEMM_SMEM_KB 100
-#endif
-  static constexpr int STAGES = (GEMM_SMEM_KB * 1024) / STAGE_BYTES;
+  // ring depth: large grids use ~100 KB per CTA so that TWO CTAs are resident per SM — the epilogue of one tile (TMEM
+  // -> registers, bias / erf-GELU / residual, stores) then overlaps the TMA + MMA main loop of the other (measured:
+  // better than one CTA with a 200 KB ring, whose tensor pipe idles during its own epilogue).  Grids smaller than the
+  // machine (the M = 257/514 shapes of cfg2) are latency-bound on the TMA round trip instead: they get an 8-stage
+  // ring so that (almost) the whole K extent is in flight at once.
+  static constexpr int STAGES = STAGES_;
   static constexpr int TOTAL = STAGES * STAGE_BYTES + 256 + 1024;  // + barriers + alignment slack
 };
 
-template <int BN>
-__global__ void __launch_bounds__(GEMM_THREADS, GEMM_SMEM_KB <= 100 ? 2 : 1)
+struct RopeArgs {            // RoPE-2D fused into the epilogue (qkv / projq / projk outputs: head_dim 64)
+  const long long* pos;      // [M, 2] int64 (y, x) per output row
+  const float2* table;       // [max_pos + 1, 16] (cos, sin) of pos * base^(-d/16)
+  int cols;                  // output columns [0, cols) are rotated (q and k parts), the rest (v) is left alone
+  int max_pos;
+};
+
+template <int BN, int STAGES_>
+__global__ void __launch_bounds__(GEMM_THREADS, (STAGES_ * (GEMM_BM + BN) * GEMM_BK * 2 <= 100 * 1024) ? 2 : 1)
 s3r_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const __nv_bfloat16* __restrict__ bias, const __nv_bfloat16* __restrict__ residual, void* __restrict__ Cout,
-                     int M, int N, int K, int ldc, int ldr, int flags) {
+                     int M, int N, int K, int ldc, int ldr, int flags, RopeArgs rope) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);  // SWIZZLE_128B atoms need 1024-B alignment
-  using S = GemmSmem<BN>;
+  using S = GemmSmem<BN, STAGES_>;
   constexpr int GEMM_STAGES = S::STAGES;
   uint64_t* full = (uint64_t*)(smem + GEMM_STAGES * S::STAGE_BYTES);
   uint64_t* empty = full + GEMM_STAGES;
@@ -201,6 +204,19 @@ s3r_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 #pragma unroll
           for (int j = 0; j < 32; j++)
             if (col0 + j < N) f[j] += __bfloat162float(bias[col0 + j]);
+        }
+        if ((flags & S3R_EPI_ROPE) && col0 < rope.cols) {
+          // this 32-column chunk is one half (y: even chunk, x: odd chunk) of one 64-wide head: pairs (d, d + 16)
+          long long pp = rope.pos[(size_t)row * 2 + ((col0 >> 5) & 1)];
+          pp = pp < 0 ? 0 : (pp > rope.max_pos ? rope.max_pos : pp);
+          const float2* tb = rope.table + pp * 16;
+#pragma unroll
+          for (int d = 0; d < 16; d++) {
+            const float2 cs = __ldg(tb + d);
+            const float u = f[d], w = f[d + 16];
+            f[d] = u * cs.x - w * cs.y;
+            f[d + 16] = w * cs.x + u * cs.y;
+          }
         }
         if (gelu) {
 #pragma unroll
@@ -290,30 +306,56 @@ static int make_map(CUtensorMap* map, const void* ptr, int rows, int cols, int l
   return r == CUDA_SUCCESS ? S3R_OK : S3R_ERR_CUDA;
 }
 
-template <int BN>
+template <int BN, int STAGES_>
 static int launch_gemm(const CUtensorMap& a, const CUtensorMap& b, const void* bias, const void* residual, void* C, int M,
-                       int N, int K, int ldc, int ldr, int flags, cudaStream_t st) {
+                       int N, int K, int ldc, int ldr, int flags, const RopeArgs& rope, cudaStream_t st) {
   static bool configured = false;
-  const int smem = GemmSmem<BN>::TOTAL;
+  const int smem = GemmSmem<BN, STAGES_>::TOTAL;
   if (!configured) {
-    S3R_CUDA_CHECK(cudaFuncSetAttribute(s3r_gemm_bf16_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    S3R_CUDA_CHECK(cudaFuncSetAttribute(s3r_gemm_bf16_kernel<BN, STAGES_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
   dim3 grid((M + GEMM_BM - 1) / GEMM_BM, (N + BN - 1) / BN);
-  s3r_gemm_bf16_kernel<BN><<<grid, GEMM_THREADS, smem, st>>>(a, b, (const __nv_bfloat16*)bias, (const __nv_bfloat16*)residual, C,
-                                                             M, N, K, ldc, ldr, flags);
+  s3r_gemm_bf16_kernel<BN, STAGES_><<<grid, GEMM_THREADS, smem, st>>>(a, b, (const __nv_bfloat16*)bias,
+                                                                      (const __nv_bfloat16*)residual, C, M, N, K, ldc, ldr,
+                                                                      flags, rope);
   S3R_CUDA_CHECK(cudaGetLastError());
   return S3R_OK;
 }
 
-extern "C" int s3r_gemm_bf16(const void* A, const void* W, const void* bias, const void* residual, void* C, int32_t M,
-                             int32_t N, int32_t K, int32_t lda, int32_t ldw, int32_t ldc, int32_t ldr, int32_t flags,
-                             void* stream) {
+// (cos, sin) table for the fused RoPE epilogue: table[pos][d] = cos/sin(pos * base^(-d/16)), pos in [0, max_pos]
+__global__ void s3r_rope_table_kernel(float2* table, int n, float base) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int pos = i >> 4, d = i & 15;
+  const float inv_freq = 1.0f / powf(base, (float)d / 16.0f);
+  float sn, cs;
+  sincosf((float)pos * inv_freq, &sn, &cs);
+  table[i] = make_float2(cs, sn);
+}
+
+extern "C" int s3r_rope_table(float* table, int32_t max_pos, float base, void* stream) {
+  if (!table || max_pos < 0) return S3R_ERR_INVALID_ARG;
+  const int n = (max_pos + 1) * 16;
+  s3r_rope_table_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>((float2*)table, n, base);
+  S3R_CUDA_CHECK(cudaGetLastError());
+  return S3R_OK;
+}
+
+extern "C" int s3r_gemm_bf16_rope(const void* A, const void* W, const void* bias, const void* residual, void* C, int32_t M,
+                                  int32_t N, int32_t K, int32_t lda, int32_t ldw, int32_t ldc, int32_t ldr, int32_t flags,
+                                  const int64_t* rope_pos, const float* rope_table, int32_t rope_cols,
+                                  int32_t rope_max_pos, void* stream) {
   if (M < 0 || N <= 0 || K <= 0) return S3R_ERR_INVALID_ARG;
   if (M == 0) return S3R_OK;
   if (!A || !W || !C) return S3R_ERR_INVALID_ARG;
   if ((flags & S3R_EPI_BIAS) && !bias) return S3R_ERR_INVALID_ARG;
   if ((flags & S3R_EPI_RESIDUAL) && !residual) return S3R_ERR_INVALID_ARG;
+  if (flags & S3R_EPI_ROPE) {
+    if (!rope_pos || !rope_table || rope_cols <= 0 || rope_cols % 64 || rope_cols > N || rope_max_pos < 0)
+      return S3R_ERR_INVALID_ARG;
+  }
+  RopeArgs rope{(const long long*)rope_pos, (const float2*)rope_table, rope_cols, rope_max_pos};
   // TMA: 16-byte aligned base and row pitch; vector epilogue: 16-byte aligned output rows
   if (K % 8 || lda % 8 || ldw % 8 || ldc % 8 || ((flags & S3R_EPI_RESIDUAL) && ldr % 8)) return S3R_ERR_UNSUPPORTED;
   if (((uintptr_t)A | (uintptr_t)W | (uintptr_t)C) & 15) return S3R_ERR_UNSUPPORTED;
@@ -322,12 +364,20 @@ extern "C" int s3r_gemm_bf16(const void* A, const void* W, const void* bias, con
   // fewer than ~1 wave of 128x128 tiles: use 128x64 tiles to fill the 148 SMs
   const long mt = (M + 127) / 128;
   const long tiles128 = mt * ((N + 127) / 128), tiles64 = mt * ((N + 63) / 64);
-  (void)tiles64;
   const int BN = tiles128 >= 120 ? 128 : 64;  // (BN=32 measured slower: every N-tile re-reads the A tile from L2)
   if ((rc = make_map(&ta, A, M, K, lda, GEMM_BM)) != S3R_OK) return rc;
   if ((rc = make_map(&tb, W, N, K, ldw, BN)) != S3R_OK) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  if (BN == 32) return launch_gemm<32>(ta, tb, bias, residual, C, M, N, K, ldc, ldr, flags, st);
-  if (BN == 64) return launch_gemm<64>(ta, tb, bias, residual, C, M, N, K, ldc, ldr, flags, st);
-  return launch_gemm<128>(ta, tb, bias, residual, C, M, N, K, ldc, ldr, flags, st);
+  if (BN == 64) {
+    if (tiles64 < 148) return launch_gemm<64, 8>(ta, tb, bias, residual, C, M, N, K, ldc, ldr, flags, rope, st);
+    return launch_gemm<64, 4>(ta, tb, bias, residual, C, M, N, K, ldc, ldr, flags, rope, st);
+  }
+  return launch_gemm<128, 3>(ta, tb, bias, residual, C, M, N, K, ldc, ldr, flags, rope, st);
+}
+
+extern "C" int s3r_gemm_bf16(const void* A, const void* W, const void* bias, const void* residual, void* C, int32_t M,
+                             int32_t N, int32_t K, int32_t lda, int32_t ldw, int32_t ldc, int32_t ldr, int32_t flags,
+                             void* stream) {
+  if (flags & S3R_EPI_ROPE) return S3R_ERR_INVALID_ARG;
+  return s3r_gemm_bf16_rope(A, W, bias, residual, C, M, N, K, lda, ldw, ldc, ldr, flags, nullptr, nullptr, 0, 0, stream);
 }

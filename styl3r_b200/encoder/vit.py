@@ -26,10 +26,15 @@ def _rope(t_bnhd: Tensor, pos: Tensor, base: float) -> Tensor:
     return cuRoPE2D_func.apply(t_bnhd, pos if pos.is_contiguous() else pos.contiguous(), base, 1.0)
 
 
+def _fast(layer: nn.Linear, x: Tensor) -> bool:
+    """bf16 inference layout (to_inference) without autograd: the tcgen05 kernels are used."""
+    return x.dtype == torch.bfloat16 and layer.weight.dtype == torch.bfloat16 and not torch.is_grad_enabled()
+
+
 def _lin(layer: nn.Linear, x: Tensor, residual: Tensor | None = None, gelu: bool = False) -> Tensor:
     """y = act(layer(x)) + residual.  bf16 inference layout (to_inference): one tcgen05 GEMM with the bias, exact
     GELU and residual add fused in its epilogue; otherwise (fp32 / training) the torch ops of the reference."""
-    if x.dtype == torch.bfloat16 and layer.weight.dtype == torch.bfloat16 and not torch.is_grad_enabled():
+    if _fast(layer, x):
         return _gemm.linear(x, layer.weight, layer.bias, residual=residual, gelu=gelu)
     y = layer(x)
     if gelu:
@@ -57,9 +62,15 @@ class Attention(nn.Module):
 
     def forward(self, x: Tensor, xpos: Tensor, residual: Tensor | None = None) -> Tensor:
         B, N, C = x.shape
-        qkv = _lin(self.qkv, x).view(B, N, 3, self.num_heads, C // self.num_heads)
-        q, k, v = qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2]          # [B,N,H,D] views, stride(2) == D
-        q, k = _rope(q, xpos, self.rope_base), _rope(k, xpos, self.rope_base)
+        if _fast(self.qkv, x) and C // self.num_heads == 64:
+            # RoPE on the q and k thirds happens in the GEMM epilogue (fp32, before the bf16 rounding)
+            qkv = _gemm.linear(x, self.qkv.weight, self.qkv.bias, rope_pos=xpos, rope_cols=2 * C, rope_base=self.rope_base)
+            qkv = qkv.view(B, N, 3, self.num_heads, C // self.num_heads)
+            q, k, v = qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2]
+        else:
+            qkv = _lin(self.qkv, x).view(B, N, 3, self.num_heads, C // self.num_heads)
+            q, k, v = qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2]      # [B,N,H,D] views, stride(2) == D
+            q, k = _rope(q, xpos, self.rope_base), _rope(k, xpos, self.rope_base)
         o = memory_efficient_attention(q, k, v, scale=self.scale)
         return _lin(self.proj, o.reshape(B, N, C), residual=residual)
 
@@ -77,8 +88,14 @@ class CrossAttention(nn.Module):
                 residual: Tensor | None = None) -> Tensor:
         B, Nq, C = query.shape
         H, D = self.num_heads, C // self.num_heads
-        q = _rope(_lin(self.projq, query).view(B, Nq, H, D), qpos, self.rope_base)
-        k = _rope(_lin(self.projk, key).view(B, key.shape[1], H, D), kpos, self.rope_base)
+        if _fast(self.projq, query) and D == 64:
+            q = _gemm.linear(query, self.projq.weight, self.projq.bias, rope_pos=qpos, rope_cols=C,
+                             rope_base=self.rope_base).view(B, Nq, H, D)
+            k = _gemm.linear(key, self.projk.weight, self.projk.bias, rope_pos=kpos, rope_cols=C,
+                             rope_base=self.rope_base).view(B, key.shape[1], H, D)
+        else:
+            q = _rope(_lin(self.projq, query).view(B, Nq, H, D), qpos, self.rope_base)
+            k = _rope(_lin(self.projk, key).view(B, key.shape[1], H, D), kpos, self.rope_base)
         v = _lin(self.projv, value).view(B, value.shape[1], H, D)
         o = memory_efficient_attention(q, k, v, scale=self.scale)
         return _lin(self.proj, o.reshape(B, Nq, C), residual=residual)

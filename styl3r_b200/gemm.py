@@ -14,11 +14,28 @@ import torch
 
 from . import _lib
 
-EPI_BIAS, EPI_GELU, EPI_RESIDUAL, EPI_OUT_F32 = 1, 2, 4, 8
+EPI_BIAS, EPI_GELU, EPI_RESIDUAL, EPI_OUT_F32, EPI_ROPE = 1, 2, 4, 8, 16
+ROPE_MAX_POS = 255  # positions are patch-grid coordinates (16 for 256 px, 64 for 1024 px)
+_rope_tables: dict = {}
+
+
+def rope_table(device, base: float) -> torch.Tensor:
+    """(cos, sin)[pos, d] of pos * base^(-d/16), built once per (device, base) by s3r_rope_table."""
+    key = (str(device), float(base))
+    t = _rope_tables.get(key)
+    if t is None:
+        t = torch.empty((ROPE_MAX_POS + 1) * 16 * 2, dtype=torch.float32, device=device)
+        _lib.check(_lib.lib().s3r_rope_table(C.c_void_p(t.data_ptr()), ROPE_MAX_POS, float(base),
+                                            C.c_void_p(torch.cuda.current_stream(device).cuda_stream)), "s3r_rope_table")
+        _rope_tables[key] = t
+    return t
 
 
 def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None,
-           residual: Optional[torch.Tensor] = None, gelu: bool = False, out_dtype: torch.dtype = torch.bfloat16):
+           residual: Optional[torch.Tensor] = None, gelu: bool = False, out_dtype: torch.dtype = torch.bfloat16,
+           rope_pos: Optional[torch.Tensor] = None, rope_cols: int = 0, rope_base: float = 100.0):
+    """rope_pos [..., 2] int64 (one (y, x) per row of x) + rope_cols: RoPE-2D (head_dim 64) is applied to output columns
+    [0, rope_cols) inside the GEMM epilogue (q and k parts of a qkv projection), replacing a separate rope pass."""
     if x.device.type != "cuda":
         raise _lib.S3RError("styl3r_b200.gemm.linear needs CUDA tensors (no CPU fallback)")
     if x.dtype != torch.bfloat16 or weight.dtype != torch.bfloat16:
@@ -46,12 +63,23 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] =
         if r2.stride(1) != 1 or r2.dtype != torch.bfloat16:
             r2 = r2.to(torch.bfloat16).contiguous()
         rp, ldr = C.c_void_p(r2.data_ptr()), r2.stride(0)
+    pp = tp = None
+    if rope_pos is not None:
+        flags |= EPI_ROPE
+        rp2 = rope_pos.reshape(-1, 2)
+        if rp2.dtype != torch.int64 or not rp2.is_contiguous():
+            rp2 = rp2.to(torch.int64).contiguous()
+        if rp2.shape[0] != M:
+            raise _lib.S3RError("rope_pos must hold one (y, x) per row")
+        table = rope_table(x.device, rope_base)
+        pp, tp = C.c_void_p(rp2.data_ptr()), C.c_void_p(table.data_ptr())
     if out_dtype == torch.float32:
         flags |= EPI_OUT_F32
     elif out_dtype != torch.bfloat16:
         raise _lib.S3RError("out_dtype must be bf16 or fp32")
-    _lib.check(_lib.lib().s3r_gemm_bf16(C.c_void_p(x2.data_ptr()), C.c_void_p(w.data_ptr()), bp, rp,
-                                        C.c_void_p(out.data_ptr()), M, N, K, x2.stride(0), w.stride(0), out.stride(0),
-                                        ldr, flags, C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)),
+    _lib.check(_lib.lib().s3r_gemm_bf16_rope(C.c_void_p(x2.data_ptr()), C.c_void_p(w.data_ptr()), bp, rp,
+                                             C.c_void_p(out.data_ptr()), M, N, K, x2.stride(0), w.stride(0),
+                                             out.stride(0), ldr, flags, pp, tp, int(rope_cols), ROPE_MAX_POS,
+                                             C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)),
                "s3r_gemm_bf16")
     return out.reshape(*lead, N)

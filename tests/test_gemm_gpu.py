@@ -48,3 +48,30 @@ def test_gemm_batched_leading_dims_and_strided_rows():
     expect = x.float() @ w.float().t()
     assert y.shape == (2, 257, 768)
     assert (y.float() - expect).abs().max() <= 1e-2 * expect.abs().max()
+
+
+@pytest.mark.parametrize("M,H", [(514, 16), (257, 12), (771, 12)])
+def test_gemm_with_fused_rope_epilogue_matches_gemm_then_rope_oracle(M, H):
+    """qkv projection with RoPE-2D on the q and k thirds fused in the epilogue == fp32 GEMM followed by the RoPE
+    oracle (oracle/rope_oracle.c restating curope.cpp:11-47)."""
+    import numpy as np
+    import torch
+    from oracle import raster_oracle as ro
+    from styl3r_b200.gemm import linear
+    torch.manual_seed(M)
+    C_ = H * 64
+    x = (torch.randn(M, C_, device="cuda") * 0.5).to(torch.bfloat16)
+    w = (torch.randn(3 * C_, C_, device="cuda") * C_ ** -0.5).to(torch.bfloat16)
+    b = (torch.randn(3 * C_, device="cuda") * 0.1).to(torch.bfloat16)
+    pos = torch.randint(0, 17, (M, 2), device="cuda")
+    y = linear(x, w, b, rope_pos=pos, rope_cols=2 * C_, rope_base=100.0)
+    torch.cuda.synchronize()
+    ref = (x.float() @ w.float().t() + b.float()).cpu().numpy().reshape(1, M, 3, H, 64)
+    expect = ref.copy()
+    for part in (0, 1):  # q and k thirds
+        expect[:, :, part] = ro.rope2d(np.ascontiguousarray(ref[:, :, part]), pos.cpu().numpy()[None], 100.0, 1.0)
+    err = np.abs(y.float().cpu().numpy().reshape(1, M, 3, H, 64) - expect).max()
+    assert err <= 1e-2 * np.abs(expect).max(), err
+    # the v third is untouched by the rotation
+    np.testing.assert_allclose(y.float().cpu().numpy().reshape(1, M, 3, H, 64)[:, :, 2], ref[:, :, 2],
+                               atol=1e-2 * np.abs(ref).max())
