@@ -210,7 +210,10 @@ int s3r_gemm_bf16(const void* A, const void* W, const void* bias, const void* re
 int s3r_gemm_bf16_rope(const void* A, const void* W, const void* bias, const void* residual, void* C, int32_t M,
                        int32_t N, int32_t K, int32_t lda, int32_t ldw, int32_t ldc, int32_t ldr, int32_t flags,
                        const int64_t* rope_pos, const float* rope_table, int32_t rope_cols, int32_t rope_max_pos,
-                       void* stream);
+                       void* workspace, size_t workspace_bytes, void* stream);
+/* workspace (optional, device memory, >= 16 KiB, ZERO-FILLED once by the caller, private to the stream): enables
+ * split-K for grids smaller than the machine — first 16 KiB are self-resetting tile counters, the rest holds fp32
+ * partial tiles.  NULL => never split. */
 int s3r_rope_table(float* table /* [(max_pos+1)*16*2] */, int32_t max_pos, float base, void* stream);
 
 /* ------------------------------------------------------------------------

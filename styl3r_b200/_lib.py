@@ -83,7 +83,7 @@ def lib():
     L.s3r_gaussian_adapter.argtypes = [C.c_void_p] * 4 + [C.c_int32] * 5 + [C.c_float] + [C.c_void_p] * 7
     L.s3r_gemm_bf16.argtypes = [C.c_void_p] * 5 + [C.c_int32] * 8 + [C.c_void_p]
     L.s3r_gemm_bf16_rope.argtypes = [C.c_void_p] * 5 + [C.c_int32] * 8 + [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
-                                                                          C.c_void_p]
+                                                                          C.c_void_p, C.c_size_t, C.c_void_p]
     L.s3r_rope_table.argtypes = [C.c_void_p, C.c_int32, C.c_float, C.c_void_p]
     L.s3r_attention_bf16.argtypes = [C.c_void_p] * 4 + [C.c_int32] * 5 + [C.POINTER(C.c_int64)] * 4 + [C.c_float, C.c_void_p]
     L.s3r_se3_update_w2c.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]

@@ -121,7 +121,8 @@ template <int BN, int STAGES_>
 __global__ void __launch_bounds__(GEMM_THREADS, (STAGES_ * (GEMM_BM + BN) * GEMM_BK * 2 <= 100 * 1024) ? 2 : 1)
 s3r_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const __nv_bfloat16* __restrict__ bias, const __nv_bfloat16* __restrict__ residual, void* __restrict__ Cout,
-                     int M, int N, int K, int ldc, int ldr, int flags, RopeArgs rope) {
+                     int M, int N, int K, int ldc, int ldr, int flags, RopeArgs rope, int splits, float* __restrict__ ws,
+                     unsigned* __restrict__ counters) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);  // SWIZZLE_128B atoms need 1024-B alignment
   using S = GemmSmem<BN, STAGES_>;
@@ -130,10 +131,15 @@ s3r_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   uint64_t* empty = full + GEMM_STAGES;
   uint64_t* tmem_full = empty + GEMM_STAGES;
   uint32_t* tmem_slot = (uint32_t*)(tmem_full + 1);
+  uint32_t* s_ticket = tmem_slot + 1;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * GEMM_BM, n0 = blockIdx.y * BN;
-  const int num_kb = (K + GEMM_BK - 1) / GEMM_BK;
+  const int total_kb = (K + GEMM_BK - 1) / GEMM_BK;
+  // split-K: CTA z owns k-blocks [kb0, kb0 + num_kb); partial tiles meet in an fp32 workspace and the last CTA to
+  // arrive for an output tile sums them (fixed order => deterministic) and runs the fused epilogue
+  const int kb0 = (int)((long long)blockIdx.z * total_kb / splits);
+  const int num_kb = (int)((long long)(blockIdx.z + 1) * total_kb / splits) - kb0;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -163,8 +169,8 @@ s3r_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         uint8_t* a_dst = smem + s * S::STAGE_BYTES;
         uint8_t* b_dst = a_dst + S::A_BYTES;
         g_mbar_expect_tx(&full[s], S::STAGE_BYTES);
-        g_tma_load_2d(a_dst, &tmA, kb * GEMM_BK, m0, &full[s]);
-        g_tma_load_2d(b_dst, &tmB, kb * GEMM_BK, n0, &full[s]);
+        g_tma_load_2d(a_dst, &tmA, (kb0 + kb) * GEMM_BK, m0, &full[s]);
+        g_tma_load_2d(b_dst, &tmB, (kb0 + kb) * GEMM_BK, n0, &full[s]);
       }
     }
   } else if (warp == 1) {
@@ -184,83 +190,167 @@ s3r_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       g_umma_commit(tmem_full);  // accumulator complete
     }
   } else {
-    // ===== epilogue warps: TMEM lane quarter = warp % 4
+    // ===== epilogue warps (TMEM lane quarter = warp % 4)
+    // phase 1: TMEM -> registers -> fp32 staging tile in shared memory (the TMA ring is idle once tmem_full fires);
+    // phase 2: the 128 threads walk the tile row-wise, 4 consecutive columns per lane, so that every global access
+    //          (partials, bias, residual, output) is a fully coalesced 256/512-byte row segment.
     const int q = warp & 3;
+    const int et = threadIdx.x - 64;  // 0..127
+    constexpr int LDS_ = BN + 4;      // padded row pitch (floats): conflict-free for both phases
+    float* stage = reinterpret_cast<float*>(smem);
+    int* spos = reinterpret_cast<int*>(smem + GEMM_STAGES * S::STAGE_BYTES - 2048);  // [128][2] row positions (RoPE)
     g_mbar_wait(tmem_full, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const int row = m0 + q * 32 + lane;
-    const bool has_bias = flags & S3R_EPI_BIAS, gelu = flags & S3R_EPI_GELU, has_res = flags & S3R_EPI_RESIDUAL,
-               out_f32 = flags & S3R_EPI_OUT_F32;
-#pragma unroll 1
-    for (int c = 0; c < BN / 32; c++) {
-      uint32_t v[32];
-      g_tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
-      const int col0 = n0 + c * 32;
-      if (row < M && col0 < N) {
-        float f[32];
-#pragma unroll
-        for (int j = 0; j < 32; j++) f[j] = __uint_as_float(v[j]);
-        if (has_bias) {
-#pragma unroll
-          for (int j = 0; j < 32; j++)
-            if (col0 + j < N) f[j] += __bfloat162float(bias[col0 + j]);
+    {
+      if (flags & S3R_EPI_ROPE) {  // one coalesced read of this tile's 128 (y, x) positions, clamped to the table
+        const int prow = m0 + q * 32 + lane;
+        long long py = 0, px = 0;
+        if (prow < M) {
+          py = rope.pos[(size_t)prow * 2];
+          px = rope.pos[(size_t)prow * 2 + 1];
         }
-        if ((flags & S3R_EPI_ROPE) && col0 < rope.cols) {
-          // this 32-column chunk is one half (y: even chunk, x: odd chunk) of one 64-wide head: pairs (d, d + 16)
-          long long pp = rope.pos[(size_t)row * 2 + ((col0 >> 5) & 1)];
-          pp = pp < 0 ? 0 : (pp > rope.max_pos ? rope.max_pos : pp);
-          const float2* tb = rope.table + pp * 16;
+        spos[(q * 32 + lane) * 2] = (int)(py < 0 ? 0 : (py > rope.max_pos ? rope.max_pos : py));
+        spos[(q * 32 + lane) * 2 + 1] = (int)(px < 0 ? 0 : (px > rope.max_pos ? rope.max_pos : px));
+      }
+      float* srow = stage + (size_t)(q * 32 + lane) * LDS_;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; c++) {
+        uint32_t v[32];
+        g_tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
 #pragma unroll
-          for (int d = 0; d < 16; d++) {
-            const float2 cs = __ldg(tb + d);
-            const float u = f[d], w = f[d + 16];
-            f[d] = u * cs.x - w * cs.y;
-            f[d + 16] = w * cs.x + u * cs.y;
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(srow + c * 32 + j) =
+              make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+      }
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    constexpr int LPR = BN / 4;        // lanes per row
+    constexpr int RPI = 128 / LPR;     // rows per iteration of the 128 epilogue threads
+    const int cl = (et % LPR) * 4;     // this lane's first column inside the tile
+    const int col = n0 + cl;
+    const bool has_bias = flags & S3R_EPI_BIAS, gelu = flags & S3R_EPI_GELU, has_res = flags & S3R_EPI_RESIDUAL,
+               out_f32 = flags & S3R_EPI_OUT_F32, do_rope = (flags & S3R_EPI_ROPE) && col < rope.cols;
+    const bool full4 = col + 4 <= N;
+    float bias4[4] = {0.f, 0.f, 0.f, 0.f};
+    if (has_bias) {
+#pragma unroll
+      for (int j = 0; j < 4; j++)
+        if (col + j < N) bias4[j] = __bfloat162float(bias[col + j]);
+    }
+    auto finish = [&](float (&f)[4], int row) {  // f = accumulators of columns col..col+3 of `row`
+#pragma unroll
+      for (int j = 0; j < 4; j++) f[j] += bias4[j];
+      if (flags & S3R_EPI_ROPE) {
+        // pairs (d, d+16) inside each 32-column half head sit 4 lanes apart: exchange with lane ^ 4 (all lanes shuffle)
+        float o[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) o[j] = __shfl_xor_sync(0xffffffffu, f[j], 4);
+        if (do_rope && row < M) {
+          const int pp = spos[(row - m0) * 2 + ((col >> 5) & 1)];
+          const int d0 = col & 15;
+          const bool lower = (col & 16) == 0;  // this lane holds u (d < 16) or v (d >= 16)
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            const float2 cs = __ldg(rope.table + pp * 16 + d0 + j);
+            f[j] = lower ? (f[j] * cs.x - o[j] * cs.y) : (f[j] * cs.x + o[j] * cs.y);
           }
         }
-        if (gelu) {
+      }
+      if (gelu) {
 #pragma unroll
-          for (int j = 0; j < 32; j++) f[j] = 0.5f * f[j] * (1.0f + erff(f[j] * 0.70710678118654752f));
-        }
+        for (int j = 0; j < 4; j++) f[j] = 0.5f * f[j] * (1.0f + erff(f[j] * 0.70710678118654752f));
+      }
+      if (row < M && col < N) {
         if (has_res) {
-          const __nv_bfloat16* rp = residual + (size_t)row * ldr + col0;
-          if (col0 + 32 <= N) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              const uint4 u = *reinterpret_cast<const uint4*>(rp + j);
-              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-              for (int t = 0; t < 4; t++) {
-                const float2 r2 = __bfloat1622float2(h[t]);
-                f[j + 2 * t] += r2.x;
-                f[j + 2 * t + 1] += r2.y;
-              }
-            }
+          const __nv_bfloat16* rp = residual + (size_t)row * ldr + col;
+          if (full4) {
+            const uint2 u = *reinterpret_cast<const uint2*>(rp);
+            const float2 r0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+            const float2 r1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+            f[0] += r0.x; f[1] += r0.y; f[2] += r1.x; f[3] += r1.y;
           } else {
-            for (int j = 0; j < 32 && col0 + j < N; j++) f[j] += __bfloat162float(rp[j]);
+            for (int j = 0; j < 4 && col + j < N; j++) f[j] += __bfloat162float(rp[j]);
           }
         }
         if (out_f32) {
-          float* op = (float*)Cout + (size_t)row * ldc + col0;
-          if (col0 + 32 <= N) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(op + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-          } else {
-            for (int j = 0; j < 32 && col0 + j < N; j++) op[j] = f[j];
-          }
+          float* op = (float*)Cout + (size_t)row * ldc + col;
+          if (full4) *reinterpret_cast<float4*>(op) = make_float4(f[0], f[1], f[2], f[3]);
+          else for (int j = 0; j < 4 && col + j < N; j++) op[j] = f[j];
         } else {
-          __nv_bfloat16* op = (__nv_bfloat16*)Cout + (size_t)row * ldc + col0;
-          if (col0 + 32 <= N) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              uint4 u;
-              __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
-#pragma unroll
-              for (int t = 0; t < 4; t++) h[t] = __floats2bfloat162_rn(f[j + 2 * t], f[j + 2 * t + 1]);
-              *reinterpret_cast<uint4*>(op + j) = u;
-            }
+          __nv_bfloat16* op = (__nv_bfloat16*)Cout + (size_t)row * ldc + col;
+          if (full4) {
+            uint2 u;
+            *reinterpret_cast<__nv_bfloat162*>(&u.x) = __floats2bfloat162_rn(f[0], f[1]);
+            *reinterpret_cast<__nv_bfloat162*>(&u.y) = __floats2bfloat162_rn(f[2], f[3]);
+            *reinterpret_cast<uint2*>(op) = u;
           } else {
-            for (int j = 0; j < 32 && col0 + j < N; j++) op[j] = __float2bfloat16_rn(f[j]);
+            for (int j = 0; j < 4 && col + j < N; j++) op[j] = __float2bfloat16_rn(f[j]);
+          }
+        }
+      }
+    };
+    if (splits == 1) {
+#pragma unroll 2
+      for (int r = et / LPR; r < GEMM_BM; r += RPI) {
+        const float4 t = *reinterpret_cast<const float4*>(stage + (size_t)r * LDS_ + cl);
+        float f[4] = {t.x, t.y, t.z, t.w};
+        finish(f, m0 + r);
+      }
+    } else {
+      // ---- split-K, phase A: park this CTA's partial tile in the workspace (coalesced)
+      for (int r = et / LPR; r < GEMM_BM; r += RPI) {
+        const int row = m0 + r;
+        if (row < M && col < N) {
+          const float4 t = *reinterpret_cast<const float4*>(stage + (size_t)r * LDS_ + cl);
+          float* wp = ws + ((size_t)blockIdx.z * M + row) * N + col;
+          if (full4) __stcg(reinterpret_cast<float4*>(wp), t);
+          else {
+            const float tt[4] = {t.x, t.y, t.z, t.w};
+            for (int j = 0; j < 4 && col + j < N; j++) __stcg(wp + j, tt[j]);
+          }
+        }
+      }
+      // release: the CTA barrier orders the 128 threads' partial stores before ONE gpu-scope fence + ticket atomic
+      // (fences are cumulative); acquire on the other side the same way; partials are read with ld.cg (L2)
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (threadIdx.x == 64) {
+        __threadfence();
+        const unsigned t = atomicAdd(&counters[blockIdx.y * gridDim.x + blockIdx.x], 1u);
+        __threadfence();
+        if (t == (unsigned)splits - 1) counters[blockIdx.y * gridDim.x + blockIdx.x] = 0u;  // ready for the next launch
+        *s_ticket = t;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (*s_ticket == (uint32_t)splits - 1) {
+        // ---- phase B (last CTA of this tile): sum the partials in split order, then the fused epilogue.
+        // 4 rows x up to 8 splits of independent ld.cg are put in flight together (a dependent load per split and
+        // row would cost one L2 round trip each: 16 x splits x ~0.3 us)
+        constexpr int RB = 2;
+        for (int rb = et / LPR; rb < GEMM_BM; rb += RPI * RB) {
+          float4 part[RB][8];
+#pragma unroll
+          for (int i = 0; i < RB; i++) {
+            const int row = m0 + rb + i * RPI;
+#pragma unroll
+            for (int z = 0; z < 8; z++) {
+              part[i][z] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (z < splits && row < M && full4)
+                part[i][z] = __ldcg(reinterpret_cast<const float4*>(ws + ((size_t)z * M + row) * N + col));
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < RB; i++) {
+            const int row = m0 + rb + i * RPI;
+            float f[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int z = 0; z < 8; z++) {
+              f[0] += part[i][z].x; f[1] += part[i][z].y; f[2] += part[i][z].z; f[3] += part[i][z].w;
+            }
+            if (!full4 && row < M && col < N) {  // ragged N tail: scalar path
+              for (int z = 0; z < splits; z++)
+                for (int j = 0; j < 4 && col + j < N; j++) f[j] += __ldcg(ws + ((size_t)z * M + row) * N + col + j);
+            }
+            finish(f, row);
           }
         }
       }
@@ -308,17 +398,18 @@ static int make_map(CUtensorMap* map, const void* ptr, int rows, int cols, int l
 
 template <int BN, int STAGES_>
 static int launch_gemm(const CUtensorMap& a, const CUtensorMap& b, const void* bias, const void* residual, void* C, int M,
-                       int N, int K, int ldc, int ldr, int flags, const RopeArgs& rope, cudaStream_t st) {
+                       int N, int K, int ldc, int ldr, int flags, const RopeArgs& rope, int splits, float* ws, unsigned* counters,
+                       cudaStream_t st) {
   static bool configured = false;
   const int smem = GemmSmem<BN, STAGES_>::TOTAL;
   if (!configured) {
     S3R_CUDA_CHECK(cudaFuncSetAttribute(s3r_gemm_bf16_kernel<BN, STAGES_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  dim3 grid((M + GEMM_BM - 1) / GEMM_BM, (N + BN - 1) / BN);
+  dim3 grid((M + GEMM_BM - 1) / GEMM_BM, (N + BN - 1) / BN, splits);
   s3r_gemm_bf16_kernel<BN, STAGES_><<<grid, GEMM_THREADS, smem, st>>>(a, b, (const __nv_bfloat16*)bias,
                                                                       (const __nv_bfloat16*)residual, C, M, N, K, ldc, ldr,
-                                                                      flags, rope);
+                                                                      flags, rope, splits, ws, counters);
   S3R_CUDA_CHECK(cudaGetLastError());
   return S3R_OK;
 }
@@ -345,7 +436,7 @@ extern "C" int s3r_rope_table(float* table, int32_t max_pos, float base, void* s
 extern "C" int s3r_gemm_bf16_rope(const void* A, const void* W, const void* bias, const void* residual, void* C, int32_t M,
                                   int32_t N, int32_t K, int32_t lda, int32_t ldw, int32_t ldc, int32_t ldr, int32_t flags,
                                   const int64_t* rope_pos, const float* rope_table, int32_t rope_cols,
-                                  int32_t rope_max_pos, void* stream) {
+                                  int32_t rope_max_pos, void* workspace, size_t workspace_bytes, void* stream) {
   if (M < 0 || N <= 0 || K <= 0) return S3R_ERR_INVALID_ARG;
   if (M == 0) return S3R_OK;
   if (!A || !W || !C) return S3R_ERR_INVALID_ARG;
@@ -368,16 +459,37 @@ extern "C" int s3r_gemm_bf16_rope(const void* A, const void* W, const void* bias
   if ((rc = make_map(&ta, A, M, K, lda, GEMM_BM)) != S3R_OK) return rc;
   if ((rc = make_map(&tb, W, N, K, ldw, BN)) != S3R_OK) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  if (BN == 64) {
-    if (tiles64 < 148) return launch_gemm<64, 8>(ta, tb, bias, residual, C, M, N, K, ldc, ldr, flags, rope, st);
-    return launch_gemm<64, 4>(ta, tb, bias, residual, C, M, N, K, ldc, ldr, flags, rope, st);
+  // split-K for grids smaller than the machine: every SM pulls ~45 B/cycle from L2, so a 36-CTA grid streams its
+  // operands at a quarter of the chip's L2 bandwidth; more CTAs with shorter K ranges fix exactly that.
+  // workspace = [4096 tile counters (uint32, zero on first use, self-resetting)] [splits x M x N fp32 partials]
+  int splits = 1;
+  float* ws = nullptr;
+  unsigned* counters = nullptr;
+  if (BN == 64 && workspace && tiles64 < 120 && tiles64 <= 4096) {
+    const int total_kb = (K + GEMM_BK - 1) / GEMM_BK;
+    int want = (int)((144 + tiles64 - 1) / tiles64);
+    want = want > 8 ? 8 : want;
+    want = want > total_kb / 2 ? total_kb / 2 : want;
+    const size_t per = (size_t)M * N * sizeof(float);
+    while (want > 1 && 16384 + per * want > workspace_bytes) want--;
+    if (want > 1) {
+      splits = want;
+      counters = (unsigned*)workspace;
+      ws = (float*)((char*)workspace + 16384);
+    }
   }
-  return launch_gemm<128, 3>(ta, tb, bias, residual, C, M, N, K, ldc, ldr, flags, rope, st);
+  if (BN == 64) {
+    if (tiles64 * splits < 148)
+      return launch_gemm<64, 8>(ta, tb, bias, residual, C, M, N, K, ldc, ldr, flags, rope, splits, ws, counters, st);
+    return launch_gemm<64, 4>(ta, tb, bias, residual, C, M, N, K, ldc, ldr, flags, rope, splits, ws, counters, st);
+  }
+  return launch_gemm<128, 3>(ta, tb, bias, residual, C, M, N, K, ldc, ldr, flags, rope, 1, nullptr, nullptr, st);
 }
 
 extern "C" int s3r_gemm_bf16(const void* A, const void* W, const void* bias, const void* residual, void* C, int32_t M,
                              int32_t N, int32_t K, int32_t lda, int32_t ldw, int32_t ldc, int32_t ldr, int32_t flags,
                              void* stream) {
   if (flags & S3R_EPI_ROPE) return S3R_ERR_INVALID_ARG;
-  return s3r_gemm_bf16_rope(A, W, bias, residual, C, M, N, K, lda, ldw, ldc, ldr, flags, nullptr, nullptr, 0, 0, stream);
+  return s3r_gemm_bf16_rope(A, W, bias, residual, C, M, N, K, lda, ldw, ldc, ldr, flags, nullptr, nullptr, 0, 0, nullptr, 0,
+                            stream);
 }

@@ -17,6 +17,18 @@ from . import _lib
 EPI_BIAS, EPI_GELU, EPI_RESIDUAL, EPI_OUT_F32, EPI_ROPE = 1, 2, 4, 8, 16
 ROPE_MAX_POS = 255  # positions are patch-grid coordinates (16 for 256 px, 64 for 1024 px)
 _rope_tables: dict = {}
+_workspaces: dict = {}
+WORKSPACE_BYTES = 16384 + 32 * 1024 * 1024
+
+
+def _workspace(device) -> torch.Tensor:
+    """Split-K scratch, private to (device, current stream): 16 KiB of zeroed tile counters + fp32 partial tiles."""
+    key = (str(device), torch.cuda.current_stream(device).cuda_stream)
+    w = _workspaces.get(key)
+    if w is None:
+        w = torch.zeros(WORKSPACE_BYTES, dtype=torch.uint8, device=device)
+        _workspaces[key] = w
+    return w
 
 
 def rope_table(device, base: float) -> torch.Tensor:
@@ -33,9 +45,13 @@ def rope_table(device, base: float) -> torch.Tensor:
 
 def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None,
            residual: Optional[torch.Tensor] = None, gelu: bool = False, out_dtype: torch.dtype = torch.bfloat16,
-           rope_pos: Optional[torch.Tensor] = None, rope_cols: int = 0, rope_base: float = 100.0):
+           rope_pos: Optional[torch.Tensor] = None, rope_cols: int = 0, rope_base: float = 100.0,
+           split_k: bool = False):
     """rope_pos [..., 2] int64 (one (y, x) per row of x) + rope_cols: RoPE-2D (head_dim 64) is applied to output columns
-    [0, rope_cols) inside the GEMM epilogue (q and k parts of a qkv projection), replacing a separate rope pass."""
+    [0, rope_cols) inside the GEMM epilogue (q and k parts of a qkv projection), replacing a separate rope pass.
+    split_k: let grids smaller than the machine split the K range over several CTAs (deterministic last-CTA fix-up
+    through an fp32 workspace).  Off by default: on B200 the extra L2 round trips of the fix-up (partials, fence, ticket)
+    cost more than the shorter K loops save for the M = 257/514 shapes measured (scripts/bench_gemm.py)."""
     if x.device.type != "cuda":
         raise _lib.S3RError("styl3r_b200.gemm.linear needs CUDA tensors (no CPU fallback)")
     if x.dtype != torch.bfloat16 or weight.dtype != torch.bfloat16:
@@ -77,9 +93,12 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] =
         flags |= EPI_OUT_F32
     elif out_dtype != torch.bfloat16:
         raise _lib.S3RError("out_dtype must be bf16 or fp32")
+    ws = _workspace(x.device) if split_k else None
     _lib.check(_lib.lib().s3r_gemm_bf16_rope(C.c_void_p(x2.data_ptr()), C.c_void_p(w.data_ptr()), bp, rp,
                                              C.c_void_p(out.data_ptr()), M, N, K, x2.stride(0), w.stride(0),
                                              out.stride(0), ldr, flags, pp, tp, int(rope_cols), ROPE_MAX_POS,
+                                             None if ws is None else C.c_void_p(ws.data_ptr()),
+                                             0 if ws is None else ws.numel(),
                                              C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)),
                "s3r_gemm_bf16")
     return out.reshape(*lead, N)

@@ -75,3 +75,22 @@ def test_gemm_with_fused_rope_epilogue_matches_gemm_then_rope_oracle(M, H):
     # the v third is untouched by the rotation
     np.testing.assert_allclose(y.float().cpu().numpy().reshape(1, M, 3, H, 64)[:, :, 2], ref[:, :, 2],
                                atol=1e-2 * np.abs(ref).max())
+
+
+@pytest.mark.parametrize("M,N,K", [(257, 768, 768), (514, 1024, 4096), (130, 200, 520)])
+def test_gemm_split_k_path_is_deterministic_and_correct(M, N, K):
+    import torch
+    from styl3r_b200.gemm import linear
+    torch.manual_seed(K)
+    x = (torch.randn(M, K, device="cuda") * 0.5).to(torch.bfloat16)
+    w = (torch.randn(N, K, device="cuda") * K ** -0.5).to(torch.bfloat16)
+    b = (torch.randn(N, device="cuda") * 0.1).to(torch.bfloat16)
+    r = torch.randn(M, N, device="cuda").to(torch.bfloat16)
+    y1 = linear(x, w, b, r, gelu=True, split_k=True)
+    y2 = linear(x, w, b, r, gelu=True, split_k=True)   # counters self-reset; fixed summation order
+    y0 = linear(x, w, b, r, gelu=True, split_k=False)
+    torch.cuda.synchronize()
+    expect = ref(x, w, b, r, True)
+    assert torch.equal(y1, y2)
+    assert (y1.float() - expect).abs().max() <= 1e-2 * expect.abs().max()
+    assert (y0.float() - expect).abs().max() <= 1e-2 * expect.abs().max()
