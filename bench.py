@@ -293,7 +293,7 @@ def run_ours(args):
             traffic = None
 
     # ---- e2e through the public API with pinned host buffers
-    Ke = K
+    Ke = min(K, 1000)
     host = []
     for s in slots:
         sc = s["sc"]
@@ -419,8 +419,8 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--slots", type=int, default=16)
     ap.add_argument("--e2e-streams", type=int, default=4, help="streams pipelining independent e2e requests")
