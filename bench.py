@@ -389,6 +389,31 @@ def run_ours(args):
         except Exception as e:  # supplementary only
             enc_info = {"error": repr(e)[:200]}
 
+    # ---- supplementary: measured GPU comparator (upstream-style stand-in, baseline/upstream_style) on slot 0
+    standin = None
+    if rank == 0 and world == 1 and not args.no_standin:
+        try:
+            from baseline import upstream_style as ups
+            g0 = slots[0]["g"]
+            bg0 = torch.zeros(V_TGT, 3, device=dev)
+            fn = lambda: ups.render_cuda_upstream_style(g0["extr"], g0["intr"], g0["near"], g0["far"], (HW, HW), bg0,
+                                                        g0["means"], g0["cov"], g0["sh"], g0["opac"])
+            with torch.no_grad():
+                for _ in range(3):
+                    fn()
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                for _ in range(30):
+                    fn()
+                torch.cuda.synchronize()
+                dt = (time.perf_counter() - t0) / 30
+            standin = {"views_per_s": V_TGT / dt, "what": "upstream-style stand-in (per-view launch chain, CUB scan + 64-bit "
+                       "radix sort, D2H num_rendered, scalar 16x16 render, reference-style Python loop) on the same "
+                       "GPU and inputs; parity unpinned; the un-vendored upstream rasterizer cannot be built here",
+                       "value_over_standin": value / (V_TGT / dt)}
+        except Exception as e:
+            standin = {"error": repr(e)[:200]}
+
     if rank == 0:
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": "views/s", "n_gpus": world, "steps": K, "warmup": Wm,
@@ -411,6 +436,7 @@ def run_ours(args):
             "stage_ms": stage_ms,
             "cpu_baseline": cb,
             "encoder": enc_info,
+            "upstream_style_standin": standin,
         }))
     if dist is not None:
         dist.destroy_process_group()
@@ -426,6 +452,7 @@ def main():
     ap.add_argument("--e2e-streams", type=int, default=4, help="streams pipelining independent e2e requests")
     ap.add_argument("--streams", type=int, default=8, help="concurrent streams over independent scenes")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-standin", action="store_true", help="skip the upstream-style GPU comparator leg")
     ap.add_argument("--with-encoder", action="store_true", help="also time the encoder (supplementary key)")
     args = ap.parse_args()
     if args.impl == "reference":

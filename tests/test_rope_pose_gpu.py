@@ -166,3 +166,22 @@ def test_render_session_matches_render_cuda_and_detects_overflow():
     torch.cuda.synchronize()
     with pytest.raises(S3RError):
         small.check()
+
+
+def test_upstream_style_standin_agrees_with_oracle():
+    """The GPU comparator used by bench.py renders the same image as the CPU oracle (same algorithm, nvcc-fused math):
+    it is a fair stand-in, not a straw man."""
+    import torch
+    from baseline import upstream_style as ups
+    from styl3r_b200 import synthetic as syn
+    from tests.helpers import oracle_scene
+    sc = syn.make_scene(seed=5, v=2, V=2, hw=64)
+    outs, _ = oracle_scene(sc)
+    t = lambda a: torch.as_tensor(a).cuda()
+    rep = lambda a: t(a)[None].expand(2, *a.shape).contiguous()
+    img, dep = ups.render_cuda_upstream_style(t(sc["extrinsics"]), t(sc["intrinsics"]), t(sc["near"]), t(sc["far"]), (64, 64),
+                                              torch.zeros(2, 3, device="cuda"), rep(sc["means"]), rep(sc["covariances"]),
+                                              rep(sc["harmonics"]), rep(sc["opacities"]))
+    for v, o in enumerate(outs):
+        err = np.abs(img[v].cpu().numpy() - o["color"])
+        assert np.mean(err > 1e-4) < 5e-3 and np.median(err) < 1e-5
