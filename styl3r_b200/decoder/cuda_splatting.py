@@ -93,7 +93,7 @@ def _render(extrinsics, tan_fov, projection, near_scale, image_shape, background
     proj_t = projection.transpose(1, 2)                 # handed over transposed (reference :86)
     view_t = extrinsics.inverse().transpose(1, 2)       # (:87)
     full = view_t @ proj_t                              # (:88)
-    degree = isqrt(sh.shape[-1]) - 1
+    degree = min(isqrt(sh.shape[-1]) - 1, 3)  # coefficients beyond degree 3 are stored but not evaluated (as upstream)
     shs = _sh_layout(sh)
     kw = dict(shs=shs) if use_sh else dict(colors_precomp=shs[:, :, 0, :])
     color, depth, opacity, radii, n_touched = _rz.rasterize(

@@ -1,0 +1,141 @@
+"""GPU: the drop-in module shims behave like the interfaces the reference binds
+(src/model/decoder/cuda_splatting.py:5-8,93-133: per-view GaussianRasterizer calls inside render_cuda's loop)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _reference_style_render_loop(sc, cam_rot_delta=None, cam_trans_delta=None):
+    """The reference's render_cuda body, verbatim in structure, on top of the *shim* module: scaled copies, torch
+    camera set-up, per-view settings with .item(), cov gathered with triu_indices, theta/rho per view."""
+    import torch
+    from styl3r_b200.compat.diff_gaussian_rasterization import GaussianRasterizationSettings, GaussianRasterizer
+    from styl3r_b200.decoder.cuda_splatting import get_fov, get_projection_matrix
+    t = lambda a: torch.as_tensor(a).cuda()
+    extr, intr, near, far = t(sc["extrinsics"]), t(sc["intrinsics"]), t(sc["near"]), t(sc["far"])
+    b = extr.shape[0]
+    h, w = sc["image_shape"]
+    means = t(sc["means"])[None].expand(b, -1, -1).clone().requires_grad_()
+    cov = t(sc["covariances"])[None].expand(b, -1, -1, -1).clone().requires_grad_()
+    sh = t(sc["harmonics"])[None].expand(b, -1, -1, -1).clone().requires_grad_()
+    op = t(sc["opacities"])[None].expand(b, -1).clone().requires_grad_()
+    scale = 1 / near
+    extr = extr.clone()
+    extr[..., :3, 3] = extr[..., :3, 3] * scale[:, None]
+    covs = cov * (scale[:, None, None, None] ** 2)
+    ms = means * scale[:, None, None]
+    near, far = near * scale, far * scale
+    shs = sh.permute(0, 1, 3, 2).contiguous()
+    fov_x, fov_y = get_fov(intr).unbind(dim=-1)
+    tan_x, tan_y = (0.5 * fov_x).tan(), (0.5 * fov_y).tan()
+    proj = get_projection_matrix(near, far, fov_x, fov_y).transpose(1, 2)
+    view = extr.inverse().transpose(1, 2)
+    full = view @ proj
+    images, depths = [], []
+    for i in range(b):
+        mean_gradients = torch.zeros_like(ms[i], requires_grad=True)
+        settings = GaussianRasterizationSettings(
+            image_height=h, image_width=w, tanfovx=tan_x[i].item(), tanfovy=tan_y[i].item(),
+            bg=torch.zeros(3, device="cuda"), scale_modifier=1.0, viewmatrix=view[i], projmatrix=full[i],
+            projmatrix_raw=proj[i], sh_degree=0, campos=extr[i, :3, 3], prefiltered=False, debug=False)
+        rasterizer = GaussianRasterizer(settings)
+        row, col = torch.triu_indices(3, 3)
+        image, radii, depth, opacity, n_touched = rasterizer(
+            means3D=ms[i], means2D=mean_gradients, shs=shs[i], colors_precomp=None, opacities=op[i, ..., None],
+            cov3D_precomp=covs[i, :, row, col],
+            theta=cam_rot_delta[i] if cam_rot_delta is not None else None,
+            rho=cam_trans_delta[i] if cam_trans_delta is not None else None)
+        assert image.shape == (3, h, w) and depth.shape == (1, h, w) and opacity.shape == (1, h, w)
+        assert radii.shape == (ms.shape[1],) and n_touched.shape == (ms.shape[1],)
+        images.append(image)
+        depths.append(depth.squeeze(0))
+    return torch.stack(images), torch.stack(depths), (means, cov, sh, op)
+
+
+def test_reference_style_per_view_loop_on_the_shim_matches_batched_render_cuda():
+    import torch
+    from styl3r_b200 import synthetic as syn
+    from styl3r_b200.decoder import render_cuda
+    sc = syn.make_scene(seed=31, v=2, V=3, hw=64)
+    rot = torch.zeros(3, 3, device="cuda", requires_grad=True)
+    trans = torch.zeros(3, 3, device="cuda", requires_grad=True)
+    img, dep, leaves = _reference_style_render_loop(sc, rot, trans)
+    w_img = torch.randn_like(img)
+    (img * w_img).sum().backward()
+    t = lambda a: torch.as_tensor(a).cuda()
+    m2 = t(sc["means"])[None].requires_grad_()
+    c2 = t(sc["covariances"])[None].requires_grad_()
+    s2 = t(sc["harmonics"])[None].requires_grad_()
+    o2 = t(sc["opacities"])[None].requires_grad_()
+    rot2 = torch.zeros(3, 3, device="cuda", requires_grad=True)
+    trans2 = torch.zeros(3, 3, device="cuda", requires_grad=True)
+    img2, dep2 = render_cuda(t(sc["extrinsics"]), t(sc["intrinsics"]), t(sc["near"]), t(sc["far"]), (64, 64),
+                             torch.zeros(3, 3, device="cuda"), m2, c2, s2, o2, cam_rot_delta=rot2, cam_trans_delta=trans2,
+                             view_set=torch.zeros(3, dtype=torch.int32, device="cuda"))
+    (img2 * w_img).sum().backward()
+    # camera matrices come from torch ops in one path and from s3r_camera_setup in the other: last-bit differences
+    assert (img - img2).abs().max() < 5e-3 and (img - img2).abs().median() < 1e-6
+    assert (dep - dep2).abs().median() < 1e-4
+    scale = lambda x: x.abs().max().item() + 1e-12
+    means, cov, sh, op = leaves
+    for name, a, b_ in [("means", means.grad.sum(0), m2.grad[0]), ("sh", sh.grad.sum(0), s2.grad[0]),
+                        ("op", op.grad.sum(0), o2.grad[0]), ("rot", rot.grad, rot2.grad), ("trans", trans.grad, trans2.grad)]:
+        assert (a - b_).abs().max().item() <= 2e-2 * scale(b_), name
+    # the reference gathers the upper triangle: gradient only there
+    g = cov.grad.sum(0)
+    assert (g[:, [1, 2, 2], [0, 0, 1]] == 0).all()
+    assert (g - c2.grad[0]).abs().max().item() <= 2e-2 * scale(c2.grad[0])
+
+
+def test_shim_scale_rotation_path_and_mark_visible():
+    import torch
+    from styl3r_b200.compat.diff_gaussian_rasterization import GaussianRasterizationSettings, GaussianRasterizer
+    torch.manual_seed(0)
+    P = 500
+    means = torch.randn(P, 3, device="cuda") * 0.5 + torch.tensor([0, 0, 4.0], device="cuda")
+    scales = torch.rand(P, 3, device="cuda") * 0.05 + 0.01
+    rots = torch.nn.functional.normalize(torch.randn(P, 4, device="cuda"), dim=-1)  # (w, x, y, z) upstream order
+    colors = torch.rand(P, 3, device="cuda")
+    op = torch.rand(P, 1, device="cuda")
+    view = torch.eye(4, device="cuda")
+    proj = torch.tensor([[1.0, 0, 0, 0], [0, 1.0, 0, 0], [0, 0, 100 / 99.9, -10 / 99.9], [0, 0, 1.0, 0]], device="cuda").t()
+    s = GaussianRasterizationSettings(64, 64, 1.0, 1.0, torch.zeros(3, device="cuda"), 1.0, view, view @ proj, proj, 0,
+                                      torch.zeros(3, device="cuda"), False, False)
+    r = GaussianRasterizer(s)
+    img, radii, depth, opacity, n_touched = r(means, torch.zeros_like(means), op, colors_precomp=colors, scales=scales,
+                                              rotations=rots)
+    R = torch.zeros(P, 3, 3, device="cuda")
+    w_, x, y, z = rots.unbind(-1)
+    R[:, 0, 0] = 1 - 2 * (y * y + z * z); R[:, 0, 1] = 2 * (x * y - w_ * z); R[:, 0, 2] = 2 * (x * z + w_ * y)
+    R[:, 1, 0] = 2 * (x * y + w_ * z); R[:, 1, 1] = 1 - 2 * (x * x + z * z); R[:, 1, 2] = 2 * (y * z - w_ * x)
+    R[:, 2, 0] = 2 * (x * z - w_ * y); R[:, 2, 1] = 2 * (y * z + w_ * x); R[:, 2, 2] = 1 - 2 * (x * x + y * y)
+    M = R * scales[:, None, :]
+    cov = M @ M.transpose(1, 2)
+    i, j = torch.triu_indices(3, 3)
+    img2, *_ = r(means, torch.zeros_like(means), op, colors_precomp=colors, cov3D_precomp=cov[:, i, j])
+    assert torch.allclose(img, img2, atol=1e-5) and img.abs().sum() > 0
+    vis = r.markVisible(means)
+    assert vis.shape == (P,) and vis.dtype == torch.bool and vis.all()
+    with pytest.raises(Exception):
+        r(means, torch.zeros_like(means), op, colors_precomp=colors)  # neither scales/rotations nor cov
+
+
+def test_render_cuda_orthographic_and_sh_degree_4_layout():
+    import torch
+    from styl3r_b200 import synthetic as syn
+    from styl3r_b200.decoder import render_cuda, render_cuda_orthographic
+    sc = syn.make_scene(seed=4, v=2, V=2, hw=64, d_sh=25)  # config default sh_degree 4: 25 coefficients stored
+    t = lambda a: torch.as_tensor(a).cuda()
+    vs = torch.zeros(2, dtype=torch.int32, device="cuda")
+    args = (t(sc["means"])[None], t(sc["covariances"])[None], t(sc["harmonics"])[None], t(sc["opacities"])[None])
+    color, depth = render_cuda(t(sc["extrinsics"]), t(sc["intrinsics"]), t(sc["near"]), t(sc["far"]), (64, 64),
+                               torch.zeros(2, 3, device="cuda"), *args, view_set=vs)
+    assert torch.isfinite(color).all() and color.abs().sum() > 0
+    dump = {}
+    ortho = render_cuda_orthographic(t(sc["extrinsics"]), torch.full((2,), 6.0, device="cuda"),
+                                     torch.full((2,), 6.0, device="cuda"), torch.zeros(2, device="cuda"),
+                                     torch.full((2,), 20.0, device="cuda"), (64, 64), torch.zeros(2, 3, device="cuda"), *args,
+                                     dump=dump, view_set=vs)
+    assert ortho.shape == (2, 3, 64, 64) and torch.isfinite(ortho).all() and ortho.abs().sum() > 0
+    assert set(dump) == {"extrinsics", "fov_x", "fov_y", "near", "far"}
