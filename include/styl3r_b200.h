@@ -198,6 +198,7 @@ int s3r_rope2d(void* tokens, const int64_t* pos, int32_t B, int32_t N, int32_t H
 #define S3R_EPI_RESIDUAL 4
 #define S3R_EPI_OUT_F32 8
 #define S3R_EPI_ROPE 16
+#define S3R_EPI_RELU 32
 int s3r_gemm_bf16(const void* A, const void* W, const void* bias, const void* residual, void* C, int32_t M,
                   int32_t N, int32_t K, int32_t lda, int32_t ldw, int32_t ldc, int32_t ldr, int32_t flags,
                   void* stream);
@@ -215,6 +216,34 @@ int s3r_gemm_bf16_rope(const void* A, const void* W, const void* bias, const voi
  * split-K for grids smaller than the machine — first 16 KiB are self-resetting tile counters, the rest holds fp32
  * partial tiles.  NULL => never split. */
 int s3r_rope_table(float* table /* [(max_pos+1)*16*2] */, int32_t max_pos, float base, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Stride-1 "same" 2-D convolution as an implicit GEMM on tcgen05/TMEM - the
+ * DPT heads' nn.Conv2d (heads/dpt_block.py:33-75,121-142,189-218;
+ * dpt_head.py:35-70; dpt_gs_head.py:113-157; dpt_gs_sh_head.py:37-74), cuDNN
+ * in the reference:
+ *   y[n,h,w,:] = act( sum_{kh,kw} x[n,h+kh-pad,w+kw-pad,:] . W[:,kh,kw,:]^T + bias ) + residual[n,h,w,:]
+ * x [n,h,w,cin] bf16 NHWC; W [cout, kh*kw, ceil(cin/64)*64] bf16 (channels zero
+ * padded to a multiple of 64); bias bf16 [cout]; residual bf16 NHWC [.., cout];
+ * y NHWC bf16 or fp32 (S3R_EPI_OUT_F32).  flags: BIAS | RELU | RESIDUAL |
+ * OUT_F32 (ReLU is applied before the residual add).  Requires 2*pad = k-1,
+ * cin, cout multiples of 8, cin >= 64 and w a divisor or multiple of 128
+ * (the 128-pixel tile must be a box of the tensor) - else S3R_ERR_UNSUPPORTED.
+ * ------------------------------------------------------------------------ */
+int s3r_conv2d_bf16(const void* x, const void* w, const void* bias, const void* residual, void* y, int32_t n,
+                    int32_t h, int32_t wd, int32_t cin, int32_t cout, int32_t kh, int32_t kw, int32_t pad,
+                    int32_t flags, void* stream);
+
+/* Tuning knob (benchmarks only; process-wide, not thread-safe).  S3R_TUNE_CONV_VARIANT: tile shape of
+ * s3r_conv2d_bf16 for cout % 256 == 0 - 0 = 128x128 tiles, 2 CTAs/SM (default; also env S3R_CONV_VARIANT),
+ * 1 = 128x256 tiles with a 4-stage ring (1 CTA/SM), 2 = 128x256 tiles with a 2-stage ring (2 CTAs/SM). */
+#define S3R_TUNE_CONV_VARIANT 1
+int s3r_set_tunable(int32_t key, int32_t value);
+
+/* Bilinear x2 upsampling, align_corners=True (F.interpolate in heads/dpt_block.py:209-211, dpt_head.py:57,
+ * dpt_gs_head.py:138), NHWC bf16: y[n,2h,2w,c] = up(x)[...] (+ add[n,2h,2w,c] when add != NULL). c % 8 == 0. */
+int s3r_upsample2x_nhwc_bf16(const void* x, const void* add, void* y, int32_t n, int32_t h, int32_t w, int32_t c,
+                             void* stream);
 
 /* ------------------------------------------------------------------------
  * Attention softmax(q k^T * scale) v on tcgen05/TMEM, head_dim 64, bf16 —
@@ -240,6 +269,12 @@ int s3r_gaussian_adapter(const float* pts_raw, const float* params, const float*
                          int32_t B, int32_t HW, int32_t d_sh, int32_t view, int32_t G, float exponent,
                          float* means, float* cov, float* harmonics, float* opacities, float* scales,
                          float* rotations, void* stream);
+/* Same, for pixel-major head outputs (the fp32 [B*HW, ld] rows the 1x1-conv GEMM of the bf16 NHWC head path writes):
+ * channel c of pixel p of batch b at (b*HW + p)*ld + c. */
+int s3r_gaussian_adapter_nhwc(const float* pts_raw, const float* params, const float* app, int32_t ld_pts,
+                              int32_t ld_params, int32_t ld_app, const float* sh_mask, int32_t B, int32_t HW,
+                              int32_t d_sh, int32_t view, int32_t G, float exponent, float* means, float* cov,
+                              float* harmonics, float* opacities, float* scales, float* rotations, void* stream);
 
 /* ------------------------------------------------------------------------
  * Pose update: w2c_out[i] = SE3_exp([rho_i, theta_i]) @ w2c_in[i] (row-major

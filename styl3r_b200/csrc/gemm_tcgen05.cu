@@ -17,6 +17,7 @@
 //            + residual, -> bf16 (or fp32), 16-byte global stores
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "s3r_common.cuh"
 
@@ -51,6 +52,13 @@ __device__ __forceinline__ void g_tma_load_2d(void* dst, const CUtensorMap* map,
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
           g_smem_u32(dst)),
       "l"(map), "r"(c0), "r"(c1), "r"(g_smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void g_tma_load_4d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(
+          g_smem_u32(dst)),
+      "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(g_smem_u32(bar))
       : "memory");
 }
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
@@ -117,12 +125,24 @@ struct RopeArgs {            // RoPE-2D fused into the epilogue (qkv / projq / p
   int max_pos;
 };
 
-template <int BN, int STAGES_>
+// Implicit-GEMM convolution (kConv): A is the NHWC activation tensor behind a 4-D tensor map {C, W, H, N}.  The M tile is
+// 128 consecutive NHWC pixels = a (BW x BH x BNimg) patch, and k-block kb = (tap, 64-channel block) loads that patch
+// shifted by the tap offset (kw - pad, kh - pad); the zero padding of the convolution is TMA's out-of-bounds zero fill
+// (negative / past-the-edge coordinates), so there is no im2col buffer and no halo logic.  The (BW, BH, BNimg, 64ch)
+// box lands in shared memory as 128 rows of 128 B under SWIZZLE_128B - exactly the K-major A tile of the plain GEMM.
+struct ConvArgs {
+  int H, W;      // spatial size of the input (= output: stride 1, "same" padding)
+  int KW;        // kernel width (taps are enumerated kh-major)
+  int cblocks;   // 64-channel blocks per tap (weights are stored [Cout][tap][cblocks*64], zero padded)
+  int pad;
+};
+
+template <int BN, int STAGES_, bool kConv>
 __global__ void __launch_bounds__(GEMM_THREADS, (STAGES_ * (GEMM_BM + BN) * GEMM_BK * 2 <= 100 * 1024) ? 2 : 1)
 s3r_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const __nv_bfloat16* __restrict__ bias, const __nv_bfloat16* __restrict__ residual, void* __restrict__ Cout,
                      int M, int N, int K, int ldc, int ldr, int flags, RopeArgs rope, int splits, float* __restrict__ ws,
-                     unsigned* __restrict__ counters) {
+                     unsigned* __restrict__ counters, ConvArgs conv) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);  // SWIZZLE_128B atoms need 1024-B alignment
   using S = GemmSmem<BN, STAGES_>;
@@ -163,13 +183,25 @@ s3r_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 
   if (warp == 0) {
     if (lane == 0) {
+      int cw0 = 0, ch0 = 0, cn0 = 0;
+      if (kConv) {  // first pixel of this CTA's patch
+        cw0 = conv.W >= GEMM_BM ? m0 % conv.W : 0;
+        ch0 = (m0 / conv.W) % conv.H;
+        cn0 = m0 / (conv.W * conv.H);
+      }
       for (int kb = 0; kb < num_kb; kb++) {
         const int s = kb % GEMM_STAGES;
         g_mbar_wait(&empty[s], ((kb / GEMM_STAGES) & 1) ^ 1);
         uint8_t* a_dst = smem + s * S::STAGE_BYTES;
         uint8_t* b_dst = a_dst + S::A_BYTES;
         g_mbar_expect_tx(&full[s], S::STAGE_BYTES);
-        g_tma_load_2d(a_dst, &tmA, (kb0 + kb) * GEMM_BK, m0, &full[s]);
+        if (kConv) {
+          const int tap = (kb0 + kb) / conv.cblocks, cb = (kb0 + kb) - tap * conv.cblocks;
+          const int kh = tap / conv.KW, kw = tap - kh * conv.KW;
+          g_tma_load_4d(a_dst, &tmA, cb * GEMM_BK, cw0 + kw - conv.pad, ch0 + kh - conv.pad, cn0, &full[s]);
+        } else {
+          g_tma_load_2d(a_dst, &tmA, (kb0 + kb) * GEMM_BK, m0, &full[s]);
+        }
         g_tma_load_2d(b_dst, &tmB, (kb0 + kb) * GEMM_BK, n0, &full[s]);
       }
     }
@@ -196,13 +228,14 @@ s3r_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     //          (partials, bias, residual, output) is a fully coalesced 256/512-byte row segment.
     const int q = warp & 3;
     const int et = threadIdx.x - 64;  // 0..127
-    constexpr int LDS_ = BN + 4;      // padded row pitch (floats): conflict-free for both phases
+    constexpr int CG = BN > 128 ? 128 : BN;  // columns staged per pass (BN = 256: two passes over one 68 KB staging tile)
+    constexpr int LDS_ = CG + 4;      // padded row pitch (floats): conflict-free for both phases
     float* stage = reinterpret_cast<float*>(smem);
     int* spos = reinterpret_cast<int*>(smem + GEMM_STAGES * S::STAGE_BYTES - 2048);  // [128][2] row positions (RoPE)
     g_mbar_wait(tmem_full, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    {
-      if (flags & S3R_EPI_ROPE) {  // one coalesced read of this tile's 128 (y, x) positions, clamped to the table
+    if (flags & S3R_EPI_ROPE) {
+      {  // one coalesced read of this tile's 128 (y, x) positions, clamped to the table
         const int prow = m0 + q * 32 + lane;
         long long py = 0, px = 0;
         if (prow < M) {
@@ -212,11 +245,15 @@ s3r_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         spos[(q * 32 + lane) * 2] = (int)(py < 0 ? 0 : (py > rope.max_pos ? rope.max_pos : py));
         spos[(q * 32 + lane) * 2 + 1] = (int)(px < 0 ? 0 : (px > rope.max_pos ? rope.max_pos : px));
       }
+    }
+#pragma unroll 1
+    for (int cg = 0; cg < BN / CG; cg++) {
+    {
       float* srow = stage + (size_t)(q * 32 + lane) * LDS_;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; c++) {
+      for (int c = 0; c < CG / 32; c++) {
         uint32_t v[32];
-        g_tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+        g_tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cg * CG + c * 32), v);
 #pragma unroll
         for (int j = 0; j < 32; j += 4)
           *reinterpret_cast<float4*>(srow + c * 32 + j) =
@@ -224,11 +261,12 @@ s3r_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       }
     }
     asm volatile("bar.sync 1, 128;" ::: "memory");
-    constexpr int LPR = BN / 4;        // lanes per row
+    constexpr int LPR = CG / 4;        // lanes per row
     constexpr int RPI = 128 / LPR;     // rows per iteration of the 128 epilogue threads
     const int cl = (et % LPR) * 4;     // this lane's first column inside the tile
-    const int col = n0 + cl;
+    const int col = n0 + cg * CG + cl;
     const bool has_bias = flags & S3R_EPI_BIAS, gelu = flags & S3R_EPI_GELU, has_res = flags & S3R_EPI_RESIDUAL,
+               relu = flags & S3R_EPI_RELU,
                out_f32 = flags & S3R_EPI_OUT_F32, do_rope = (flags & S3R_EPI_ROPE) && col < rope.cols;
     const bool full4 = col + 4 <= N;
     float bias4[4] = {0.f, 0.f, 0.f, 0.f};
@@ -259,6 +297,10 @@ s3r_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       if (gelu) {
 #pragma unroll
         for (int j = 0; j < 4; j++) f[j] = 0.5f * f[j] * (1.0f + erff(f[j] * 0.70710678118654752f));
+      }
+      if (relu) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) f[j] = fmaxf(f[j], 0.0f);
       }
       if (row < M && col < N) {
         if (has_res) {
@@ -355,6 +397,8 @@ s3r_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         }
       }
     }
+    if (BN > CG) asm volatile("bar.sync 1, 128;" ::: "memory");  // staging tile is reused by the next column group
+    }  // cg
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -396,22 +440,36 @@ static int make_map(CUtensorMap* map, const void* ptr, int rows, int cols, int l
   return r == CUDA_SUCCESS ? S3R_OK : S3R_ERR_CUDA;
 }
 
-template <int BN, int STAGES_>
+template <int BN, int STAGES_, bool kConv = false>
 static int launch_gemm(const CUtensorMap& a, const CUtensorMap& b, const void* bias, const void* residual, void* C, int M,
                        int N, int K, int ldc, int ldr, int flags, const RopeArgs& rope, int splits, float* ws, unsigned* counters,
-                       cudaStream_t st) {
+                       cudaStream_t st, const ConvArgs& conv = ConvArgs{}) {
   static bool configured = false;
   const int smem = GemmSmem<BN, STAGES_>::TOTAL;
   if (!configured) {
-    S3R_CUDA_CHECK(cudaFuncSetAttribute(s3r_gemm_bf16_kernel<BN, STAGES_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    S3R_CUDA_CHECK(cudaFuncSetAttribute(s3r_gemm_bf16_kernel<BN, STAGES_, kConv>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
   dim3 grid((M + GEMM_BM - 1) / GEMM_BM, (N + BN - 1) / BN, splits);
-  s3r_gemm_bf16_kernel<BN, STAGES_><<<grid, GEMM_THREADS, smem, st>>>(a, b, (const __nv_bfloat16*)bias,
-                                                                      (const __nv_bfloat16*)residual, C, M, N, K, ldc, ldr,
-                                                                      flags, rope, splits, ws, counters);
+  s3r_gemm_bf16_kernel<BN, STAGES_, kConv><<<grid, GEMM_THREADS, smem, st>>>(
+      a, b, (const __nv_bfloat16*)bias, (const __nv_bfloat16*)residual, C, M, N, K, ldc, ldr, flags, rope, splits, ws,
+      counters, conv);
   S3R_CUDA_CHECK(cudaGetLastError());
   return S3R_OK;
+}
+
+// 4-D bf16 NHWC activation map {C, W, H, N} with box {64, bw, bh, bn} (bw*bh*bn = 128 pixels), SWIZZLE_128B, zero fill
+static int make_map_nhwc(CUtensorMap* map, const void* ptr, int n, int h, int w, int c, int bw, int bh, int bn) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return S3R_ERR_CUDA;
+  const cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+  const cuuint64_t strides[3] = {(cuuint64_t)c * 2, (cuuint64_t)w * c * 2, (cuuint64_t)h * w * c * 2};
+  const cuuint32_t box[4] = {GEMM_BK, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? S3R_OK : S3R_ERR_CUDA;
 }
 
 // (cos, sin) table for the fused RoPE epilogue: table[pos][d] = cos/sin(pos * base^(-d/16)), pos in [0, max_pos]
@@ -492,4 +550,70 @@ extern "C" int s3r_gemm_bf16(const void* A, const void* W, const void* bias, con
   if (flags & S3R_EPI_ROPE) return S3R_ERR_INVALID_ARG;
   return s3r_gemm_bf16_rope(A, W, bias, residual, C, M, N, K, lda, ldw, ldc, ldr, flags, nullptr, nullptr, 0, 0, nullptr, 0,
                             stream);
+}
+
+// ---------------------------------------------------------------------------------------------------------- conv2d
+// Stride-1 "same" convolution as an implicit GEMM on the same tcgen05 pipeline (DPT heads: heads/dpt_block.py:33-75,
+// 121-142,189-218; dpt_head.py:35-70, dpt_gs_head.py:113-157, dpt_gs_sh_head.py:37-74 - cuDNN in the reference).
+static int g_conv_variant = -1;  // S3R_CONV_VARIANT env: 0 = 128x128 tiles (2 CTAs/SM), 1 = 128x256 4-stage, 2 = 128x256 2-stage
+
+extern "C" int s3r_set_tunable(int32_t key, int32_t value) {
+  if (key == S3R_TUNE_CONV_VARIANT) {
+    if (value < 0 || value > 2) return S3R_ERR_INVALID_ARG;
+    g_conv_variant = value;
+    return S3R_OK;
+  }
+  return S3R_ERR_INVALID_ARG;
+}
+
+extern "C" int s3r_conv2d_bf16(const void* x, const void* w, const void* bias, const void* residual, void* y, int32_t n,
+                               int32_t h, int32_t wd, int32_t cin, int32_t cout, int32_t kh, int32_t kw, int32_t pad,
+                               int32_t flags, void* stream) {
+  if (n < 0 || h <= 0 || wd <= 0 || cin <= 0 || cout <= 0 || kh <= 0 || kw <= 0 || pad < 0) return S3R_ERR_INVALID_ARG;
+  if (n == 0) return S3R_OK;
+  if (!x || !w || !y) return S3R_ERR_INVALID_ARG;
+  if ((flags & S3R_EPI_BIAS) && !bias) return S3R_ERR_INVALID_ARG;
+  if ((flags & S3R_EPI_RESIDUAL) && !residual) return S3R_ERR_INVALID_ARG;
+  if (flags & (S3R_EPI_ROPE | S3R_EPI_GELU)) return S3R_ERR_INVALID_ARG;
+  if (2 * pad != kh - 1 || 2 * pad != kw - 1) return S3R_ERR_UNSUPPORTED;            // "same" convolutions only
+  if (cin % 8 || cout % 8 || cin < GEMM_BK) return S3R_ERR_UNSUPPORTED;              // TMA pitch / vector epilogue
+  if (((uintptr_t)x | (uintptr_t)w | (uintptr_t)y) & 15) return S3R_ERR_UNSUPPORTED;
+  // the 128-pixel M tile must be a (bw x bh x bn) box of the NHWC tensor
+  int bw, bh, bn;
+  if (wd >= GEMM_BM) {
+    if (wd % GEMM_BM) return S3R_ERR_UNSUPPORTED;
+    bw = GEMM_BM, bh = 1, bn = 1;
+  } else {
+    if (GEMM_BM % wd) return S3R_ERR_UNSUPPORTED;
+    bw = wd;
+    const int rows = GEMM_BM / wd;
+    if (rows <= h) {
+      if (h % rows) return S3R_ERR_UNSUPPORTED;
+      bh = rows, bn = 1;
+    } else {
+      if (rows % h) return S3R_ERR_UNSUPPORTED;
+      bh = h, bn = rows / h;
+    }
+  }
+  const long long M = (long long)n * h * wd;
+  if (M > 0x7fffffffLL) return S3R_ERR_UNSUPPORTED;
+  ConvArgs conv{h, wd, kw, (cin + GEMM_BK - 1) / GEMM_BK, pad};
+  const int K = kh * kw * conv.cblocks * GEMM_BK;  // weights: [cout][kh*kw][cblocks*64], zero padded channels
+  if (g_conv_variant < 0) {
+    const char* e = getenv("S3R_CONV_VARIANT");
+    g_conv_variant = e ? atoi(e) : 0;
+  }
+  const int BN = cout <= 64 ? 64 : ((g_conv_variant > 0 && cout % 256 == 0) ? 256 : 128);
+  CUtensorMap ta, tb;
+  int rc;
+  if ((rc = make_map_nhwc(&ta, x, n, h, wd, cin, bw, bh, bn)) != S3R_OK) return rc;
+  if ((rc = make_map(&tb, w, cout, K, K, BN)) != S3R_OK) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  RopeArgs rope{nullptr, nullptr, 0, 0};
+  if (BN == 64) return launch_gemm<64, 4, true>(ta, tb, bias, residual, y, (int)M, cout, K, cout, cout, flags, rope, 1, nullptr, nullptr, st, conv);
+  if (BN == 256 && g_conv_variant == 1)
+    return launch_gemm<256, 4, true>(ta, tb, bias, residual, y, (int)M, cout, K, cout, cout, flags, rope, 1, nullptr, nullptr, st, conv);
+  if (BN == 256)
+    return launch_gemm<256, 2, true>(ta, tb, bias, residual, y, (int)M, cout, K, cout, cout, flags, rope, 1, nullptr, nullptr, st, conv);
+  return launch_gemm<128, 3, true>(ta, tb, bias, residual, y, (int)M, cout, K, cout, cout, flags, rope, 1, nullptr, nullptr, st, conv);
 }

@@ -107,6 +107,138 @@ class DPTAdapter(nn.Module):
         return self.head(p)
 
 
+# ----------------------------------------------------------------------------------------------------------------------
+# B200 inference path: the whole pyramid in bf16 NHWC on the tcgen05 kernels (tokens are already NHWC, so no layout
+# change anywhere).  3x3 convolutions -> implicit GEMM (`conv.conv2d_nhwc`); 1x1 convolutions and the kernel==stride
+# transposed convolutions -> plain GEMM (`gemm.linear`) on the pixel-major view; the 7x7 image skip and the one
+# strided 3x3 (2 % of the head FLOPs) -> im2col + GEMM; bias / ReLU / residual adds fused into the epilogues; bilinear
+# x2 (+ add) -> `conv.upsample2x_nhwc`.  Returns the head output as fp32 pixel-major rows [B*H*W, 8].
+class _PreparedHead:
+    """bf16 GEMM operands derived from a DPTAdapter's parameters (not registered: the state dict is untouched)."""
+
+    def __init__(self, m: "DPTAdapter"):
+        from ..conv import prep_conv_weight
+        bf = lambda t: None if t is None else t.detach().to(torch.bfloat16).contiguous()
+        self.device = m.scratch.layer1_rn.weight.device
+        self.pp = []
+        for i, seq in enumerate(m.act_postprocess):
+            c0 = seq[0]
+            e = {"w0": bf(c0.weight.flatten(1)), "b0": bf(c0.bias)}
+            if i in (0, 1):  # ConvTranspose2d(k = stride): out[(i, j, co)] = sum_ci x[ci] * W[ci, co, i, j]
+                ct = seq[1]
+                k = ct.kernel_size[0]
+                e["k"] = k
+                e["wt"] = bf(ct.weight.permute(2, 3, 1, 0).reshape(k * k * ct.out_channels, ct.in_channels))
+                e["bt"] = bf(ct.bias.repeat(k * k))
+            elif i == 3:     # Conv2d(3, stride 2, pad 1) through im2col: columns ordered (ci, kh, kw) like F.unfold
+                e["ws"] = bf(seq[1].weight.flatten(1))
+                e["bs"] = bf(seq[1].bias)
+            self.pp.append(e)
+        self.rn = [prep_conv_weight(c.weight) for c in m.scratch.layer_rn]
+        self.fusion = []
+        for blk in (m.scratch.refinenet1, m.scratch.refinenet2, m.scratch.refinenet3, m.scratch.refinenet4):
+            f = {"out_w": bf(blk.out_conv.weight.flatten(1)), "out_b": bf(blk.out_conv.bias)}
+            for name in ("resConfUnit1", "resConfUnit2"):
+                u = getattr(blk, name)
+                f[name] = (prep_conv_weight(u.conv1.weight), bf(u.conv1.bias), prep_conv_weight(u.conv2.weight), bf(u.conv2.bias))
+            self.fusion.append(f)
+        h = m.head
+        self.h0_w, self.h0_b = prep_conv_weight(h[0].weight), bf(h[0].bias)
+        if m.kind == "pts3d":
+            self.h2_w, self.h2_b = prep_conv_weight(h[2].weight), bf(h[2].bias)
+        last = h[4]
+        ld = (last.out_channels + 7) // 8 * 8  # pad Cout (3, 8, 3*d_sh) to a multiple of 8 rows (16-byte output rows)
+        w = torch.zeros(ld, last.in_channels, dtype=torch.bfloat16, device=self.device)
+        b = torch.zeros(ld, dtype=torch.bfloat16, device=self.device)
+        w[:last.out_channels] = last.weight.detach().flatten(1).to(torch.bfloat16)
+        b[:last.out_channels] = last.bias.detach().to(torch.bfloat16)
+        self.last_w, self.last_b = w, b
+        if m.kind == "gs_params":
+            mw = m.input_merger[0].weight.detach().flatten(1)  # [256, 147], columns (ci, kh, kw)
+            self.mg_w = torch.zeros(mw.shape[0], 152, dtype=torch.bfloat16, device=self.device)
+            self.mg_w[:, :mw.shape[1]] = mw.to(torch.bfloat16)
+            self.mg_b = bf(m.input_merger[0].bias)
+
+
+def _rcu(x: Tensor, u) -> Tensor:
+    from ..conv import conv2d_nhwc
+    w1, b1, w2, b2 = u
+    t = conv2d_nhwc(torch.relu(x), w1, (3, 3), bias=b1, relu=True)
+    return conv2d_nhwc(t, w2, (3, 3), bias=b2, residual=x)
+
+
+def _fusion(f, x: Tensor, skip: Tensor | None = None) -> Tensor:
+    from ..conv import conv2d_nhwc, upsample2x_nhwc
+    from ..gemm import linear
+    if skip is not None:  # x + rcu1(skip) = conv2(...) + (skip + x)
+        w1, b1, w2, b2 = f["resConfUnit1"]
+        t = conv2d_nhwc(torch.relu(skip), w1, (3, 3), bias=b1, relu=True)
+        x = conv2d_nhwc(t, w2, (3, 3), bias=b2, residual=skip + x)
+    up = upsample2x_nhwc(_rcu(x, f["resConfUnit2"]))
+    return linear(up, f["out_w"], f["out_b"])
+
+
+def dpt_forward_nhwc(m: "DPTAdapter", tokens: List[Tensor], image_size, img: Tensor | None = None) -> Tensor:
+    from ..conv import conv2d_nhwc, upsample2x_nhwc
+    from ..gemm import linear
+    prep = getattr(m, "_prep", None)
+    if prep is None or prep.device != tokens[0].device:
+        prep = m._prep = _PreparedHead(m)
+    H, W = image_size
+    nh, nw = H // 16, W // 16
+    feats = []
+    for i, hook in enumerate(HOOKS):
+        t = tokens[hook]
+        B = t.shape[0]
+        e = prep.pp[i]
+        x = linear(t.reshape(B * nh * nw, t.shape[-1]), e["w0"], e["b0"])          # 1x1 conv
+        if i in (0, 1):
+            k, co = e["k"], LAYER_DIMS[i]
+            x = linear(x, e["wt"], e["bt"])                                         # [B*nh*nw, k*k*co]
+            x = x.view(B, nh, nw, k, k, co).permute(0, 1, 3, 2, 4, 5).reshape(B, nh * k, nw * k, co)
+        elif i == 2:
+            x = x.view(B, nh, nw, -1)
+        else:
+            cols = F.unfold(x.view(B, nh, nw, -1).permute(0, 3, 1, 2), 3, padding=1, stride=2)   # [B, C*9, L]
+            oh, ow = (nh + 1) // 2, (nw + 1) // 2
+            x = linear(cols.transpose(1, 2).reshape(B * oh * ow, -1), e["ws"], e["bs"]).view(B, oh, ow, -1)
+        feats.append(conv2d_nhwc(x.contiguous(), prep.rn[i], (3, 3)))
+    f1, f2, f3, f4 = prep.fusion
+    p = _fusion(f4, feats[3])[:, :feats[2].shape[1], :feats[2].shape[2]].contiguous()
+    p = _fusion(f3, p, feats[2])
+    p = _fusion(f2, p, feats[1])
+    p = _fusion(f1, p, feats[0])
+    if m.kind == "pts3d":
+        p = conv2d_nhwc(p, prep.h0_w, (3, 3), bias=prep.h0_b)
+        p = conv2d_nhwc(upsample2x_nhwc(p), prep.h2_w, (3, 3), bias=prep.h2_b, relu=True)
+    else:
+        add = None
+        if m.kind == "gs_params":
+            B = img.shape[0]
+            cols = F.unfold(img.to(torch.bfloat16), 7, padding=3).transpose(1, 2)   # [B, H*W, 147], columns (ci, kh, kw)
+            add = linear(F.pad(cols, (0, 5)).reshape(B * H * W, 152), prep.mg_w, prep.mg_b, relu=True).view(B, H, W, -1)
+        p = conv2d_nhwc(upsample2x_nhwc(p, add), prep.h0_w, (3, 3), relu=True)
+    return linear(p.reshape(-1, p.shape[-1]), prep.last_w, prep.last_b, out_dtype=torch.float32)   # [B*H*W, ld] fp32
+
+
+def nhwc_supported(image_size) -> bool:
+    """The implicit-GEMM kernel tiles 128 consecutive pixels as a box: every pyramid width must divide or be a multiple
+    of 128 (true for the 256x256 production resolution and any power-of-two size >= 128)."""
+    H, W = image_size
+    if H % 16 or W % 16:
+        return False
+    ok = True
+    for div in (32, 16, 8, 4, 2, 1):
+        w, h = W // div, H // div
+        if w >= 128:
+            ok &= w % 128 == 0
+        else:
+            ok &= 128 % w == 0
+            rows = 128 // w if w else 0
+            ok &= (h % rows == 0) if rows <= h else (rows % h == 0)
+    return ok
+
+
 class PixelwiseDPT(nn.Module):
     """Holds the adapter under the attribute name `dpt` like the reference's PixelwiseTaskWithDPT."""
 
@@ -116,3 +248,6 @@ class PixelwiseDPT(nn.Module):
 
     def forward(self, tokens: List[Tensor], image_size, img: Tensor | None = None) -> Tensor:
         return self.dpt(tokens, image_size, img)
+
+    def forward_nhwc(self, tokens: List[Tensor], image_size, img: Tensor | None = None) -> Tensor:
+        return dpt_forward_nhwc(self.dpt, tokens, image_size, img)

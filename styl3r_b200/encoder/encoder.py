@@ -207,16 +207,23 @@ class EncoderNoPoSplatMultiTokenStyle(nn.Module):
         self.token_stylizer = TokenStylizer(cfg.token_stylizer)
         self.gaussian_appearance_head = PixelwiseDPT("gs_sh", 3 * d_sh)
 
-    def to_inference(self, vit_dtype: torch.dtype = torch.bfloat16):
+    def to_inference(self, vit_dtype: torch.dtype = torch.bfloat16, heads: str = "tcgen05"):
         """Inference layout for B200: ViT trunks (backbone, token stylizer) hold `vit_dtype` weights (bf16 operands,
-        fp32 accumulation in the GEMMs / attention; no per-call autocast weight casts), DPT heads stay fp32 (TF32
+        fp32 accumulation in the GEMMs / attention; no per-call autocast weight casts).  DPT heads:
+        `heads="tcgen05"` (default with bf16 trunks) runs the whole pyramid in bf16 NHWC on the implicit-GEMM
+        convolution kernel (fp32 accumulation; `dpt.dpt_forward_nhwc`), `heads="cudnn"` keeps them fp32 (TF32
         convolutions — the reference disables autocast there, encoder…style.py:150) in channels_last so cuDNN runs
-        NHWC kernels without layout transposes.  Checkpoints still load strictly (load_state_dict casts)."""
+        NHWC kernels without layout transposes.  Parameters stay registered as they are: checkpoints still load
+        strictly (load_state_dict casts)."""
+        if heads not in ("tcgen05", "cudnn"):
+            raise ValueError(heads)
         self.backbone.to(vit_dtype)
         self.token_stylizer.to(vit_dtype)
+        self._nhwc_heads = heads == "tcgen05" and vit_dtype == torch.bfloat16
         for head in (self.downstream_head1, self.downstream_head2, self.gaussian_param_head, self.gaussian_param_head2,
                      self.gaussian_appearance_head):
             head.to(memory_format=torch.channels_last)
+            head.dpt._prep = None  # bf16 operands are rebuilt from the (possibly reloaded) parameters on first use
         return self
 
     def opacity_exponent(self, global_step: int) -> float:
@@ -247,8 +254,22 @@ class EncoderNoPoSplatMultiTokenStyle(nn.Module):
         rots = torch.empty(b, G, 4, device=dev) if visualization_dump is not None else None
         L = _lib.lib()
         p = lambda t: None if t is None else C.c_void_p(t.data_ptr())
+        from .dpt import nhwc_supported
+        nhwc = getattr(self, "_nhwc_heads", False) and not torch.is_grad_enabled() and nhwc_supported(shape)
         with torch.autocast("cuda", enabled=False):
-            for i in range(v):
+            for i in range(v if nhwc else 0):  # bf16 NHWC pyramid on the tcgen05 implicit-GEMM convolutions
+                toks = [t[:, i] for t in dec_feat]
+                pts_raw = (self.downstream_head1 if i == 0 else self.downstream_head2).forward_nhwc(toks, shape)
+                prm = (self.gaussian_param_head if i == 0 else self.gaussian_param_head2).forward_nhwc(
+                    toks, shape, img[:, i, :3])
+                app = self.gaussian_appearance_head.forward_nhwc([t[:, i] for t in sty_feat], shape)
+                _lib.check(L.s3r_gaussian_adapter_nhwc(p(pts_raw), p(prm), p(app), pts_raw.shape[1], prm.shape[1], app.shape[1],
+                                                       p(self.gaussian_adapter.sh_mask),
+                                                       b, HW, d_sh, i, G, float(self.opacity_exponent(global_step)),
+                                                       p(means), p(cov), p(harm), p(opac), p(scales), p(rots),
+                                                       C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)),
+                           "s3r_gaussian_adapter_nhwc")
+            for i in range(0 if nhwc else v):
                 toks = [t[:, i].float() for t in dec_feat]
                 pts_raw = (self.downstream_head1 if i == 0 else self.downstream_head2)(toks, shape).contiguous()
                 prm = (self.gaussian_param_head if i == 0 else self.gaussian_param_head2)(

@@ -14,7 +14,7 @@ import torch
 
 from . import _lib
 
-EPI_BIAS, EPI_GELU, EPI_RESIDUAL, EPI_OUT_F32, EPI_ROPE = 1, 2, 4, 8, 16
+EPI_BIAS, EPI_GELU, EPI_RESIDUAL, EPI_OUT_F32, EPI_ROPE, EPI_RELU = 1, 2, 4, 8, 16, 32
 ROPE_MAX_POS = 255  # positions are patch-grid coordinates (16 for 256 px, 64 for 1024 px)
 _rope_tables: dict = {}
 _workspaces: dict = {}
@@ -46,7 +46,7 @@ def rope_table(device, base: float) -> torch.Tensor:
 def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None,
            residual: Optional[torch.Tensor] = None, gelu: bool = False, out_dtype: torch.dtype = torch.bfloat16,
            rope_pos: Optional[torch.Tensor] = None, rope_cols: int = 0, rope_base: float = 100.0,
-           split_k: bool = False):
+           split_k: bool = False, relu: bool = False):
     """rope_pos [..., 2] int64 (one (y, x) per row of x) + rope_cols: RoPE-2D (head_dim 64) is applied to output columns
     [0, rope_cols) inside the GEMM epilogue (q and k parts of a qkv projection), replacing a separate rope pass.
     split_k: let grids smaller than the machine split the K range over several CTAs (deterministic last-CTA fix-up
@@ -73,6 +73,8 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] =
         bp = C.c_void_p(bias.data_ptr())
     if gelu:
         flags |= EPI_GELU
+    if relu:
+        flags |= EPI_RELU
     if residual is not None:
         flags |= EPI_RESIDUAL
         r2 = residual.reshape(-1, N)
