@@ -235,8 +235,8 @@ int s3r_conv2d_bf16(const void* x, const void* w, const void* bias, const void* 
                     int32_t flags, void* stream);
 
 /* Tuning knob (benchmarks only; process-wide, not thread-safe).  S3R_TUNE_CONV_VARIANT: tile shape of
- * s3r_conv2d_bf16 for cout % 256 == 0 - 0 = 128x128 tiles, 2 CTAs/SM (default; also env S3R_CONV_VARIANT),
- * 1 = 128x256 tiles with a 4-stage ring (1 CTA/SM), 2 = 128x256 tiles with a 2-stage ring (2 CTAs/SM). */
+ * s3r_conv2d_bf16 for cout % 256 == 0 - -1 = auto (default; also env S3R_CONV_VARIANT), 0 = 128x128 tiles,
+ * 2 CTAs/SM, 1 = 128x256 tiles with a 4-stage ring (1 CTA/SM), 2 = 128x256 tiles with a 2-stage ring (2 CTAs/SM). */
 #define S3R_TUNE_CONV_VARIANT 1
 int s3r_set_tunable(int32_t key, int32_t value);
 
@@ -282,6 +282,19 @@ int s3r_gaussian_adapter_nhwc(const float* pts_raw, const float* params, const f
  * ------------------------------------------------------------------------ */
 int s3r_se3_update_w2c(const float* w2c_in, const float* rho, const float* theta, float* w2c_out,
                        int32_t n, void* stream);
+
+/* ------------------------------------------------------------------------
+ * .ply export packing (src/model/ply_export.py:26-74): one row of
+ * 17 + (save_rest ? 3*(d_sh-1) : 0) float32 per Gaussian in the file's binary
+ * layout: x y z, nx ny nz (0), f_dc_0..2, [f_rest_*], opacity, log(scale_0..2),
+ * rot_0..3 (w x y z after scipy's from_quat -> as_matrix -> from_matrix ->
+ * as_quat round trip, float64).  rotations are xyzw; harmonics [n,3,d_sh].
+ * xform (device, optional) = {shift_x, shift_y, shift_z, scale_factor} of the
+ * reference's shift_and_scale: mean' = (mean - shift)/factor, scale' = scale/factor.
+ * ------------------------------------------------------------------------ */
+int s3r_ply_pack(const float* means, const float* scales, const float* rotations, const float* harmonics,
+                 const float* opacities, const float* xform, int32_t n, int32_t d_sh, int32_t save_rest, float* out,
+                 void* stream);
 
 #ifdef __cplusplus
 }

@@ -84,14 +84,13 @@ from styl3r_b200.encoder import EncoderNoPoSplatTokenStyleCfg, get_encoder, Grap
 from tests.encoder_weights import make_inputs
 torch.backends.cuda.matmul.allow_tf32 = True; torch.backends.cudnn.allow_tf32 = True
 enc, _ = get_encoder(EncoderNoPoSplatTokenStyleCfg(stylized=True)); enc = enc.cuda().eval()
-for heads in ("cudnn", "tcgen05"):
-    enc.to_inference(torch.bfloat16, heads=heads)
-    for var in ((0,) if heads == "cudnn" else (0, 1, 2)):
-        _lib.check(L.s3r_set_tunable(1, var))
-        for (b, v) in ((1, 2), (4, 4)):
-            context, style = make_inputs(b, v, 256, seed=1, device="cuda")
-            fast = GraphedEncoder(enc)
-            out = fast(context, style); torch.cuda.synchronize()
-            ms = t_ms(lambda: fast(context, style), 5)
-            flops = {2: 1270.8e9, 4: 2437.2e9}[v] * b
-            print(f"GRAPH encoder heads={heads} v{var} b={b} v={v}: {ms:.2f} ms {flops/ms/1e9:.1f} TFLOP/s  means|mean| {out.means.abs().mean().item():.4f}", flush=True)
+_lib.check(L.s3r_set_tunable(1, -1))
+for heads, br in (("cudnn", False), ("tcgen05", False), ("cudnn", True), ("tcgen05", True)):
+    enc.to_inference(torch.bfloat16, heads=heads, branches=br)
+    for (b, v) in ((1, 2), (4, 4)):
+        context, style = make_inputs(b, v, 256, seed=1, device="cuda")
+        fast = GraphedEncoder(enc)
+        out = fast(context, style); torch.cuda.synchronize()
+        ms = t_ms(lambda: fast(context, style), 5)
+        flops = {2: 1270.8e9, 4: 2437.2e9}[v] * b
+        print(f"GRAPH encoder heads={heads} branches={br} b={b} v={v}: {ms:.2f} ms {flops/ms/1e9:.1f} TFLOP/s  means|mean| {out.means.abs().mean().item():.4f}", flush=True)

@@ -555,11 +555,15 @@ extern "C" int s3r_gemm_bf16(const void* A, const void* W, const void* bias, con
 // ---------------------------------------------------------------------------------------------------------- conv2d
 // Stride-1 "same" convolution as an implicit GEMM on the same tcgen05 pipeline (DPT heads: heads/dpt_block.py:33-75,
 // 121-142,189-218; dpt_head.py:35-70, dpt_gs_head.py:113-157, dpt_gs_sh_head.py:37-74 - cuDNN in the reference).
-static int g_conv_variant = -1;  // S3R_CONV_VARIANT env: 0 = 128x128 tiles (2 CTAs/SM), 1 = 128x256 4-stage, 2 = 128x256 2-stage
+// tile variant: -1 = auto, 0 = 128x128 tiles (3-stage ring, 2 CTAs/SM), 1 = 128x256 4-stage (1 CTA/SM), 2 = 128x256
+// 2-stage (2 CTAs/SM).  Measured on B200 (scripts/dev_conv.py, 3x3 256->256): at 256x256 variant 2 reaches 1071-1174
+// TFLOP/s vs 882-980 for variant 0 (the A patch is read once per tap instead of twice); on the small pyramid levels
+// (<= 64x64, fewer CTAs than SMs) the 128-wide tile wins because it yields twice as many CTAs.
+static int g_conv_variant = -2;
 
 extern "C" int s3r_set_tunable(int32_t key, int32_t value) {
   if (key == S3R_TUNE_CONV_VARIANT) {
-    if (value < 0 || value > 2) return S3R_ERR_INVALID_ARG;
+    if (value < -1 || value > 2) return S3R_ERR_INVALID_ARG;
     g_conv_variant = value;
     return S3R_OK;
   }
@@ -599,11 +603,13 @@ extern "C" int s3r_conv2d_bf16(const void* x, const void* w, const void* bias, c
   if (M > 0x7fffffffLL) return S3R_ERR_UNSUPPORTED;
   ConvArgs conv{h, wd, kw, (cin + GEMM_BK - 1) / GEMM_BK, pad};
   const int K = kh * kw * conv.cblocks * GEMM_BK;  // weights: [cout][kh*kw][cblocks*64], zero padded channels
-  if (g_conv_variant < 0) {
+  if (g_conv_variant == -2) {
     const char* e = getenv("S3R_CONV_VARIANT");
-    g_conv_variant = e ? atoi(e) : 0;
+    g_conv_variant = e ? atoi(e) : -1;
   }
-  const int BN = cout <= 64 ? 64 : ((g_conv_variant > 0 && cout % 256 == 0) ? 256 : 128);
+  int variant = g_conv_variant;
+  if (variant < 0) variant = (cout % 256 == 0 && (M + GEMM_BM - 1) / GEMM_BM >= 256) ? 2 : 0;
+  const int BN = cout <= 64 ? 64 : ((variant > 0 && cout % 256 == 0) ? 256 : 128);
   CUtensorMap ta, tb;
   int rc;
   if ((rc = make_map_nhwc(&ta, x, n, h, wd, cin, bw, bh, bn)) != S3R_OK) return rc;
@@ -611,7 +617,7 @@ extern "C" int s3r_conv2d_bf16(const void* x, const void* w, const void* bias, c
   cudaStream_t st = (cudaStream_t)stream;
   RopeArgs rope{nullptr, nullptr, 0, 0};
   if (BN == 64) return launch_gemm<64, 4, true>(ta, tb, bias, residual, y, (int)M, cout, K, cout, cout, flags, rope, 1, nullptr, nullptr, st, conv);
-  if (BN == 256 && g_conv_variant == 1)
+  if (BN == 256 && variant == 1)
     return launch_gemm<256, 4, true>(ta, tb, bias, residual, y, (int)M, cout, K, cout, cout, flags, rope, 1, nullptr, nullptr, st, conv);
   if (BN == 256)
     return launch_gemm<256, 2, true>(ta, tb, bias, residual, y, (int)M, cout, K, cout, cout, flags, rope, 1, nullptr, nullptr, st, conv);

@@ -23,6 +23,7 @@ import torch
 from torch import Tensor, nn
 
 from .. import _lib
+from ..streams import fork_join
 from .dpt import PixelwiseDPT
 from .vit import CroCoTrunk, _lin
 
@@ -120,29 +121,44 @@ class AsymmetricCroCoMulti(CroCoTrunk):
             cls._others_idx[key] = torch.tensor([[j for j in range(v) if j != i] for i in range(v)], device=x.device)
         return x[:, cls._others_idx[key]].reshape(b, v, (v - 1) * l, c)
 
-    def forward(self, context: dict):
+    def encode_views(self, context: dict):
+        """Shared ViT-L encoder over the b*v context images (+ intrinsics token): (feat [b,v,l,1024], pos [b,v,l,2])."""
         img = context["image"]
-        b, v, _, h, w = img.shape
+        b, v = img.shape[:2]
         tok = self.intrinsic_encoder(context["intrinsics"].flatten(2)).reshape(b * v, 1, -1)
         feat, pos = self.encode(img.reshape(b * v, *img.shape[2:]), tok)
-        feat, pos = feat.reshape(b, v, *feat.shape[1:]), pos.reshape(b, v, *pos.shape[1:])
+        return feat.reshape(b, v, *feat.shape[1:]), pos.reshape(b, v, *pos.shape[1:])
+
+    def decode_views(self, feat: Tensor, pos: Tensor, parallel: bool = False):
+        """The two cross-view decoders; `parallel`: view 0 (`dec_blocks`) and views >= 1 (`dec_blocks2`) of a layer
+        are independent given the previous layer's output and run as concurrent branches (streams.fork_join)."""
+        b, v = feat.shape[:2]
         outs = [feat]
         cur = _lin(self.decoder_embed, feat)
         pos_ctx = self._others(pos)
         blocks2 = self.dec_blocks2 if self.asymmetric else self.dec_blocks
         for blk1, blk2 in zip(self.dec_blocks, blocks2):
             ctx = self._others(cur)
-            f1 = blk1(cur[:, 0], ctx[:, 0], pos[:, 0], pos_ctx[:, 0])
-            parts = [f1[:, None]]
+            branches = [lambda: blk1(cur[:, 0], ctx[:, 0], pos[:, 0], pos_ctx[:, 0], parallel=parallel)]
             if v > 1:
-                f2 = blk2(cur[:, 1:].reshape(b * (v - 1), *cur.shape[2:]), ctx[:, 1:].reshape(b * (v - 1), *ctx.shape[2:]),
-                          pos[:, 1:].reshape(b * (v - 1), *pos.shape[2:]), pos_ctx[:, 1:].reshape(b * (v - 1), *pos_ctx.shape[2:]))
-                parts.append(f2.reshape(b, v - 1, *f2.shape[1:]))
+                branches.append(lambda: blk2(
+                    cur[:, 1:].reshape(b * (v - 1), *cur.shape[2:]), ctx[:, 1:].reshape(b * (v - 1), *ctx.shape[2:]),
+                    pos[:, 1:].reshape(b * (v - 1), *pos.shape[2:]), pos_ctx[:, 1:].reshape(b * (v - 1), *pos_ctx.shape[2:]),
+                    parallel=parallel))
+            res = fork_join(branches, feat.device, parallel=parallel)
+            parts = [res[0][:, None]]
+            if v > 1:
+                parts.append(res[1].reshape(b, v - 1, *res[1].shape[1:]))
             cur = torch.cat(parts, dim=1)
             outs.append(cur)
         outs[-1] = self.dec_norm(outs[-1])
-        dec_feat = [o[:, :, :-1] for o in outs]  # drop the intrinsics token
-        return feat, pos, dec_feat, (h, w), img
+        return [o[:, :, :-1] for o in outs]  # drop the intrinsics token
+
+    def forward(self, context: dict):
+        img = context["image"]
+        h, w = img.shape[-2:]
+        feat, pos = self.encode_views(context)
+        return feat, pos, self.decode_views(feat, pos), (h, w), img
 
 
 class TokenStylizer(CroCoTrunk):
@@ -152,15 +168,22 @@ class TokenStylizer(CroCoTrunk):
     def __init__(self, cfg: TokenStylizerCfg):
         super().__init__(second_decoder=False, intrinsics_token=False)
 
-    def forward(self, style: dict, content_feat: Tensor, content_pos: Tensor) -> List[Tensor]:
-        b, v, l, _ = content_feat.shape
+    def encode_style(self, style: dict):
+        """Style ViT-L + decoder_embed: (y [b,256,768], spos [b,256,2]) - independent of the content branch."""
         sfeat, spos = self.encode(style["image"])
+        return _lin(self.decoder_embed, sfeat), spos
+
+    def forward(self, style: dict, content_feat: Tensor, content_pos: Tensor) -> List[Tensor]:
+        return self.decode(*self.encode_style(style), content_feat, content_pos)
+
+    def decode(self, y: Tensor, spos: Tensor, content_feat: Tensor, content_pos: Tensor,
+               parallel: bool = False) -> List[Tensor]:
+        b, v, l, _ = content_feat.shape
         outs = [content_feat]
         x = _lin(self.decoder_embed, content_feat.reshape(b, v * l, -1))
         xpos = content_pos.reshape(b, v * l, 2)
-        y = _lin(self.decoder_embed, sfeat)
         for blk in self.dec_blocks:
-            x = blk(x, y, xpos, spos)
+            x = blk(x, y, xpos, spos, parallel=parallel)
             outs.append(x.reshape(b, v, l, -1))
         outs[-1] = self.dec_norm(x).reshape(b, v, l, -1)
         return [o[:, :, :-1] for o in outs]
@@ -207,19 +230,23 @@ class EncoderNoPoSplatMultiTokenStyle(nn.Module):
         self.token_stylizer = TokenStylizer(cfg.token_stylizer)
         self.gaussian_appearance_head = PixelwiseDPT("gs_sh", 3 * d_sh)
 
-    def to_inference(self, vit_dtype: torch.dtype = torch.bfloat16, heads: str = "tcgen05"):
+    def to_inference(self, vit_dtype: torch.dtype = torch.bfloat16, heads: str = "tcgen05", branches: bool = True):
         """Inference layout for B200: ViT trunks (backbone, token stylizer) hold `vit_dtype` weights (bf16 operands,
         fp32 accumulation in the GEMMs / attention; no per-call autocast weight casts).  DPT heads:
         `heads="tcgen05"` (default with bf16 trunks) runs the whole pyramid in bf16 NHWC on the implicit-GEMM
         convolution kernel (fp32 accumulation; `dpt.dpt_forward_nhwc`), `heads="cudnn"` keeps them fp32 (TF32
         convolutions — the reference disables autocast there, encoder…style.py:150) in channels_last so cuDNN runs
-        NHWC kernels without layout transposes.  Parameters stay registered as they are: checkpoints still load
+        NHWC kernels without layout transposes.  `branches`: independent sub-graphs (content ViT | style ViT, backbone
+        decoder | stylizer decoder, dec_blocks | dec_blocks2, the 5 DPT pyramids of every view) run as concurrent
+        stream branches (streams.fork_join; graph edges under GraphedEncoder) - at batch 1 the forward is bound by the
+        length of its kernel chain, not by FLOPs.  Parameters stay registered as they are: checkpoints still load
         strictly (load_state_dict casts)."""
         if heads not in ("tcgen05", "cudnn"):
             raise ValueError(heads)
         self.backbone.to(vit_dtype)
         self.token_stylizer.to(vit_dtype)
         self._nhwc_heads = heads == "tcgen05" and vit_dtype == torch.bfloat16
+        self._branches = bool(branches)
         for head in (self.downstream_head1, self.downstream_head2, self.gaussian_param_head, self.gaussian_param_head2,
                      self.gaussian_appearance_head):
             head.to(memory_format=torch.channels_last)
@@ -242,8 +269,14 @@ class EncoderNoPoSplatMultiTokenStyle(nn.Module):
         if img.dtype != vit_dtype:  # to_inference(): bf16 trunks
             context = {**context, "image": img.to(vit_dtype), "intrinsics": context["intrinsics"].to(vit_dtype)}
             style = {**style, "image": style["image"].to(vit_dtype)}
-        enc_feat, enc_pos, dec_feat, shape, images = self.backbone(context)
-        sty_feat = self.token_stylizer(style, enc_feat, enc_pos)
+        par = getattr(self, "_branches", False) and not torch.is_grad_enabled()
+        shape = (h, w)
+        (enc_feat, enc_pos), (sty_y, sty_pos) = fork_join(
+            [lambda: self.backbone.encode_views(context), lambda: self.token_stylizer.encode_style(style)], img.device,
+            parallel=par)
+        dec_feat, sty_feat = fork_join(
+            [lambda: self.backbone.decode_views(enc_feat, enc_pos, parallel=par),
+             lambda: self.token_stylizer.decode(sty_y, sty_pos, enc_feat, enc_pos, parallel=par)], img.device, parallel=par)
         HW, G, d_sh = h * w, v * h * w, self.gaussian_adapter.d_sh
         dev = img.device
         means = torch.empty(b, G, 3, device=dev)
@@ -256,29 +289,36 @@ class EncoderNoPoSplatMultiTokenStyle(nn.Module):
         p = lambda t: None if t is None else C.c_void_p(t.data_ptr())
         from .dpt import nhwc_supported
         nhwc = getattr(self, "_nhwc_heads", False) and not torch.is_grad_enabled() and nhwc_supported(shape)
-        with torch.autocast("cuda", enabled=False):
-            for i in range(v if nhwc else 0):  # bf16 NHWC pyramid on the tcgen05 implicit-GEMM convolutions
-                toks = [t[:, i] for t in dec_feat]
-                pts_raw = (self.downstream_head1 if i == 0 else self.downstream_head2).forward_nhwc(toks, shape)
-                prm = (self.gaussian_param_head if i == 0 else self.gaussian_param_head2).forward_nhwc(
-                    toks, shape, img[:, i, :3])
-                app = self.gaussian_appearance_head.forward_nhwc([t[:, i] for t in sty_feat], shape)
-                _lib.check(L.s3r_gaussian_adapter_nhwc(p(pts_raw), p(prm), p(app), pts_raw.shape[1], prm.shape[1], app.shape[1],
-                                                       p(self.gaussian_adapter.sh_mask),
-                                                       b, HW, d_sh, i, G, float(self.opacity_exponent(global_step)),
-                                                       p(means), p(cov), p(harm), p(opac), p(scales), p(rots),
-                                                       C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)),
+
+        def head_branch(head, feats, i, with_img):
+            """One DPT pyramid of view i: bf16 NHWC on the tcgen05 implicit-GEMM convolutions (pixel-major fp32 rows
+            out), or the fp32 module (planar NCHW out)."""
+            def run():
+                with torch.autocast("cuda", enabled=False):
+                    if nhwc:
+                        return head.forward_nhwc([t[:, i] for t in feats], shape, img[:, i, :3] if with_img else None)
+                    return head([t[:, i].float() for t in feats], shape,
+                                img[:, i, :3].float() if with_img else None).contiguous()
+            return run
+
+        branches = []
+        for i in range(v):
+            branches += [head_branch(self.downstream_head1 if i == 0 else self.downstream_head2, dec_feat, i, False),
+                         head_branch(self.gaussian_param_head if i == 0 else self.gaussian_param_head2, dec_feat, i, True),
+                         head_branch(self.gaussian_appearance_head, sty_feat, i, False)]
+        raw = fork_join(branches, dev, parallel=par)
+        st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        expo = float(self.opacity_exponent(global_step))
+        for i in range(v):
+            pts_raw, prm, app = raw[3 * i:3 * i + 3]
+            if nhwc:
+                _lib.check(L.s3r_gaussian_adapter_nhwc(p(pts_raw), p(prm), p(app), pts_raw.shape[1], prm.shape[1],
+                                                       app.shape[1], p(self.gaussian_adapter.sh_mask), b, HW, d_sh, i, G,
+                                                       expo, p(means), p(cov), p(harm), p(opac), p(scales), p(rots), st),
                            "s3r_gaussian_adapter_nhwc")
-            for i in range(0 if nhwc else v):
-                toks = [t[:, i].float() for t in dec_feat]
-                pts_raw = (self.downstream_head1 if i == 0 else self.downstream_head2)(toks, shape).contiguous()
-                prm = (self.gaussian_param_head if i == 0 else self.gaussian_param_head2)(
-                    toks, shape, img[:, i, :3].float()).contiguous()
-                app = self.gaussian_appearance_head([t[:, i].float() for t in sty_feat], shape).contiguous()
+            else:
                 _lib.check(L.s3r_gaussian_adapter(p(pts_raw), p(prm), p(app), p(self.gaussian_adapter.sh_mask), b, HW, d_sh,
-                                                  i, G, float(self.opacity_exponent(global_step)), p(means), p(cov),
-                                                  p(harm), p(opac), p(scales), p(rots),
-                                                  C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)),
+                                                  i, G, expo, p(means), p(cov), p(harm), p(opac), p(scales), p(rots), st),
                            "s3r_gaussian_adapter")
         if visualization_dump is not None:  # keys consumed by export_ply (infer_model_re10k.py:542-557)
             visualization_dump["depth"] = means[..., 2].reshape(b, v, h, w, 1, 1)

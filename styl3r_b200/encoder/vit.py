@@ -17,6 +17,7 @@ from torch import Tensor, nn
 from .. import gemm as _gemm
 from ..curope import cuRoPE2D_func
 from ..ops import memory_efficient_attention
+from ..streams import fork_join
 
 LN_EPS = 1e-6  # croco.py:34
 
@@ -84,21 +85,36 @@ class CrossAttention(nn.Module):
         self.projv = nn.Linear(dim, dim, bias=True)
         self.proj = nn.Linear(dim, dim)
 
-    def forward(self, query: Tensor, key: Tensor, value: Tensor, qpos: Tensor, kpos: Tensor,
-                residual: Tensor | None = None) -> Tensor:
+    def project_q(self, query: Tensor, qpos: Tensor) -> Tensor:
         B, Nq, C = query.shape
         H, D = self.num_heads, C // self.num_heads
         if _fast(self.projq, query) and D == 64:
-            q = _gemm.linear(query, self.projq.weight, self.projq.bias, rope_pos=qpos, rope_cols=C,
-                             rope_base=self.rope_base).view(B, Nq, H, D)
+            return _gemm.linear(query, self.projq.weight, self.projq.bias, rope_pos=qpos, rope_cols=C,
+                                rope_base=self.rope_base).view(B, Nq, H, D)
+        return _rope(_lin(self.projq, query).view(B, Nq, H, D), qpos, self.rope_base)
+
+    def project_kv(self, key: Tensor, value: Tensor, kpos: Tensor):
+        """K (with RoPE) and V of the context tokens - independent of the query stream, so a DecoderBlock can compute
+        them concurrently with its self-attention."""
+        B, Nk, C = key.shape
+        H, D = self.num_heads, C // self.num_heads
+        if _fast(self.projk, key) and D == 64:
             k = _gemm.linear(key, self.projk.weight, self.projk.bias, rope_pos=kpos, rope_cols=C,
-                             rope_base=self.rope_base).view(B, key.shape[1], H, D)
+                             rope_base=self.rope_base).view(B, Nk, H, D)
         else:
-            q = _rope(_lin(self.projq, query).view(B, Nq, H, D), qpos, self.rope_base)
-            k = _rope(_lin(self.projk, key).view(B, key.shape[1], H, D), kpos, self.rope_base)
-        v = _lin(self.projv, value).view(B, value.shape[1], H, D)
+            k = _rope(_lin(self.projk, key).view(B, Nk, H, D), kpos, self.rope_base)
+        return k, _lin(self.projv, value).view(B, value.shape[1], H, D)
+
+    def attend(self, q: Tensor, k: Tensor, v: Tensor, residual: Tensor | None = None) -> Tensor:
+        B, Nq, H, D = q.shape
         o = memory_efficient_attention(q, k, v, scale=self.scale)
-        return _lin(self.proj, o.reshape(B, Nq, C), residual=residual)
+        return _lin(self.proj, o.reshape(B, Nq, H * D), residual=residual)
+
+    def forward(self, query: Tensor, key: Tensor, value: Tensor, qpos: Tensor, kpos: Tensor,
+                residual: Tensor | None = None) -> Tensor:
+        q = self.project_q(query, qpos)
+        k, v = self.project_kv(key, value, kpos)
+        return self.attend(q, k, v, residual=residual)
 
 
 class Block(nn.Module):
@@ -125,11 +141,20 @@ class DecoderBlock(nn.Module):
         self.mlp = Mlp(dim, int(dim * mlp_ratio))
         self.norm_y = nn.LayerNorm(dim, eps=LN_EPS)
 
-    def forward(self, x: Tensor, y: Tensor, xpos: Tensor, ypos: Tensor) -> Tensor:
-        x = self.attn(self.norm1(x), xpos, residual=x)
-        y_ = self.norm_y(y)
-        x = self.cross_attn(self.norm2(x), y_, y_, xpos, ypos, residual=x)
-        return self.mlp(self.norm3(x), residual=x)
+    def forward(self, x: Tensor, y: Tensor, xpos: Tensor, ypos: Tensor, parallel: bool = False) -> Tensor:
+        """`parallel`: the context branch (norm_y -> projk/projv) runs concurrently with the self-attention branch
+        (streams.fork_join); same kernels and operands either way, so the result is identical."""
+        def self_branch():
+            x1 = self.attn(self.norm1(x), xpos, residual=x)
+            return x1, self.cross_attn.project_q(self.norm2(x1), xpos)
+
+        def ctx_branch():
+            y_ = self.norm_y(y)
+            return self.cross_attn.project_kv(y_, y_, ypos)
+
+        (x1, q), (k, v) = fork_join([self_branch, ctx_branch], x.device, parallel=parallel)
+        x2 = self.cross_attn.attend(q, k, v, residual=x1)
+        return self.mlp(self.norm3(x2), residual=x2)
 
 
 class PatchEmbed(nn.Module):
