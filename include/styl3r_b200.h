@@ -296,6 +296,23 @@ int s3r_ply_pack(const float* means, const float* scales, const float* rotations
                  const float* opacities, const float* xform, int32_t n, int32_t d_sh, int32_t save_rest, float* out,
                  void* stream);
 
+/* ------------------------------------------------------------------------
+ * Input staging: rescale_and_crop + normalize_image (src/dataset/shims/
+ * crop_shim.py:11-79, normalize_shim.py:15-18), bit-exact with Pillow's 8-bit
+ * LANCZOS resize.  img: float planes [planes, h_in, w_in] in [0,1]
+ * (planes = images x channels); resized to (h_s, w_s) through a uint8
+ * intermediate (scratch: planes*h_in*w_s bytes), window (crop_row, crop_col,
+ * h_out, w_out) cut out, out = u8/255, then (out - mean[c])/std[c] when mean
+ * and std (device, [channels]) are given.  Tap tables per output row/column:
+ * bounds int32 [n,2] = (first, count), coeffs int32 [n, ksize] in Pillow's
+ * 22-bit fixed point (device memory; styl3r_b200.staging builds them).
+ * ------------------------------------------------------------------------ */
+int s3r_rescale_crop(const float* img, int32_t planes, int32_t channels, int32_t h_in, int32_t w_in, int32_t h_s,
+                     int32_t w_s, const int32_t* h_bounds, const int32_t* h_coeffs, int32_t h_ksize,
+                     const int32_t* v_bounds, const int32_t* v_coeffs, int32_t v_ksize, int32_t crop_row,
+                     int32_t crop_col, int32_t h_out, int32_t w_out, const float* mean, const float* stdv,
+                     uint8_t* scratch, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,3 +1,5 @@
+"""Per-kernel device-time breakdown of one encoder forward (torch profiler, eager launches, branches off so that the
+kernel times are not inflated by concurrency).  usage: profile_encoder.py [inf|bf16|fp32] [b] [v]"""
 import sys
 from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
@@ -5,12 +7,14 @@ import torch
 from torch.profiler import profile, ProfilerActivity
 from styl3r_b200.encoder import EncoderNoPoSplatTokenStyleCfg, get_encoder
 from tests.encoder_weights import make_inputs
-mode = sys.argv[1] if len(sys.argv) > 1 else "bf16"
+mode = sys.argv[1] if len(sys.argv) > 1 else "inf"
+b = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+v = int(sys.argv[3]) if len(sys.argv) > 3 else 2
 enc, _ = get_encoder(EncoderNoPoSplatTokenStyleCfg(stylized=True)); enc = enc.cuda().eval()
 torch.backends.cuda.matmul.allow_tf32 = True; torch.backends.cudnn.allow_tf32 = True
 if mode == "inf":
-    enc.to_inference(torch.bfloat16)
-context, style = make_inputs(1, 2, 256, seed=1, device="cuda")
+    enc.to_inference(torch.bfloat16, branches=False)
+context, style = make_inputs(b, v, 256, seed=1, device="cuda")
 def step():
     with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=(mode == "bf16")):
         return enc(context, style)
@@ -19,8 +23,8 @@ torch.cuda.synchronize()
 with profile(activities=[ProfilerActivity.CUDA]) as prof:
     step(); torch.cuda.synchronize()
 ev = prof.key_averages()
-rows = sorted(ev, key=lambda e: -e.device_time_total)[:28]
+rows = sorted(ev, key=lambda e: -e.device_time_total)[:32]
 tot = sum(e.device_time_total for e in ev)
-print(f"total device time {tot/1000:.2f} ms")
+print(f"mode={mode} b={b} v={v}: total device time {tot/1000:.2f} ms, {sum(e.count for e in ev)} kernels")
 for e in rows:
-    print(f"{e.device_time_total/1000:8.3f} ms {100*e.device_time_total/tot:5.1f}% n={e.count:4d}  {e.key[:110]}")
+    print(f"{e.device_time_total/1000:8.3f} ms {100*e.device_time_total/tot:5.1f}% n={e.count:4d} avg {e.device_time_total/e.count:7.1f} us  {e.key[:100]}")

@@ -32,7 +32,7 @@ def test_ply_file_round_trip(tmp_path):
     names, rows = read_ply(tmp_path / "sub" / "scene.ply")
     assert names == list(GOLD["ply_plain_names"])
     assert np.abs(rows - GOLD["ply_plain"]).max() <= 2e-6 * np.abs(GOLD["ply_plain"]).max()
-    head = (tmp_path / "sub" / "scene.ply").read_bytes()[:64]
+    head = (tmp_path / "sub" / "scene.ply").read_bytes()[:96]
     assert head.startswith(b"ply\nformat binary_little_endian 1.0\nelement vertex 257\nproperty float x\n")
 
 
