@@ -238,6 +238,12 @@ int s3r_conv2d_bf16(const void* x, const void* w, const void* bias, const void* 
  * s3r_conv2d_bf16 for cout % 256 == 0 - -1 = auto (default; also env S3R_CONV_VARIANT), 0 = 128x128 tiles,
  * 2 CTAs/SM, 1 = 128x256 tiles with a 4-stage ring (1 CTA/SM), 2 = 128x256 tiles with a 2-stage ring (2 CTAs/SM). */
 #define S3R_TUNE_CONV_VARIANT 1
+/* S3R_TUNE_GEMM_CLUSTER: thread-block cluster shape of s3r_gemm_bf16 (TMA multicast of the shared operand tile):
+ * 0 = built-in default, else CM*10 + CN with CM in {1,2} (adjacent M tiles share the W tile), CN in {1,2,4}.
+ * S3R_TUNE_GEMM_BIG_TILE: != 0 lets large grids use 128x256 output tiles. */
+#define S3R_TUNE_GEMM_CLUSTER 2
+#define S3R_TUNE_GEMM_BIG_TILE 3
+#define S3R_TUNE_CONV_CLUSTER 4 /* != 0: s3r_conv2d_bf16 runs clusters of 2 pixel tiles that multicast the weight tile */
 int s3r_set_tunable(int32_t key, int32_t value);
 
 /* Bilinear x2 upsampling, align_corners=True (F.interpolate in heads/dpt_block.py:209-211, dpt_head.py:57,

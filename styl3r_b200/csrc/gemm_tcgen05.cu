@@ -61,6 +61,30 @@ __device__ __forceinline__ void g_tma_load_4d(void* dst, const CUtensorMap* map,
       "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(g_smem_u32(bar))
       : "memory");
 }
+// Multicast variants (thread-block clusters): one L2 read lands in the same shared-memory offset of every CTA in `mask`
+// and completes bytes on each destination CTA's own mbarrier at that offset.
+__device__ __forceinline__ void g_tma_load_2d_mc(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%2, %3}], [%4], %5;" ::"r"(
+          g_smem_u32(dst)),
+      "l"(map), "r"(c0), "r"(c1), "r"(g_smem_u32(bar)), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void g_umma_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   g_smem_u32(bar)),
+               "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ void g_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t g_cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
 //   [0,14) start>>4 | [16,30) LBO>>4 = 1 | [32,46) SBO>>4 = 1024>>4 | [46,48) version = 1 | [61,64) layout = 2 (SW128)
 __device__ __forceinline__ uint64_t g_make_desc(const void* smem_ptr) {
@@ -137,7 +161,13 @@ struct ConvArgs {
   int pad;
 };
 
-template <int BN, int STAGES_, bool kConv>
+// Clusters (CM x CN CTAs = CM adjacent M tiles x CN adjacent N tiles): the CN CTAs that share an M tile each load 1/CN of
+// the A tile and multicast it to the others, the CM CTAs that share an N tile do the same with the W tile, so the L2 ->
+// SM traffic of a cluster is that of one (CM*128) x (CN*BN) tile while the grid keeps the parallelism of small tiles -
+// the M = 257/514-row GEMMs of the batch-1 encoder are bound by exactly that traffic (every SM pulls ~45-64 B/cycle).
+// Ring slots are released cluster-wide: a CTA's `empty` barrier collects one tcgen05.commit from every CTA it
+// multicasts into (its cluster row and column, CM + CN - 1 CTAs).
+template <int BN, int STAGES_, bool kConv, int CM = 1, int CN = 1>
 __global__ void __launch_bounds__(GEMM_THREADS, (STAGES_ * (GEMM_BM + BN) * GEMM_BK * 2 <= 100 * 1024) ? 2 : 1)
 s3r_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const __nv_bfloat16* __restrict__ bias, const __nv_bfloat16* __restrict__ residual, void* __restrict__ Cout,
@@ -166,10 +196,23 @@ s3r_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
     for (int s = 0; s < GEMM_STAGES; s++) {
       g_mbar_init(&full[s], 1);
-      g_mbar_init(&empty[s], 1);
+      g_mbar_init(&empty[s], CM + CN - 1);
     }
     g_mbar_init(tmem_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  constexpr bool kCluster = CM * CN > 1;
+  uint32_t xr = 0, yr = 0;       // this CTA's position inside its cluster (x = M direction, fastest)
+  uint16_t mask_a = 1, mask_b = 1, mask_rel = 1;
+  if (kCluster) {
+    const uint32_t crank = g_cluster_ctarank();
+    xr = crank % CM, yr = crank / CM;
+    mask_a = mask_b = 0;
+#pragma unroll
+    for (int k = 0; k < CN; k++) mask_a |= (uint16_t)(1u << (xr + k * CM));   // CTAs sharing my M tile
+#pragma unroll
+    for (int k = 0; k < CM; k++) mask_b |= (uint16_t)(1u << (k + yr * CM));   // CTAs sharing my N tile
+    mask_rel = mask_a | mask_b;
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(g_smem_u32(tmem_slot)), "r"(BN)
@@ -177,7 +220,9 @@ s3r_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
+  __syncwarp();
+  if (kCluster) g_cluster_sync();  // every CTA's barriers are initialised before any remote multicast / commit
+  else __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
 
@@ -199,10 +244,18 @@ s3r_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           const int tap = (kb0 + kb) / conv.cblocks, cb = (kb0 + kb) - tap * conv.cblocks;
           const int kh = tap / conv.KW, kw = tap - kh * conv.KW;
           g_tma_load_4d(a_dst, &tmA, cb * GEMM_BK, cw0 + kw - conv.pad, ch0 + kh - conv.pad, cn0, &full[s]);
+        } else if (CN > 1) {  // my 128/CN-row slice of the A tile, to every CTA that shares this M tile
+          constexpr int AR = GEMM_BM / CN;
+          g_tma_load_2d_mc(a_dst + yr * AR * 128, &tmA, (kb0 + kb) * GEMM_BK, m0 + yr * AR, &full[s], mask_a);
         } else {
           g_tma_load_2d(a_dst, &tmA, (kb0 + kb) * GEMM_BK, m0, &full[s]);
         }
-        g_tma_load_2d(b_dst, &tmB, (kb0 + kb) * GEMM_BK, n0, &full[s]);
+        if (CM > 1) {         // my BN/CM-row slice of the W tile, to every CTA that shares this N tile
+          constexpr int BR = BN / CM;
+          g_tma_load_2d_mc(b_dst + xr * BR * 128, &tmB, (kb0 + kb) * GEMM_BK, n0 + xr * BR, &full[s], mask_b);
+        } else {
+          g_tma_load_2d(b_dst, &tmB, (kb0 + kb) * GEMM_BK, n0, &full[s]);
+        }
       }
     }
   } else if (warp == 1) {
@@ -217,7 +270,9 @@ s3r_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 #pragma unroll
         for (int k = 0; k < GEMM_BK / 16; k++)  // advance 16 bf16 = 32 B inside the 128-B swizzle atom: +2 in >>4 units
           g_umma(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
-        g_umma_commit(&empty[s]);  // frees the ring slot once these MMAs have read it
+        // frees the ring slot once these MMAs have read it (in every CTA that multicasts into it)
+        if (kCluster) g_umma_commit_mc(&empty[s], mask_rel);
+        else g_umma_commit(&empty[s]);
       }
       g_umma_commit(tmem_full);  // accumulator complete
     }
@@ -401,7 +456,9 @@ s3r_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     }  // cg
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
+  __syncwarp();                    // reconverge the single-lane producer / MMA warps: barrier.cluster is .aligned
+  if (kCluster) g_cluster_sync();  // no CTA may retire while a peer can still multicast into it / signal its barriers
+  else __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(BN) : "memory");
@@ -412,6 +469,10 @@ s3r_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int g_gemm_cluster = 0;   // S3R_TUNE_GEMM_CLUSTER: 0 = default, else CM*10 + CN
+static int g_gemm_big_tile = 0;  // S3R_TUNE_GEMM_BIG_TILE: 128x256 tiles for grids of >= 120 such tiles
+static int g_conv_cluster = 0;   // S3R_TUNE_CONV_CLUSTER: pairs of pixel tiles multicast the weight tile
 
 static PFN_encodeTiled get_encode() {
   static PFN_encodeTiled fn = nullptr;
@@ -440,21 +501,34 @@ static int make_map(CUtensorMap* map, const void* ptr, int rows, int cols, int l
   return r == CUDA_SUCCESS ? S3R_OK : S3R_ERR_CUDA;
 }
 
-template <int BN, int STAGES_, bool kConv = false>
+template <int BN, int STAGES_, bool kConv = false, int CM = 1, int CN = 1>
 static int launch_gemm(const CUtensorMap& a, const CUtensorMap& b, const void* bias, const void* residual, void* C, int M,
                        int N, int K, int ldc, int ldr, int flags, const RopeArgs& rope, int splits, float* ws, unsigned* counters,
                        cudaStream_t st, const ConvArgs& conv = ConvArgs{}) {
   static bool configured = false;
   const int smem = GemmSmem<BN, STAGES_>::TOTAL;
+  auto kern = s3r_gemm_bf16_kernel<BN, STAGES_, kConv, CM, CN>;
   if (!configured) {
-    S3R_CUDA_CHECK(cudaFuncSetAttribute(s3r_gemm_bf16_kernel<BN, STAGES_, kConv>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    S3R_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  dim3 grid((M + GEMM_BM - 1) / GEMM_BM, (N + BN - 1) / BN, splits);
-  s3r_gemm_bf16_kernel<BN, STAGES_, kConv><<<grid, GEMM_THREADS, smem, st>>>(
-      a, b, (const __nv_bfloat16*)bias, (const __nv_bfloat16*)residual, C, M, N, K, ldc, ldr, flags, rope, splits, ws,
-      counters, conv);
-  S3R_CUDA_CHECK(cudaGetLastError());
+  // grid padded to whole clusters: CTAs past the last tile still take part in the multicast (their own loads are fully
+  // out of bounds = zero fill, their epilogue is masked)
+  const unsigned gx = ((M + GEMM_BM - 1) / GEMM_BM + CM - 1) / CM * CM, gy = ((N + BN - 1) / BN + CN - 1) / CN * CN;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(gx, gy, splits);
+  cfg.blockDim = dim3(GEMM_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CM;
+  attr[0].val.clusterDim.y = CN;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (CM * CN > 1) ? 1 : 0;
+  S3R_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, a, b, (const __nv_bfloat16*)bias, (const __nv_bfloat16*)residual, C, M, N, K,
+                                    ldc, ldr, flags, rope, splits, ws, counters, conv));
   return S3R_OK;
 }
 
@@ -513,9 +587,14 @@ extern "C" int s3r_gemm_bf16_rope(const void* A, const void* W, const void* bias
   // fewer than ~1 wave of 128x128 tiles: use 128x64 tiles to fill the 148 SMs
   const long mt = (M + 127) / 128;
   const long tiles128 = mt * ((N + 127) / 128), tiles64 = mt * ((N + 63) / 64);
-  const int BN = tiles128 >= 120 ? 128 : 64;  // (BN=32 measured slower: every N-tile re-reads the A tile from L2)
-  if ((rc = make_map(&ta, A, M, K, lda, GEMM_BM)) != S3R_OK) return rc;
-  if ((rc = make_map(&tb, W, N, K, ldw, BN)) != S3R_OK) return rc;
+  int BN = tiles128 >= 120 ? 128 : 64;  // (BN=32 measured slower: every N-tile re-reads the A tile from L2)
+  if (BN == 128 && g_gemm_big_tile && N % 256 == 0 && mt * (N / 256) >= 120) BN = 256;
+  int cm = 1, cn = 1;  // cluster shape (multicast): tunable, else the measured default per tile class
+  if (g_gemm_cluster > 0) cm = g_gemm_cluster / 10, cn = g_gemm_cluster % 10;
+  if ((N + BN - 1) / BN < cn) cn = 1;
+  if (mt < cm) cm = 1;
+  if ((rc = make_map(&ta, A, M, K, lda, GEMM_BM / cn)) != S3R_OK) return rc;
+  if ((rc = make_map(&tb, W, N, K, ldw, BN / cm)) != S3R_OK) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   // split-K for grids smaller than the machine: every SM pulls ~45 B/cycle from L2, so a 36-CTA grid streams its
   // operands at a quarter of the chip's L2 bandwidth; more CTAs with shorter K ranges fix exactly that.
@@ -536,12 +615,27 @@ extern "C" int s3r_gemm_bf16_rope(const void* A, const void* W, const void* bias
       ws = (float*)((char*)workspace + 16384);
     }
   }
+#define S3R_GEMM_GO(BN_, ST_, CM_, CN_)                                                                             \
+  return launch_gemm<BN_, ST_, false, CM_, CN_>(ta, tb, bias, residual, C, M, N, K, ldc, ldr, flags, rope, splits, ws, \
+                                                 counters, st)
+#define S3R_GEMM_CLUSTERS(BN_, ST_)                  \
+  do {                                               \
+    if (cm == 1 && cn == 2) S3R_GEMM_GO(BN_, ST_, 1, 2); \
+    if (cm == 1 && cn == 4) S3R_GEMM_GO(BN_, ST_, 1, 4); \
+    if (cm == 2 && cn == 1) S3R_GEMM_GO(BN_, ST_, 2, 1); \
+    if (cm == 2 && cn == 2) S3R_GEMM_GO(BN_, ST_, 2, 2); \
+    if (cm == 2 && cn == 4) S3R_GEMM_GO(BN_, ST_, 2, 4); \
+    S3R_GEMM_GO(BN_, ST_, 1, 1);                     \
+  } while (0)
   if (BN == 64) {
-    if (tiles64 * splits < 148)
-      return launch_gemm<64, 8>(ta, tb, bias, residual, C, M, N, K, ldc, ldr, flags, rope, splits, ws, counters, st);
-    return launch_gemm<64, 4>(ta, tb, bias, residual, C, M, N, K, ldc, ldr, flags, rope, splits, ws, counters, st);
+    if (tiles64 * splits < 148) S3R_GEMM_CLUSTERS(64, 8);
+    S3R_GEMM_CLUSTERS(64, 4);
   }
-  return launch_gemm<128, 3>(ta, tb, bias, residual, C, M, N, K, ldc, ldr, flags, rope, 1, nullptr, nullptr, st);
+  splits = 1, ws = nullptr, counters = nullptr;
+  if (BN == 256) S3R_GEMM_CLUSTERS(256, 2);
+  S3R_GEMM_CLUSTERS(128, 3);
+#undef S3R_GEMM_CLUSTERS
+#undef S3R_GEMM_GO
 }
 
 extern "C" int s3r_gemm_bf16(const void* A, const void* W, const void* bias, const void* residual, void* C, int32_t M,
@@ -562,6 +656,20 @@ extern "C" int s3r_gemm_bf16(const void* A, const void* W, const void* bias, con
 static int g_conv_variant = -2;
 
 extern "C" int s3r_set_tunable(int32_t key, int32_t value) {
+  if (key == S3R_TUNE_GEMM_CLUSTER) {
+    const int cm = value / 10, cn = value % 10;
+    if (value != 0 && !((cm == 1 || cm == 2) && (cn == 1 || cn == 2 || cn == 4))) return S3R_ERR_INVALID_ARG;
+    g_gemm_cluster = value;
+    return S3R_OK;
+  }
+  if (key == S3R_TUNE_CONV_CLUSTER) {
+    g_conv_cluster = value != 0;
+    return S3R_OK;
+  }
+  if (key == S3R_TUNE_GEMM_BIG_TILE) {
+    g_gemm_big_tile = value != 0;
+    return S3R_OK;
+  }
   if (key == S3R_TUNE_CONV_VARIANT) {
     if (value < -1 || value > 2) return S3R_ERR_INVALID_ARG;
     g_conv_variant = value;
@@ -613,9 +721,19 @@ extern "C" int s3r_conv2d_bf16(const void* x, const void* w, const void* bias, c
   CUtensorMap ta, tb;
   int rc;
   if ((rc = make_map_nhwc(&ta, x, n, h, wd, cin, bw, bh, bn)) != S3R_OK) return rc;
-  if ((rc = make_map(&tb, w, cout, K, K, BN)) != S3R_OK) return rc;
+  // clusters of 2 adjacent pixel tiles share the weight tile: each loads half of it and multicasts (the weights are the
+  // operand every M tile re-reads; the activation patch of a 128x256 tile is already read once per tap)
+  const int cm = (g_conv_cluster && (M + GEMM_BM - 1) / GEMM_BM >= 2 && BN >= 128) ? 2 : 1;
+  if ((rc = make_map(&tb, w, cout, K, K, BN / cm)) != S3R_OK) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   RopeArgs rope{nullptr, nullptr, 0, 0};
+  if (cm == 2) {
+    if (BN == 256 && variant == 1)
+      return launch_gemm<256, 4, true, 2, 1>(ta, tb, bias, residual, y, (int)M, cout, K, cout, cout, flags, rope, 1, nullptr, nullptr, st, conv);
+    if (BN == 256)
+      return launch_gemm<256, 2, true, 2, 1>(ta, tb, bias, residual, y, (int)M, cout, K, cout, cout, flags, rope, 1, nullptr, nullptr, st, conv);
+    return launch_gemm<128, 3, true, 2, 1>(ta, tb, bias, residual, y, (int)M, cout, K, cout, cout, flags, rope, 1, nullptr, nullptr, st, conv);
+  }
   if (BN == 64) return launch_gemm<64, 4, true>(ta, tb, bias, residual, y, (int)M, cout, K, cout, cout, flags, rope, 1, nullptr, nullptr, st, conv);
   if (BN == 256 && variant == 1)
     return launch_gemm<256, 4, true>(ta, tb, bias, residual, y, (int)M, cout, K, cout, cout, flags, rope, 1, nullptr, nullptr, st, conv);

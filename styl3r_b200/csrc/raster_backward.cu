@@ -21,8 +21,8 @@
 #define BB_U 3  // records per reduction batch: 3 x 10 gradient values fill a 32-lane butterfly
 #define ACC_STRIDE 12
 #define ALPHA_MIN (1.0f / 255.0f)
-#define ALPHA_LO (ALPHA_MIN * (1.0f - 2e-5f))
-#define ALPHA_HI (ALPHA_MIN * (1.0f + 2e-5f))
+#define ALPHA_LO (ALPHA_MIN * (1.0f - S3R_ALPHA_BAND))
+#define ALPHA_HI (ALPHA_MIN * (1.0f + S3R_ALPHA_BAND))
 
 __device__ __forceinline__ uint32_t bsmem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void bmbar_init(uint64_t* bar, uint32_t count) {
@@ -57,6 +57,11 @@ __device__ __forceinline__ void bbulk_g2s(void* dst, const void* src, uint32_t b
                "l"(src), "r"(bytes), "r"(bsmem_u32(bar))
                : "memory");
 }
+__device__ __forceinline__ float bfast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __noinline__ float bexact_alpha(float power, float opacity) {
   const float e = (float)exp((double)power);
   return fminf(0.99f, __fmul_rn(opacity, e));
@@ -87,7 +92,8 @@ struct __align__(128) BwdSmem {
 
 __global__ void __launch_bounds__(BB_THREADS, 2) s3r_blend_bwd_kernel(
     int W, int H, int P, int tiles_x, int tiles, const uint2* __restrict__ ranges, const float4* __restrict__ records,
-    const uint32_t* __restrict__ point_list, const float* __restrict__ background, const float* __restrict__ final_T,
+    const uint32_t* __restrict__ point_list, const float4* __restrict__ conic_opacity,
+    const float* __restrict__ background, const float* __restrict__ final_T,
     const uint32_t* __restrict__ n_contrib, const float* __restrict__ dL_dcolor, const float* __restrict__ dL_ddepth,
     float* __restrict__ acc) {
   __shared__ BwdSmem sm;
@@ -203,16 +209,29 @@ __global__ void __launch_bounds__(BB_THREADS, 2) s3r_blend_bwd_kernel(
           const float4 r1 = sm.rec[s][i * 3 + 1];
           const float4 r2 = sm.rec[s][i * 3 + 2];
           const float dx = r0.x - pxf, dy = r0.y - pyf;
-          const float qf = __fadd_rn(__fmul_rn(__fmul_rn(r0.z, dx), dx), __fmul_rn(__fmul_rn(r1.x, dy), dy));
-          const float power = __fsub_rn(__fmul_rn(-0.5f, qf), __fmul_rn(__fmul_rn(r0.w, dx), dy));
-          const float G = __expf(power);
+          // same fast log2-domain evaluation and guard bands as the forward kernel (raster_blend.cu), so that the
+          // set of contributing Gaussians is the one the forward pass composited
+          const float l2g = fmaf(dx, fmaf(r0.z, dx, r0.w * dy), (r1.x * dy) * dy);
+          float G = bfast_exp2(l2g);
           float alpha = fminf(0.99f, r1.y * G);
-          bool kp = kk >= 0 && (base_idx + (uint32_t)i) < last && !(power > 0.0f);
-          if (kp && alpha < ALPHA_HI) {
-            kp = false;
-            if (alpha >= ALPHA_LO) {
-              alpha = bexact_alpha(power, r1.y);
-              kp = alpha >= ALPHA_MIN;
+          bool kp = kk >= 0 && (base_idx + (uint32_t)i) < last;
+          // the true conic for the gradient formulas (the record holds A' = KA*A, B' = KB*B, C' = KA*C)
+          float cA = r0.z * S3R_INV_KA, cB = r0.w * S3R_INV_KB, cC = r1.x * S3R_INV_KA;
+          if (kp) {
+            if ((alpha >= ALPHA_LO && alpha < ALPHA_HI) || fabsf(l2g) < S3R_PZERO_BAND) {
+              const uint32_t gid = __ldg(point_list + (size_t)rg.x + base_idx + i);
+              const float4 co = __ldg(conic_opacity + (size_t)view * P + gid);
+              const float qf = __fadd_rn(__fmul_rn(__fmul_rn(co.x, dx), dx), __fmul_rn(__fmul_rn(co.z, dy), dy));
+              const float power = __fsub_rn(__fmul_rn(-0.5f, qf), __fmul_rn(__fmul_rn(co.y, dx), dy));
+              kp = !(power > 0.0f);
+              if (kp) {
+                alpha = bexact_alpha(power, co.w);
+                kp = alpha >= ALPHA_MIN;
+                G = __expf(power);
+                cA = co.x, cB = co.y, cC = co.z;
+              }
+            } else {
+              kp = !(l2g > 0.0f) && alpha >= ALPHA_HI;
             }
           }
           if (kp) {
@@ -231,8 +250,8 @@ __global__ void __launch_bounds__(BB_THREADS, 2) s3r_blend_bwd_kernel(
             dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot;
             const float dL_dG = r1.y * dL_dalpha;
             const float gdx = G * dx, gdy = G * dy;
-            const float dG_ddelx = -gdx * r0.z - gdy * r0.w;
-            const float dG_ddely = -gdy * r1.x - gdx * r0.w;
+            const float dG_ddelx = -gdx * cA - gdy * cB;
+            const float dG_ddely = -gdy * cC - gdx * cB;
             v[u * 10 + 0] = dL_dG * dG_ddelx * ddelx_dx;
             v[u * 10 + 1] = dL_dG * dG_ddely * ddely_dy;
             v[u * 10 + 2] = -0.5f * gdx * dx * dL_dG;
@@ -561,7 +580,8 @@ extern "C" int s3r_raster_backward(const s3r_raster_params* params, const void* 
   dim3 g1(L.tiles, params->n_views);
   s3r_blend_bwd_kernel<<<g1, BB_THREADS, 0, st>>>(
       params->width, params->height, params->P, L.tiles_x, L.tiles, (const uint2*)(s + L.ranges),
-      (const float4*)(s + L.records), (const uint32_t*)(s + L.point_list), params->background,
+      (const float4*)(s + L.records), (const uint32_t*)(s + L.point_list), (const float4*)(s + L.conic_opacity),
+      params->background,
       (const float*)(s + L.final_T), (const uint32_t*)(s + L.n_contrib), grads->dL_dcolor, grads->dL_ddepth, acc);
   S3R_CUDA_CHECK(cudaGetLastError());
   dim3 g2((params->P + 255) / 256, params->n_views);

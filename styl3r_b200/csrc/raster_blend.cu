@@ -10,16 +10,17 @@
 // 1/255 is result-neutral).
 //
 // Semantics follow upstream renderCUDA + the "-w-pose" fork (blended depth, opacity, n_touched) as restated by
-// oracle/raster_oracle.c:s3r_oracle_render:  power is evaluated with the
-// oracle's exact unfused fp32 operation order; exp uses MUFU.EX2, and the rare evaluations whose alpha
-// lands within 2e-5 (relative) of the 1/255 threshold are re-evaluated with a correctly rounded exp so
-// that the keep/skip decision matches the oracle.
+// oracle/raster_oracle.c:s3r_oracle_render.  The Gaussian exponent is evaluated
+// in the log2 domain from the pre-scaled conic of the record (2 FMUL + 2 FFMA + FMUL, MUFU.EX2); the rare
+// evaluations whose alpha lands within 1e-4 (relative) of the 1/255 threshold, or whose exponent is within
+// 1e-5 of zero, are decided again from the exact per-Gaussian conic with the oracle's unfused fp32 operation
+// order and a correctly rounded exp, so that every keep/skip decision equals the oracle's.
 #include "s3r_common.cuh"
 
 #define BLEND_CHUNK 128
 #define ALPHA_MIN (1.0f / 255.0f)
-#define ALPHA_LO (ALPHA_MIN * (1.0f - 2e-5f))
-#define ALPHA_HI (ALPHA_MIN * (1.0f + 2e-5f))
+#define ALPHA_LO (ALPHA_MIN * (1.0f - S3R_ALPHA_BAND))
+#define ALPHA_HI (ALPHA_MIN * (1.0f + S3R_ALPHA_BAND))
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -72,7 +73,7 @@ __device__ __noinline__ float exact_alpha(float power, float opacity) {
 #define BLEND_THREADS (32 * (BLEND_CWARPS + 1))
 
 struct __align__(128) BlendSmem {
-  float4 rec[BLEND_STAGES][BLEND_CHUNK * 3];
+  float4 rec[BLEND_STAGES][(BLEND_CHUNK + 1) * 3];  // + one dummy record per stage (never hits): pads survivor batches
   uint8_t list[BLEND_CWARPS][BLEND_CHUNK + 16];  // per-warp compacted survivor indices
   uint64_t full[BLEND_STAGES];                   // producer -> consumers (expect_tx / complete_tx)
   uint64_t empty[BLEND_STAGES];                  // consumers -> producer (one arrival per consumer warp)
@@ -99,16 +100,26 @@ __device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
 // Warp-specialised: warp 8 streams the tile's records through a BLEND_STAGES-deep ring with TMA bulk copies;
 // the 8 consumer warps run decoupled from each other (no CTA-wide barrier in the main loop): each culls the
 // stage against its own 8x4 pixel block, composites the survivors front to back, and releases the stage.
-__device__ __forceinline__ float fast_exp(float x) {  // MUFU.EX2 (flush-to-zero): |rel err| ~2^-21 * |x|
+__device__ __forceinline__ float fast_exp2(float x) {  // MUFU.EX2 (flush-to-zero): |rel err| ~2^-22
   float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+// oracle-identical decision for one (pixel, Gaussian): unfused fp32 power from the exact conic, correctly rounded exp
+__device__ __noinline__ bool exact_decide(const float4 co, float dx, float dy, float* alpha_out) {
+  const float q = __fadd_rn(__fmul_rn(__fmul_rn(co.x, dx), dx), __fmul_rn(__fmul_rn(co.z, dy), dy));
+  const float power = __fsub_rn(__fmul_rn(-0.5f, q), __fmul_rn(__fmul_rn(co.y, dx), dy));
+  if (power > 0.0f) return false;
+  const float a = exact_alpha(power, co.w);
+  *alpha_out = a;
+  return a >= ALPHA_MIN;
 }
 
 template <bool kHasNT>
 __global__ void __launch_bounds__(BLEND_THREADS, BLEND_MINB) s3r_blend_fwd_kernel(
     int W, int H, int P, int tiles_x, int tiles, const uint2* __restrict__ ranges, const float4* __restrict__ records,
-    const uint32_t* __restrict__ point_list, const float* __restrict__ background, float* __restrict__ out_color,
+    const uint32_t* __restrict__ point_list, const float4* __restrict__ conic_opacity,
+    const float* __restrict__ background, float* __restrict__ out_color,
     float* __restrict__ out_depth, float* __restrict__ out_opacity, float* __restrict__ final_T,
     uint32_t* __restrict__ n_contrib, int32_t* __restrict__ n_touched) {
   __shared__ BlendSmem sm;
@@ -127,6 +138,11 @@ __global__ void __launch_bounds__(BLEND_THREADS, BLEND_MINB) s3r_blend_fwd_kerne
     }
     sm.done_warps = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (tid < BLEND_STAGES) {  // dummy record: so far away that log2 G = -1.8e19 -> alpha = 0 (no range predicates in the loop)
+    sm.rec[tid][BLEND_CHUNK * 3] = make_float4(3e9f, 3e9f, -1.0f, 0.0f);
+    sm.rec[tid][BLEND_CHUNK * 3 + 1] = make_float4(-1.0f, 0.0f, 0.0f, 0.0f);
+    sm.rec[tid][BLEND_CHUNK * 3 + 2] = make_float4(0.0f, 0.0f, -1.0f, -1.0f);
   }
   __syncthreads();
 
@@ -209,6 +225,7 @@ __global__ void __launch_bounds__(BLEND_THREADS, BLEND_MINB) s3r_blend_fwd_kerne
       if (hit) list[count + __popc(m & lt)] = (uint8_t)i;
       count += __popc(m);
     }
+    if (lane < BLEND_U) list[count + lane] = (uint8_t)BLEND_CHUNK;  // pad the last batch with the dummy record
     __syncwarp();
     const uint32_t base_idx = c * BLEND_CHUNK;
 #pragma unroll 1
@@ -219,45 +236,45 @@ __global__ void __launch_bounds__(BLEND_THREADS, BLEND_MINB) s3r_blend_fwd_kerne
       float alpha[BLEND_U], cr[BLEND_U], cg[BLEND_U], cb[BLEND_U], dp[BLEND_U];
       bool keep[BLEND_U];
       int idx[BLEND_U];
-      bool near_thr = false;
+      unsigned near_thr = 0u;  // (bitwise flag arithmetic below: short-circuit && / || would compile to divergent branches)
       // ---- BLEND_U independent alpha chains (branch-free)
 #pragma unroll
       for (int u = 0; u < BLEND_U; u++) {
-        // bytes past `count` are stale: mask them into range, `valid` discards them
-        const int i = (packed[u >> 2] >> (8 * (u & 3))) & (BLEND_CHUNK - 1);
+        const int i = (packed[u >> 2] >> (8 * (u & 3))) & 0xff;  // entries past `count` are the dummy record
         idx[u] = i;
         const float4 r0 = sm.rec[s][i * 3];
         const float4 r1 = sm.rec[s][i * 3 + 1];
         const float2 r2 = *reinterpret_cast<const float2*>(&sm.rec[s][i * 3 + 2]);
         const float dx = r0.x - pxf, dy = r0.y - pyf;
-        const float q = __fadd_rn(__fmul_rn(__fmul_rn(r0.z, dx), dx), __fmul_rn(__fmul_rn(r1.x, dy), dy));
-        const float power = __fsub_rn(__fmul_rn(-0.5f, q), __fmul_rn(__fmul_rn(r0.w, dx), dy));
-        const float a = fminf(0.99f, r1.y * fast_exp(power));
-        const bool valid = (k + u < count) && !(power > 0.0f);
-        keep[u] = valid && a >= ALPHA_HI;
-        near_thr |= valid && a >= ALPHA_LO && a < ALPHA_HI;
+        // log2 G = dx*(A'*dx + B'*dy) + C'*dy*dy on the pre-scaled conic: 2 FMUL + 2 FFMA + 1 FMUL, then MUFU.EX2
+        const float l2g = fmaf(dx, fmaf(r0.z, dx, r0.w * dy), (r1.x * dy) * dy);
+        const float a = fminf(0.99f, r1.y * fast_exp2(l2g));
+        const unsigned hi = (unsigned)(a >= ALPHA_HI);
+        keep[u] = ((unsigned)(l2g <= 0.0f) & hi) != 0u;
+        // guard bands: alpha within 1e-4 (relative) of 1/255, or an exponent so close to 0 that its sign is in doubt
+        near_thr |= ((unsigned)(a >= ALPHA_LO) & (hi ^ 1u)) | (unsigned)(fabsf(l2g) < S3R_PZERO_BAND);
         alpha[u] = a;
         cr[u] = r1.z;
         cg[u] = r1.w;
         cb[u] = r2.x;
         dp[u] = r2.y;
       }
-      // ---- rare: some evaluation landed within 2e-5 of the 1/255 threshold -> decide it with the exact exp
-      if (__any_sync(0xffffffffu, near_thr)) {
+      // ---- rare: some evaluation landed in a guard band -> decide it like the oracle, from the exact conic
+      if (__any_sync(0xffffffffu, near_thr != 0u)) {
 #pragma unroll
         for (int u = 0; u < BLEND_U; u++) {
-          const float a = alpha[u];
-          if ((k + u < count) && a >= ALPHA_LO && a < ALPHA_HI) {
+          if (k + u < count) {
             const int i = idx[u];
             const float4 r0 = sm.rec[s][i * 3];
             const float4 r1 = sm.rec[s][i * 3 + 1];
             const float dx = r0.x - pxf, dy = r0.y - pyf;
-            const float q = __fadd_rn(__fmul_rn(__fmul_rn(r0.z, dx), dx), __fmul_rn(__fmul_rn(r1.x, dy), dy));
-            const float power = __fsub_rn(__fmul_rn(-0.5f, q), __fmul_rn(__fmul_rn(r0.w, dx), dy));
-            if (!(power > 0.0f)) {
-              const float ax = exact_alpha(power, r1.y);
+            const float l2g = fmaf(dx, fmaf(r0.z, dx, r0.w * dy), (r1.x * dy) * dy);
+            const float a = alpha[u];
+            if ((a >= ALPHA_LO && a < ALPHA_HI) || fabsf(l2g) < S3R_PZERO_BAND) {
+              const uint32_t gid = point_list[(size_t)rg.x + base_idx + i];
+              float ax = a;
+              keep[u] = exact_decide(conic_opacity[(size_t)view * P + gid], dx, dy, &ax);
               alpha[u] = ax;
-              keep[u] = ax >= ALPHA_MIN;
             }
           }
         }
@@ -314,7 +331,8 @@ int s3r_launch_blend(const s3r_raster_params& p, const s3r_raster_outputs& o, co
   auto kern = o.n_touched ? s3r_blend_fwd_kernel<true> : s3r_blend_fwd_kernel<false>;
   kern<<<grid, BLEND_THREADS, 0, st>>>(
       p.width, p.height, p.P, L.tiles_x, L.tiles, (const uint2*)(state + L.ranges),
-      (const float4*)(state + L.records), (const uint32_t*)(state + L.point_list), p.background, o.color, o.depth,
+      (const float4*)(state + L.records), (const uint32_t*)(state + L.point_list),
+      (const float4*)(state + L.conic_opacity), p.background, o.color, o.depth,
       o.opacity, (float*)(state + L.final_T), (uint32_t*)(state + L.n_contrib), o.n_touched);
   S3R_CUDA_CHECK(cudaGetLastError());
   return S3R_OK;

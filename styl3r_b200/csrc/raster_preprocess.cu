@@ -18,9 +18,12 @@ __device__ __constant__ float kSH_C3[7] = {-0.5900435899266435f, 2.8906114426405
 
 __device__ __forceinline__ float3 sh_to_rgb(int deg, int M, const float* __restrict__ sh, float3 p, const float* campos,
                                             unsigned& clampmask) {
-  float dx = p.x - campos[0], dy = p.y - campos[1], dz = p.z - campos[2];
-  float len = sqrtf(dx * dx + dy * dy + dz * dz);
-  float x = dx / len, y = dy / len, z = dz / len;
+  float x = 0.f, y = 0.f, z = 0.f;
+  if (deg > 0) {  // the view direction only enters the degree >= 1 bands (Styl3R ships degree 0)
+    float dx = p.x - campos[0], dy = p.y - campos[1], dz = p.z - campos[2];
+    float len = sqrtf(dx * dx + dy * dy + dz * dz);
+    x = dx / len, y = dy / len, z = dz / len;
+  }
   float out[3];
 #pragma unroll
   for (int c = 0; c < 3; c++) {
@@ -76,6 +79,11 @@ __global__ void __launch_bounds__(S3R_CHUNK) s3r_preprocess_kernel(
     vc.scale = s;
     vc.scale2 = s * s;
     vc.set = prm.view_set ? prm.view_set[view] : view;
+    // per-view constants of computeCov2D, evaluated once (same single-rounding ops as per Gaussian)
+    vc.fx = W / (2.0f * vc.tanx);
+    vc.fy = H / (2.0f * vc.tany);
+    vc.limx = 1.3f * vc.tanx;
+    vc.limy = 1.3f * vc.tany;
   }
   for (int i = tid; i < tiles * 8; i += S3R_CHUNK) s_mask[i] = 0u;
   if (view == 0 && chunk == 0 && tid < 4) {
@@ -91,7 +99,23 @@ __global__ void __launch_bounds__(S3R_CHUNK) s3r_preprocess_kernel(
     const size_t vi = (size_t)view * P + g;     // index into per-view arrays
     const float s = vc.scale, s2 = vc.scale2;
     const float* mp = prm.means3D + gi * 3;
-    float3 p = make_float3(__ldg(mp) * s, __ldg(mp + 1) * s, __ldg(mp + 2) * s);
+    // all inputs of this Gaussian are requested up front: one DRAM round trip instead of three dependent ones
+    // (mean -> cull test -> covariance -> rect test -> colour / opacity)
+    const float m0 = __ldg(mp), m1 = __ldg(mp + 1), m2 = __ldg(mp + 2);
+    const float* cp = prm.cov3D + gi * prm.cov_stride;
+    const bool full33 = prm.cov_stride == 9;
+    const float r0 = __ldg(cp), r1 = __ldg(cp + 1), r2 = __ldg(cp + 2), r3 = __ldg(cp + (full33 ? 4 : 3)),
+                r4 = __ldg(cp + (full33 ? 5 : 4)), r5 = __ldg(cp + (full33 ? 8 : 5));
+    const float opac_in = __ldg(prm.opacities + gi);
+    float sh0[3] = {0.f, 0.f, 0.f};
+    if (prm.colors_precomp) {
+      const float* q = prm.colors_precomp + gi * 3;
+      sh0[0] = __ldg(q), sh0[1] = __ldg(q + 1), sh0[2] = __ldg(q + 2);
+    } else if (prm.sh_degree == 0) {
+      const float* q = prm.shs + gi * prm.sh_coeffs * 3;
+      sh0[0] = __ldg(q), sh0[1] = __ldg(q + 1), sh0[2] = __ldg(q + 2);
+    }
+    float3 p = make_float3(m0 * s, m1 * s, m2 * s);
     const float* vm = vc.vm;
     const float* pm = vc.pm;
     float3 t;
@@ -110,18 +134,9 @@ __global__ void __launch_bounds__(S3R_CHUNK) s3r_preprocess_kernel(
       float pw = 1.0f / (hw + 0.0000001f);
       float ndcx = hx * pw, ndcy = hy * pw;
       // packed symmetric covariance (xx,xy,xz,yy,yz,zz), scaled
-      const float* cp = prm.cov3D + gi * prm.cov_stride;
-      float c0, c1, c2, c3, c4, c5;
-      if (prm.cov_stride == 9) {
-        c0 = __ldg(cp) * s2; c1 = __ldg(cp + 1) * s2; c2 = __ldg(cp + 2) * s2;
-        c3 = __ldg(cp + 4) * s2; c4 = __ldg(cp + 5) * s2; c5 = __ldg(cp + 8) * s2;
-      } else {
-        c0 = __ldg(cp) * s2; c1 = __ldg(cp + 1) * s2; c2 = __ldg(cp + 2) * s2;
-        c3 = __ldg(cp + 3) * s2; c4 = __ldg(cp + 4) * s2; c5 = __ldg(cp + 5) * s2;
-      }
+      const float c0 = r0 * s2, c1 = r1 * s2, c2 = r2 * s2, c3 = r3 * s2, c4 = r4 * s2, c5 = r5 * s2;
       // --- computeCov2D, glm op order (see oracle cov2d) with the structurally-zero terms dropped
-      const float fx = W / (2.0f * vc.tanx), fy = H / (2.0f * vc.tany);
-      const float limx = 1.3f * vc.tanx, limy = 1.3f * vc.tany;
+      const float fx = vc.fx, fy = vc.fy, limx = vc.limx, limy = vc.limy;
       const float txtz = t.x / t.z, tytz = t.y / t.z;
       const float tx = fminf(limx, fmaxf(-limx, txtz)) * t.z;
       const float ty = fminf(limy, fmaxf(-limy, tytz)) * t.z;
@@ -159,15 +174,27 @@ __global__ void __launch_bounds__(S3R_CHUNK) s3r_preprocess_kernel(
           unsigned clampmask = 0u;
           float3 c;
           if (prm.colors_precomp) {
-            const float* q = prm.colors_precomp + gi * 3;
-            c = make_float3(__ldg(q), __ldg(q + 1), __ldg(q + 2));
+            c = make_float3(sh0[0], sh0[1], sh0[2]);
+          } else if (prm.sh_degree == 0) {  // DC band already in registers: rgb = C0 * sh + 0.5, clamped at 0
+            float o3[3];
+#pragma unroll
+            for (int ch = 0; ch < 3; ch++) {
+              float r = SH_C0 * sh0[ch];
+              r += 0.5f;
+              if (r < 0.0f) {
+                clampmask |= (1u << ch);
+                r = 0.0f;
+              }
+              o3[ch] = r;
+            }
+            c = make_float3(o3[0], o3[1], o3[2]);
           } else {
             c = sh_to_rgb(prm.sh_degree, prm.sh_coeffs, prm.shs + gi * prm.sh_coeffs * 3, p, vc.campos, clampmask);
           }
           radius = r;
           depth = t.z;
           pix = make_float2(px, py);
-          co = make_float4(cyy * det_inv, -cxy * det_inv, cxx * det_inv, __ldg(prm.opacities + gi));
+          co = make_float4(cyy * det_inv, -cxy * det_inv, cxx * det_inv, opac_in);
           col = make_float4(c.x, c.y, c.z, __uint_as_float(clampmask));
           rect = (uint32_t)xmin | ((uint32_t)ymin << 8) | ((uint32_t)xmax << 16) | ((uint32_t)ymax << 24);
           const uint32_t bit = 1u << (tid & 31);

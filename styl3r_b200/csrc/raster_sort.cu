@@ -7,7 +7,7 @@
 // (oracle/raster_oracle.c:s3r_oracle_bin_sort).
 //
 // The epilogue writes point_list (sorted gaussian ids), optionally the 64-bit upstream-format keys, and
-// the 48-byte sorted-gathered blend records that the blend kernel streams with TMA bulk copies:
+// the 48-byte sorted-gathered blend records (conic pre-scaled to the log2 domain) that the blend kernels stream with TMA bulk copies:
 //   (x, y, conicA, conicB | conicC, opacity, r, g | b, depth, ex, ey)
 // where (ex, ey) is the half-extent in pixels of the region where alpha can reach 1/255.
 #include "s3r_common.cuh"
@@ -163,8 +163,8 @@ __global__ void __launch_bounds__(SORT_THREADS) s3r_tile_sort_kernel(
       ex = ey = 1e30f;  // degenerate conic: never cull
     }
     float4* r = records + o * 3;
-    r[0] = make_float4(p.x, p.y, co.x, co.y);
-    r[1] = make_float4(co.z, co.w, c.x, c.y);
+    r[0] = make_float4(p.x, p.y, co.x * S3R_KA, co.y * S3R_KB);   // log2-domain conic (s3r_common.cuh)
+    r[1] = make_float4(co.z * S3R_KA, co.w, c.x, c.y);
     r[2] = make_float4(c.z, __uint_as_float(dbits), ex, ey);
   }
 }

@@ -6,7 +6,18 @@
 #include "../../include/styl3r_b200.h"
 
 #define S3R_CHUNK 256          // Gaussians per preprocess / emit CTA (= one bit-mask row of 8 words)
-#define S3R_REC_FLOATS 12      // blend record: x y A B | C o r g | b depth ex ey
+#define S3R_REC_FLOATS 12      // blend record: x y A' B' | C' o r g | b depth ex ey
+// The record carries the conic pre-scaled into the log2 domain, A' = -0.5*log2(e)*A, B' = -log2(e)*B,
+// C' = -0.5*log2(e)*C, so that the blend kernels evaluate  log2(G) = dx*(A'*dx + B'*dy) + C'*dy*dy  with two FMAs and
+// feed MUFU.EX2 directly (5 FP32 ops instead of 10).  Decisions that must equal the oracle's unfused fp32 arithmetic
+// (power > 0, alpha >= 1/255) are re-taken from the exact per-Gaussian conic (conic_opacity[]) whenever the fast value
+// lands inside a guard band around a threshold.
+#define S3R_KA (-0.72134752044448170368f)   // -0.5 * log2(e)
+#define S3R_KB (-1.44269504088896340736f)   // -log2(e)
+#define S3R_INV_KA (-1.38629436111989061883f)  // A = A' * (-2 ln 2)
+#define S3R_INV_KB (-0.69314718055994530942f)  // B = B' * (-ln 2)
+#define S3R_ALPHA_BAND 1e-4f   // relative half-width of the guard band around alpha = 1/255
+#define S3R_PZERO_BAND 1e-5f   // |log2 G| below this: the sign of the exponent is decided exactly
 #define S3R_REC_BYTES 48
 #ifndef S3R_SORT_SMEM_CAP
 #define S3R_SORT_SMEM_CAP 4096 // per-tile instances sorted entirely in shared memory
@@ -23,6 +34,7 @@ struct S3rViewConst {  // per-view constants staged in shared memory by the per-
   float pm[16];
   float campos[3];
   float tanx, tany, scale, scale2;
+  float fx, fy, limx, limy;  // focal lengths in pixels and frustum clamp limits (computeCov2D)
   int set;
 };
 

@@ -170,10 +170,16 @@ class PatchEmbed(nn.Module):
         ph, pw = self.patch_size
         assert H % ph == 0, f"Input image height ({H}) is not a multiple of patch size ({ph})."
         assert W % pw == 0, f"Input image width ({W}) is not a multiple of patch size ({pw})."
-        x = self.proj(img)
-        gh, gw = x.shape[2], x.shape[3]
+        gh, gw = H // ph, W // pw
         ys, xs = torch.meshgrid(torch.arange(gh, device=img.device), torch.arange(gw, device=img.device), indexing="ij")
         pos = torch.stack((ys.reshape(-1), xs.reshape(-1)), dim=-1)[None].expand(B, -1, -1).contiguous()
+        w = self.proj.weight
+        if img.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and not torch.is_grad_enabled():
+            # kernel == stride: the convolution is a GEMM over non-overlapping patches, columns ordered (c, kh, kw)
+            # like weight.flatten(1) - one gather copy + the tcgen05 GEMM instead of a cuDNN conv with layout transposes
+            cols = img.reshape(B, -1, gh, ph, gw, pw).permute(0, 2, 4, 1, 3, 5).reshape(B * gh * gw, -1)
+            return _gemm.linear(cols, w.flatten(1), self.proj.bias).view(B, gh * gw, -1), pos
+        x = self.proj(img)
         return x.flatten(2).transpose(1, 2), pos
 
 
