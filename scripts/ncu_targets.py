@@ -1,0 +1,49 @@
+"""Launches each hot kernel a few times so that one `ncu --set full` pass captures them (development aid):
+raster forward chain on the bench scene (cfg2), the implicit-GEMM convolution at the gs-head shape, GEMMs at the
+cfg2 / cfg3 qkv shapes, attention at 257 tokens."""
+import sys
+from pathlib import Path
+sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+import torch
+import bench
+from styl3r_b200 import rasterizer as rz
+from styl3r_b200.decoder import cuda_splatting as cs
+from styl3r_b200.conv import conv2d_nhwc, prep_conv_weight
+from styl3r_b200.gemm import linear
+from styl3r_b200.ops import memory_efficient_attention
+
+dev = torch.device("cuda", 0)
+sc = bench.make_scene(1234)
+t = lambda a: torch.as_tensor(a, device=dev)
+g = dict(means=t(sc["means"])[None], cov=t(sc["covariances"])[None], sh=t(sc["harmonics"])[None], opac=t(sc["opacities"])[None],
+         extr=t(sc["extrinsics"]), intr=t(sc["intrinsics"]), near=t(sc["near"]), far=t(sc["far"]))
+scale = 1 / g["near"]
+extr = g["extr"].clone(); extr[:, :3, 3] = extr[:, :3, 3] * scale[:, None]
+fov = cs.get_fov(g["intr"])
+proj_t = cs.get_projection_matrix(g["near"] * scale, g["far"] * scale, fov[:, 0], fov[:, 1]).transpose(1, 2).contiguous()
+view_t = extr.inverse().transpose(1, 2).contiguous()
+full = (view_t @ proj_t).contiguous()
+tensors = (g["means"], g["cov"], g["opac"], g["sh"].reshape(1, -1, 1, 3), None, view_t, full, proj_t, extr[:, :3, 3].contiguous(),
+           (0.5 * fov).tan().contiguous(), scale.contiguous(), torch.zeros(1, 3, device=dev), torch.zeros(1, dtype=torch.int32, device=dev))
+P = g["means"].shape[1]
+plan = rz.RasterPlan(tensors, 1, P, 1, 256, 256, 1, 0, 9, 3 * P)
+for _ in range(3):
+    plan.launch()
+torch.cuda.synchronize()
+x = torch.randn(1, 256, 256, 256, device=dev).to(torch.bfloat16)
+w = prep_conv_weight((torch.randn(256, 256, 3, 3, device=dev) / 48).to(torch.bfloat16))
+for _ in range(2):
+    conv2d_nhwc(x, w, (3, 3), relu=True)
+x64 = torch.randn(1, 64, 64, 256, device=dev).to(torch.bfloat16)
+for _ in range(2):
+    conv2d_nhwc(x64, w, (3, 3), relu=True)
+for M in (514, 4112):
+    a = torch.randn(M, 1024, device=dev).to(torch.bfloat16); wt = torch.randn(3072, 1024, device=dev).to(torch.bfloat16)
+    b = torch.randn(3072, device=dev).to(torch.bfloat16)
+    for _ in range(2):
+        linear(a, wt, b)
+q = torch.randn(2, 257, 3, 16, 64, device=dev).to(torch.bfloat16)
+for _ in range(2):
+    memory_efficient_attention(q[:, :, 0], q[:, :, 1], q[:, :, 2], scale=0.125)
+torch.cuda.synchronize()
+print("done")

@@ -307,6 +307,13 @@ class EncoderNoPoSplatMultiTokenStyle(nn.Module):
                          head_branch(self.gaussian_param_head if i == 0 else self.gaussian_param_head2, dec_feat, i, True),
                          head_branch(self.gaussian_appearance_head, sty_feat, i, False)]
         raw = fork_join(branches, dev, parallel=par)
+        if torch.is_grad_enabled() and any(t.requires_grad for t in raw):
+            # training: differentiable restatement of the adapter with torch ops (the fused kernel has no backward)
+            g = self._adapter_autograd(raw, b, v, h, w, global_step)
+            if visualization_dump is not None:
+                visualization_dump.update(depth=g[0][..., 2].reshape(b, v, h, w, 1, 1), scales=g[4], rotations=g[5],
+                                          means=g[0].reshape(b, v, h, w, 1, 3), opacities=g[3].reshape(b, v, h, w, 1, 1))
+            return Gaussians(g[0], g[1], g[2], g[3])
         st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
         expo = float(self.opacity_exponent(global_step))
         for i in range(v):
@@ -327,6 +334,33 @@ class EncoderNoPoSplatMultiTokenStyle(nn.Module):
             visualization_dump["means"] = means.reshape(b, v, h, w, 1, 3)
             visualization_dump["opacities"] = opac.reshape(b, v, h, w, 1, 1)
         return Gaussians(means, cov, harm, opac)
+
+    def _adapter_autograd(self, raw, b: int, v: int, h: int, w: int, global_step: int):
+        """Head outputs -> Gaussians with autograd (same arithmetic as csrc/adapter.cu; reference:
+        encoder_noposplat_multi_token_style.py:178-251, postprocess.py:45-61, gaussian_adapter.py:122-153,
+        gaussians.py:8-44).  raw = per view (pts [b,3,h,w], params [b,8,h,w], app [b,3*d_sh,h,w])."""
+        d_sh, expo = self.gaussian_adapter.d_sh, float(self.opacity_exponent(global_step))
+        flat = lambda t: t.flatten(2).transpose(1, 2)                               # [b, HW, C]
+        pts = torch.stack([flat(raw[3 * i]) for i in range(v)], dim=1).flatten(1, 2)        # [b, G, 3]
+        prm = torch.stack([flat(raw[3 * i + 1]) for i in range(v)], dim=1).flatten(1, 2)    # [b, G, 8]
+        app = torch.stack([flat(raw[3 * i + 2]) for i in range(v)], dim=1).flatten(1, 2)    # [b, G, 3*d_sh]
+        d = pts.norm(dim=-1, keepdim=True)
+        means = pts * (torch.expm1(d) / d.clamp(min=1e-8))
+        pdf = torch.sigmoid(prm[..., 0])
+        opac = pdf if expo == 1.0 else 0.5 * (1 - (1 - pdf) ** expo + pdf ** (1 / expo))
+        scales = (0.001 * torch.nn.functional.softplus(prm[..., 1:4])).clamp(max=0.3)
+        q = prm[..., 4:8]
+        q = q / (q.norm(dim=-1, keepdim=True) + 1e-8)
+        qi, qj, qk, qr = q.unbind(-1)                                               # xyzw
+        two_s = 2.0 / ((q * q).sum(-1) + 1e-8)
+        R = torch.stack((1 - two_s * (qj * qj + qk * qk), two_s * (qi * qj - qk * qr), two_s * (qi * qk + qj * qr),
+                         two_s * (qi * qj + qk * qr), 1 - two_s * (qi * qi + qk * qk), two_s * (qj * qk - qi * qr),
+                         two_s * (qi * qk - qj * qr), two_s * (qj * qk + qi * qr), 1 - two_s * (qi * qi + qj * qj)),
+                        dim=-1).reshape(*q.shape[:-1], 3, 3)
+        M = R * scales[..., None, :]
+        cov = M @ M.transpose(-1, -2)
+        harm = app.reshape(*app.shape[:-1], 3, d_sh) * self.gaussian_adapter.sh_mask
+        return means, cov, harm, opac, scales, q
 
     def get_data_shim(self):
         mean, std = self.cfg.input_mean, self.cfg.input_std

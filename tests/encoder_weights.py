@@ -36,3 +36,15 @@ def make_inputs(b: int, v: int, hw: int, seed: int, device="cpu"):
     sty = torch.rand(b, 3, hw, hw, generator=g) * 2 - 1
     K = torch.tensor([[0.8, 0.0, 0.5], [0.0, 0.8, 0.5], [0.0, 0.0, 1.0]]).expand(b, v, 3, 3).contiguous()
     return {"image": img.to(device), "intrinsics": K.to(device)}, {"image": sty.to(device)}
+
+
+def fill_vgg_named(named_tensors) -> None:
+    """VGG-19 slices (src/test/vgg_model.py VGGEncoder): He-scaled kernels / small biases as a function of the name
+    (`slice2.5.weight`, ...).  Accepts named_parameters() or named_buffers() (the reference's losses convert the VGG
+    parameters to buffers)."""
+    with torch.no_grad():
+        for name, t in named_tensors:
+            if t.dim() == 4:
+                t.copy_(named_tensor("vgg." + name, t.shape, (2.0 / t[0].numel()) ** 0.5).to(t.device))
+            else:
+                t.copy_(named_tensor("vgg." + name, t.shape, 0.02).to(t.device))
