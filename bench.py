@@ -140,6 +140,7 @@ def run_reference(args):
     if rank != 0:
         return
     from oracle import raster_oracle as ro
+    ro.set_num_threads(len(os.sched_getaffinity(0)))  # every host core of the box, also under torchrun (OMP_NUM_THREADS=1)
     scenes = [make_scene(1234 + i) for i in range(2)]
     for i in range(args.warmup):
         oracle_step(scenes[i % 2])

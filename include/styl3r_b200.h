@@ -240,7 +240,7 @@ int s3r_conv2d_bf16(const void* x, const void* w, const void* bias, const void* 
 #define S3R_TUNE_CONV_VARIANT 1
 /* S3R_TUNE_GEMM_CLUSTER: thread-block cluster shape of s3r_gemm_bf16 (TMA multicast of the shared operand tile):
  * 0 = built-in default, else CM*10 + CN with CM in {1,2} (adjacent M tiles share the W tile), CN in {1,2,4}.
- * S3R_TUNE_GEMM_BIG_TILE: != 0 lets large grids use 128x256 output tiles. */
+ * S3R_TUNE_GEMM_BIG_TILE: 128x256 output tiles - 0 = auto (N >= 4096 and >= 3 waves), 1 = whenever >= 120 tiles, 2 = never. */
 #define S3R_TUNE_GEMM_CLUSTER 2
 #define S3R_TUNE_GEMM_BIG_TILE 3
 #define S3R_TUNE_CONV_CLUSTER 4 /* != 0: s3r_conv2d_bf16 runs clusters of 2 pixel tiles that multicast the weight tile */

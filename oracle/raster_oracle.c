@@ -587,6 +587,15 @@ void s3r_oracle_preprocess_backward(int P, int deg, int M, const float* means, c
   }
 }
 
+void s3r_oracle_set_num_threads(int n) {
+#ifdef _OPENMP
+  extern void omp_set_num_threads(int);
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 int s3r_oracle_num_threads(void) {
 #ifdef _OPENMP
   extern int omp_get_max_threads(void);

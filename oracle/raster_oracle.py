@@ -62,6 +62,11 @@ def num_threads() -> int:
     return int(lib().s3r_oracle_num_threads())
 
 
+def set_num_threads(n: int) -> None:
+    """OpenMP team size of the oracle (torchrun exports OMP_NUM_THREADS=1; the reference arm wants every host core)."""
+    lib().s3r_oracle_set_num_threads(int(n))
+
+
 def _p(a, t):
     return a.ctypes.data_as(t) if a is not None else None
 

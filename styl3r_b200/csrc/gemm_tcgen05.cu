@@ -471,7 +471,7 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 static int g_gemm_cluster = 0;   // S3R_TUNE_GEMM_CLUSTER: 0 = default, else CM*10 + CN
-static int g_gemm_big_tile = 0;  // S3R_TUNE_GEMM_BIG_TILE: 128x256 tiles for grids of >= 120 such tiles
+static int g_gemm_big_tile = 0;  // S3R_TUNE_GEMM_BIG_TILE: 0 = auto (wide many-wave grids), 1 = whenever >= 120 tiles, 2 = never
 static int g_conv_cluster = 0;   // S3R_TUNE_CONV_CLUSTER: pairs of pixel tiles multicast the weight tile
 
 static PFN_encodeTiled get_encode() {
@@ -588,7 +588,11 @@ extern "C" int s3r_gemm_bf16_rope(const void* A, const void* W, const void* bias
   const long mt = (M + 127) / 128;
   const long tiles128 = mt * ((N + 127) / 128), tiles64 = mt * ((N + 63) / 64);
   int BN = tiles128 >= 120 ? 128 : 64;  // (BN=32 measured slower: every N-tile re-reads the A tile from L2)
-  if (BN == 128 && g_gemm_big_tile && N % 256 == 0 && mt * (N / 256) >= 120) BN = 256;
+  // 128x256 tiles halve the A re-reads; measured faster only for wide, many-wave grids (4112x4096x1024: 44.2 vs 50.7 us;
+  // 4112x3072: 41.3 vs 38.8 us; 8192^3: 825 vs 979 us) - S3R_TUNE_GEMM_BIG_TILE: 0 auto, 1 always, 2 never
+  if (BN == 128 && N % 256 == 0 && g_gemm_big_tile != 2 &&
+      ((g_gemm_big_tile == 1 && mt * (N / 256) >= 120) || (N >= 4096 && mt * (N / 256) >= 444)))
+    BN = 256;
   int cm = 1, cn = 1;  // cluster shape (multicast): tunable, else the measured default per tile class
   if (g_gemm_cluster > 0) cm = g_gemm_cluster / 10, cn = g_gemm_cluster % 10;
   if ((N + BN - 1) / BN < cn) cn = 1;
@@ -667,7 +671,8 @@ extern "C" int s3r_set_tunable(int32_t key, int32_t value) {
     return S3R_OK;
   }
   if (key == S3R_TUNE_GEMM_BIG_TILE) {
-    g_gemm_big_tile = value != 0;
+    if (value < 0 || value > 2) return S3R_ERR_INVALID_ARG;
+    g_gemm_big_tile = value;
     return S3R_OK;
   }
   if (key == S3R_TUNE_CONV_VARIANT) {

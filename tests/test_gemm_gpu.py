@@ -94,3 +94,48 @@ def test_gemm_split_k_path_is_deterministic_and_correct(M, N, K):
     assert torch.equal(y1, y2)
     assert (y1.float() - expect).abs().max() <= 1e-2 * expect.abs().max()
     assert (y0.float() - expect).abs().max() <= 1e-2 * expect.abs().max()
+
+
+@pytest.mark.parametrize("code", [12, 14, 21, 22, 24])
+@pytest.mark.parametrize("M,N,K,big", [(514, 3072, 1024, 0), (257, 768, 768, 0), (4112, 1024, 1024, 0), (4112, 3072, 1024, 1)])
+def test_gemm_cluster_multicast_variants_match_reference(code, M, N, K, big):
+    """Thread-block clusters (CM x CN) with TMA multicast of the shared operand tile and cluster-wide slot release
+    (S3R_TUNE_GEMM_CLUSTER = CM*10 + CN; off by default - measured not to pay off on B200): same
+    result as the plain kernel, including ragged M (padded cluster rows) and the 128x256 tile."""
+    import torch
+    from styl3r_b200 import _lib
+    from styl3r_b200.gemm import linear
+    L = _lib.lib()
+    g = torch.Generator(device="cuda").manual_seed(M + N + K + code)
+    x = torch.randn(M, K, device="cuda", generator=g).to(torch.bfloat16)
+    w = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5).to(torch.bfloat16)
+    b = torch.randn(N, device="cuda", generator=g).to(torch.bfloat16)
+    base = linear(x, w, b, gelu=True)
+    try:
+        _lib.check(L.s3r_set_tunable(2, code))
+        _lib.check(L.s3r_set_tunable(3, big))
+        y = linear(x, w, b, gelu=True)
+        torch.cuda.synchronize()
+    finally:
+        L.s3r_set_tunable(2, 0)
+        L.s3r_set_tunable(3, 0)
+    assert torch.equal(y, base) or (y.float() - base.float()).abs().max().item() <= 2 ** -6
+
+
+def test_conv_cluster_multicast_matches_plain():
+    import torch
+    from styl3r_b200 import _lib
+    from styl3r_b200.conv import conv2d_nhwc, prep_conv_weight
+    L = _lib.lib()
+    g = torch.Generator(device="cuda").manual_seed(3)
+    for (n, h, w, ci, co) in [(1, 128, 128, 256, 256), (3, 8, 8, 128, 128), (1, 256, 256, 64, 256)]:
+        x = torch.randn(n, h, w, ci, device="cuda", generator=g).to(torch.bfloat16)
+        wp = prep_conv_weight((torch.randn(co, ci, 3, 3, device="cuda", generator=g) / (9 * ci) ** 0.5).to(torch.bfloat16))
+        base = conv2d_nhwc(x, wp, (3, 3), relu=True)
+        try:
+            _lib.check(L.s3r_set_tunable(4, 1))
+            y = conv2d_nhwc(x, wp, (3, 3), relu=True)
+            torch.cuda.synchronize()
+        finally:
+            L.s3r_set_tunable(4, 0)
+        assert torch.equal(y, base)
