@@ -199,6 +199,7 @@ int s3r_rope2d(void* tokens, const int64_t* pos, int32_t B, int32_t N, int32_t H
 #define S3R_EPI_OUT_F32 8
 #define S3R_EPI_ROPE 16
 #define S3R_EPI_RELU 32
+#define S3R_EPI_PDL 64 /* internal: set by the launcher when programmatic dependent launch is enabled (S3R_TUNE_PDL) */
 int s3r_gemm_bf16(const void* A, const void* W, const void* bias, const void* residual, void* C, int32_t M,
                   int32_t N, int32_t K, int32_t lda, int32_t ldw, int32_t ldc, int32_t ldr, int32_t flags,
                   void* stream);
@@ -243,6 +244,7 @@ int s3r_conv2d_bf16(const void* x, const void* w, const void* bias, const void* 
  * S3R_TUNE_GEMM_BIG_TILE: 128x256 output tiles - 0 = auto (N >= 4096 and >= 3 waves), 1 = whenever >= 120 tiles, 2 = never. */
 #define S3R_TUNE_GEMM_CLUSTER 2
 #define S3R_TUNE_GEMM_BIG_TILE 3
+#define S3R_TUNE_PDL 5 /* != 0: GEMM / conv / attention launches use programmatic dependent launch (prologue overlaps the previous kernel's tail; griddepcontrol.wait before the first global access) */
 #define S3R_TUNE_CONV_CLUSTER 4 /* != 0: s3r_conv2d_bf16 runs clusters of 2 pixel tiles that multicast the weight tile */
 int s3r_set_tunable(int32_t key, int32_t value);
 
@@ -250,6 +252,15 @@ int s3r_set_tunable(int32_t key, int32_t value);
  * dpt_gs_head.py:138), NHWC bf16: y[n,2h,2w,c] = up(x)[...] (+ add[n,2h,2w,c] when add != NULL). c % 8 == 0. */
 int s3r_upsample2x_nhwc_bf16(const void* x, const void* add, void* y, int32_t n, int32_t h, int32_t w, int32_t c,
                              void* stream);
+
+/* ------------------------------------------------------------------------
+ * LayerNorm over the last dimension, bf16 in / out, fp32 statistics - the
+ * nn.LayerNorm(dim, eps=1e-6) of the ViT blocks (croco/blocks.py:140-147,
+ * 206-217; croco.py:34).  x [M, C] with row pitch ldx (elements), y [M, C]
+ * contiguous; C % 256 == 0, C <= 2048.
+ * ------------------------------------------------------------------------ */
+int s3r_layernorm_bf16(const void* x, const void* weight, const void* bias, void* y, int32_t M, int32_t C, int64_t ldx,
+                       float eps, void* stream);
 
 /* ------------------------------------------------------------------------
  * Attention softmax(q k^T * scale) v on tcgen05/TMEM, head_dim 64, bf16 —

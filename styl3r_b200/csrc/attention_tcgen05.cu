@@ -126,7 +126,7 @@ struct AttSmem {  // offsets from a 1024-B aligned base
 __global__ void __launch_bounds__(ATT_THREADS, 2)
 s3r_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, __nv_bfloat16* __restrict__ O, int H, int Nq, int Nk,
-                     long long so_b, long long so_n, long long so_h, float scale_log2e) {
+                     long long so_b, long long so_n, long long so_h, float scale_log2e, int pdl) {
   extern __shared__ uint8_t att_smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)att_smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = (uint64_t*)(smem + AttSmem::BARS);
@@ -177,6 +177,10 @@ s3r_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 128;  // S0 [0,64), S1 [64,128), O [128,192)
+  if (pdl) {  // programmatic dependent launch: the prologue above overlapped the previous kernel's tail (see gemm_tcgen05.cu)
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+  }
 
   if (warp == 0) {
     if (lane == 0) {
@@ -382,9 +386,21 @@ extern "C" int s3r_attention_bf16(const void* q, const void* k, const void* v, v
     S3R_CUDA_CHECK(cudaFuncSetAttribute(s3r_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AttSmem::TOTAL));
     configured = true;
   }
-  dim3 grid((Nq + ATT_BM - 1) / ATT_BM, H, B);
-  s3r_attention_kernel<<<grid, ATT_THREADS, AttSmem::TOTAL, (cudaStream_t)stream>>>(
-      tq, tk, tv, (__nv_bfloat16*)o, H, Nq, Nk, o_strides[0], o_strides[1], o_strides[2], scale * 1.4426950408889634f);
-  S3R_CUDA_CHECK(cudaGetLastError());
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((Nq + ATT_BM - 1) / ATT_BM, H, B);
+  cfg.blockDim = dim3(ATT_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = AttSmem::TOTAL;
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[1];
+  const int pdl = s3r_pdl_enabled();
+  if (pdl) {
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+  }
+  S3R_CUDA_CHECK(cudaLaunchKernelEx(&cfg, s3r_attention_kernel, tq, tk, tv, (__nv_bfloat16*)o, (int)H, (int)Nq, (int)Nk,
+                                    (long long)o_strides[0], (long long)o_strides[1], (long long)o_strides[2],
+                                    scale * 1.4426950408889634f, pdl));
   return S3R_OK;
 }

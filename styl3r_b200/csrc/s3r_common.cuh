@@ -48,3 +48,6 @@ int s3r_launch_bin(const s3r_raster_params& p, const s3r_raster_layout& L, char*
 int s3r_launch_sort(const s3r_raster_params& p, const s3r_raster_layout& L, char* state, cudaStream_t st);
 int s3r_launch_blend(const s3r_raster_params& p, const s3r_raster_outputs& o, const s3r_raster_layout& L,
                      char* state, cudaStream_t st);
+
+// Programmatic dependent launch switch shared by the encoder kernels (S3R_TUNE_PDL; defined in gemm_tcgen05.cu)
+int s3r_pdl_enabled();

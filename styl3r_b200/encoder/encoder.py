@@ -25,7 +25,7 @@ from torch import Tensor, nn
 from .. import _lib
 from ..streams import fork_join
 from .dpt import PixelwiseDPT
-from .vit import CroCoTrunk, _lin
+from .vit import CroCoTrunk, _lin, _ln
 
 
 @dataclass
@@ -151,7 +151,7 @@ class AsymmetricCroCoMulti(CroCoTrunk):
                 parts.append(res[1].reshape(b, v - 1, *res[1].shape[1:]))
             cur = torch.cat(parts, dim=1)
             outs.append(cur)
-        outs[-1] = self.dec_norm(outs[-1])
+        outs[-1] = _ln(self.dec_norm, outs[-1])
         return [o[:, :, :-1] for o in outs]  # drop the intrinsics token
 
     def forward(self, context: dict):
@@ -185,7 +185,7 @@ class TokenStylizer(CroCoTrunk):
         for blk in self.dec_blocks:
             x = blk(x, y, xpos, spos, parallel=parallel)
             outs.append(x.reshape(b, v, l, -1))
-        outs[-1] = self.dec_norm(x).reshape(b, v, l, -1)
+        outs[-1] = _ln(self.dec_norm, x).reshape(b, v, l, -1)
         return [o[:, :, :-1] for o in outs]
 
 

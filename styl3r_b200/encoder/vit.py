@@ -43,6 +43,27 @@ def _lin(layer: nn.Linear, x: Tensor, residual: Tensor | None = None, gelu: bool
     return y if residual is None else residual + y
 
 
+def _ln(norm: nn.LayerNorm, x: Tensor) -> Tensor:
+    """LayerNorm: bf16 inference layout -> `s3r_layernorm_bf16` (one warp per row, fp32 statistics, launched with
+    programmatic dependent launch); otherwise the torch module."""
+    C_ = x.shape[-1]
+    if (x.dtype == torch.bfloat16 and norm.weight.dtype == torch.bfloat16 and not torch.is_grad_enabled() and x.is_cuda
+            and C_ % 256 == 0 and C_ <= 2048):
+        import ctypes as C
+        from .. import _lib
+        x2 = x.reshape(-1, C_)
+        if x2.stride(1) != 1 or x2.stride(0) % 8:
+            x2 = x2.contiguous()
+        y = torch.empty((x2.shape[0], C_), dtype=torch.bfloat16, device=x.device)
+        _lib.check(_lib.lib().s3r_layernorm_bf16(C.c_void_p(x2.data_ptr()), C.c_void_p(norm.weight.data_ptr()),
+                                                 C.c_void_p(norm.bias.data_ptr()), C.c_void_p(y.data_ptr()), x2.shape[0], C_,
+                                                 x2.stride(0), float(norm.eps),
+                                                 C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)),
+                   "s3r_layernorm_bf16")
+        return y.view(*x.shape)
+    return norm(x)
+
+
 class Mlp(nn.Module):
     def __init__(self, dim: int, hidden: int):
         super().__init__()
@@ -126,8 +147,8 @@ class Block(nn.Module):
         self.mlp = Mlp(dim, int(dim * mlp_ratio))
 
     def forward(self, x: Tensor, xpos: Tensor) -> Tensor:
-        x = self.attn(self.norm1(x), xpos, residual=x)
-        return self.mlp(self.norm2(x), residual=x)
+        x = self.attn(_ln(self.norm1, x), xpos, residual=x)
+        return self.mlp(_ln(self.norm2, x), residual=x)
 
 
 class DecoderBlock(nn.Module):
@@ -145,16 +166,16 @@ class DecoderBlock(nn.Module):
         """`parallel`: the context branch (norm_y -> projk/projv) runs concurrently with the self-attention branch
         (streams.fork_join); same kernels and operands either way, so the result is identical."""
         def self_branch():
-            x1 = self.attn(self.norm1(x), xpos, residual=x)
-            return x1, self.cross_attn.project_q(self.norm2(x1), xpos)
+            x1 = self.attn(_ln(self.norm1, x), xpos, residual=x)
+            return x1, self.cross_attn.project_q(_ln(self.norm2, x1), xpos)
 
         def ctx_branch():
-            y_ = self.norm_y(y)
+            y_ = _ln(self.norm_y, y)
             return self.cross_attn.project_kv(y_, y_, ypos)
 
         (x1, q), (k, v) = fork_join([self_branch, ctx_branch], x.device, parallel=parallel)
         x2 = self.cross_attn.attend(q, k, v, residual=x1)
-        return self.mlp(self.norm3(x2), residual=x2)
+        return self.mlp(_ln(self.norm3, x2), residual=x2)
 
 
 class PatchEmbed(nn.Module):
@@ -229,4 +250,4 @@ class CroCoTrunk(nn.Module):
             pos = torch.cat((pos, tok_pos), dim=1)
         for blk in self.enc_blocks:
             x = blk(x, pos)
-        return self.enc_norm(x), pos
+        return _ln(self.enc_norm, x), pos

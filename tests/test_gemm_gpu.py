@@ -139,3 +139,26 @@ def test_conv_cluster_multicast_matches_plain():
         finally:
             L.s3r_set_tunable(4, 0)
         assert torch.equal(y, base)
+
+
+@pytest.mark.parametrize("M,C,strided", [(514, 1024, False), (257, 768, False), (1, 256, False), (1028, 768, True), (33, 2048, False)])
+def test_layernorm_matches_fp32_reference(M, C, strided):
+    """s3r_layernorm_bf16 (one warp per row, fp32 statistics) vs torch fp32 LayerNorm on the same bf16 values:
+    |err| <= one bf16 rounding of the output (2^-8 relative)."""
+    import torch
+    from styl3r_b200.encoder.vit import _ln
+    g = torch.Generator(device="cuda").manual_seed(M + C)
+    norm = torch.nn.LayerNorm(C, eps=1e-6).cuda()
+    with torch.no_grad():
+        norm.weight.copy_(1 + 0.1 * torch.randn(C, device="cuda", generator=g))
+        norm.bias.copy_(0.1 * torch.randn(C, device="cuda", generator=g))
+    norm = norm.to(torch.bfloat16)
+    x = (torch.randn(M, 2 * C if strided else C, device="cuda", generator=g) * 3 + 0.5).to(torch.bfloat16)
+    if strided:
+        x = x[:, :C]          # row pitch 2*C: the kernel takes the pitch, no copy
+    with torch.no_grad():
+        y = _ln(norm, x)
+        ref = torch.nn.functional.layer_norm(x.float(), (C,), norm.weight.float(), norm.bias.float(), 1e-6)
+    torch.cuda.synchronize()
+    assert y.dtype == torch.bfloat16 and y.shape == x.shape
+    assert (y.float() - ref).abs().max().item() <= 2.0 ** -8 * max(1.0, ref.abs().max().item())
