@@ -1,0 +1,83 @@
+"""End-to-end stylised inference on one GPU - the body of `infer` in infer_model_re10k.py:404-560 composed from the
+B200 pieces (every step a device-side kernel path, no host round trip in between):
+
+    raw frames [v,3,H0,W0] in [0,1], K, c2w, style image
+      -> staging.rescale_and_crop (+ normalise)  /  staging.apply_style_image_augmentation        rows f2
+      -> encoder(context, style = first context image)  -> Gaussians (+ scales / rotations dump)   rows a1-a10
+      -> encoder(context, style image)                   -> stylised Gaussians
+      -> pose_align (optional; target poses refined against the non-stylised render)               row f1 / a15
+      -> decoder.forward for both Gaussian sets (all target views in one launch chain)              rows a11-a14
+      -> video.render_video_interpolation, ply_export.export_ply                                    rows f3
+
+Reference quirks kept on purpose: the style image goes to the encoder in [0,1] at inference
+(D-3), the identity pass uses the first *normalised* context image as its style, `depth_mode` is ignored (D-1)."""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from pathlib import Path
+from typing import Optional
+
+import torch
+from torch import Tensor
+
+from .decoder import DecoderSplattingCUDA
+from .encoder import GraphedEncoder
+from .ply_export import export_ply
+from .pose_align import pose_align
+from .staging import apply_style_image_augmentation, rescale_and_crop
+from .video import render_video_interpolation
+
+
+@dataclass
+class InferOutput:
+    color: Tensor                  # [1, V, 3, h, w] non-stylised target renders
+    stylized_color: Tensor         # [1, V, 3, h, w]
+    extrinsics: Tensor             # [1, V, 4, 4] target poses actually rendered (refined when pose_align_steps > 0)
+    video: Optional[Tensor]        # uint8 [T', 3, h, w] stylised interpolation video
+    gaussians: object
+    stylized_gaussians: object
+
+
+@torch.no_grad()
+def infer(encoder, decoder: DecoderSplattingCUDA, context_images: Tensor, context_intrinsics: Tensor,
+          context_extrinsics: Tensor, target_images: Tensor, target_intrinsics: Tensor, target_extrinsics: Tensor,
+          style_image: Tensor, image_shape=(256, 256), near: float = 0.1, far: float = 100.0, pose_align_steps: int = 0,
+          num_video_frames: int = 60, output_dir: Optional[Path] = None) -> InferOutput:
+    """context/target_images: raw [v,3,H0,W0] in [0,1]; *_intrinsics normalised [v,3,3]; *_extrinsics c2w [v,4,4]
+    (already in the relative-pose frame of the first context camera); style_image [3,Hs,Ws] in [0,1]."""
+    dev = context_images.device
+    ctx_img, ctx_K = rescale_and_crop(context_images, context_intrinsics, image_shape, normalize=True)   # -> [-1,1]
+    tgt_img, tgt_K = rescale_and_crop(target_images, target_intrinsics, image_shape)
+    sty = apply_style_image_augmentation(style_image, "val")
+    v, V = ctx_img.shape[0], tgt_img.shape[0]
+    bound = lambda val, n: torch.full((1, n), float(val), device=dev)
+    batch = {"context": {"image": ctx_img[None], "intrinsics": ctx_K[None], "extrinsics": context_extrinsics[None],
+                         "near": bound(near, v), "far": bound(far, v)},
+             "target": {"image": tgt_img[None], "intrinsics": tgt_K[None], "extrinsics": target_extrinsics[None],
+                        "near": bound(near, V), "far": bound(far, V)},
+             "style": {"image": sty[None]}}
+    fast = encoder if isinstance(encoder, GraphedEncoder) else None
+    enc = encoder.encoder if fast is not None else encoder
+    dump: dict = {}
+    gaussians = enc(batch["context"], {"image": batch["context"]["image"][:, 0]}, visualization_dump=dump)
+    if fast is not None:
+        s = fast(batch["context"], batch["style"])
+        from .encoder.encoder import Gaussians
+        stylized = Gaussians(s.means.clone(), s.covariances.clone(), s.harmonics.clone(), s.opacities.clone())
+    else:
+        stylized = enc(batch["context"], batch["style"])
+    tgt = batch["target"]
+    extr = tgt["extrinsics"]
+    if pose_align_steps > 0:  # test_step_align: poses refined against the non-stylised Gaussians
+        extr, _ = pose_align(gaussians, extr, tgt["intrinsics"], tgt["near"], tgt["far"], image_shape, tgt["image"],
+                             steps=pose_align_steps)
+    out = decoder.forward(gaussians, extr, tgt["intrinsics"], tgt["near"], tgt["far"], image_shape)
+    sout = decoder.forward(stylized, extr, tgt["intrinsics"], tgt["near"], tgt["far"], image_shape)
+    video = render_video_interpolation(stylized, decoder, batch, num_frames=num_video_frames) if num_video_frames else None
+    if output_dir is not None:
+        output_dir = Path(output_dir)
+        export_ply(stylized.means[0], dump["scales"][0], dump["rotations"][0], stylized.harmonics[0], stylized.opacities[0],
+                   output_dir / "stylized_gaussians.ply")
+        export_ply(gaussians.means[0], dump["scales"][0], dump["rotations"][0], gaussians.harmonics[0], gaussians.opacities[0],
+                   output_dir / "gaussians.ply")
+    return InferOutput(out.color, sout.color, extr, video, gaussians, stylized)
