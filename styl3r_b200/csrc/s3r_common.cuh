@@ -20,7 +20,10 @@
 #define S3R_PZERO_BAND 1e-5f   // |log2 G| below this: the sign of the exponent is decided exactly
 #define S3R_REC_BYTES 48
 #ifndef S3R_SORT_SMEM_CAP
-#define S3R_SORT_SMEM_CAP 4096 // per-tile instances sorted entirely in shared memory
+// per-tile instances sorted entirely in shared memory (2 x 8 B each).  3584 -> 56 KB + 8 KB of histograms per CTA: three
+// CTAs per SM like 4096, but they leave ~30 KB of the SM's 228 KB to L1, which the epilogue's random gathers of
+// (xy, conic, rgb) need: tile sort 30.1 -> 27.9 us per launch, 19.8k -> 21.2k views/s (scripts/sweep_sortcap.sh, A/B/A/B)
+#define S3R_SORT_SMEM_CAP 3584
 #endif
 
 #define S3R_CUDA_CHECK(x)                    \

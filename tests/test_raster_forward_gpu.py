@@ -100,7 +100,7 @@ def test_all_culled_and_empty_tiles():
 
 
 def test_oversized_tiles_use_global_sort_path():
-    # > S3R_SORT_SMEM_CAP (4096) instances in single tiles: big splats stacked in front of the camera
+    # > S3R_SORT_SMEM_CAP (3584) instances in single tiles: big splats stacked in front of the camera
     sc = syn.make_small_scene(seed=6, P=6000, W=48, H=32, V=1, big_frac=0.0, behind_frac=0.0)
     sc["means"][:, 0] *= 0.1
     sc["means"][:, 1] *= 0.1
