@@ -419,7 +419,15 @@ def run_ours(args):
             e1.record()
             torch.cuda.synchronize()
             enc_ms = e0.elapsed_time(e1) / 10
-            enc_info = {"ms_per_scene": enc_ms, "tflops": 1270.8 / enc_ms, "config": "b=1, v=2, 256x256 + style image; bf16 ViT "
+            cpu_enc = None
+            if not args.no_cpu:  # the reference's PyTorch-CPU encoder path, restated (oracle/encoder_oracle.py), same box
+                from oracle import encoder_oracle as eo
+                ncores = len(os.sched_getaffinity(0))
+                sec = eo.time_encoder(ncores, runs=2)
+                cpu_enc = {"value": 1.0 / sec, "unit": "scenes/s", "s_per_scene": sec, "cores": ncores, "kind": "port",
+                           "sample": "1 warm-up + 2 forwards of the same cfg1 workload (b=1, v=2, 256x256, random weights), "
+                                     "median; oracle/encoder_oracle.py pinned on reference goldens"}
+            enc_info = {"ms_per_scene": enc_ms, "tflops": 1270.8 / enc_ms, "cpu_baseline": cpu_enc, "config": "b=1, v=2, 256x256 + style image; bf16 ViT "
                         "trunks (tcgen05 GEMM + attention), bf16 NHWC DPT heads on the tcgen05 implicit-GEMM convolution, "
                         "independent branches on concurrent streams, CUDA-graph replay; random weights",
                         "reference_cpu_s_per_scene_survey_probe": 2.72}
