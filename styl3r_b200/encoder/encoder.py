@@ -9,9 +9,11 @@ with `context = {"image": [b,v,3,h,w] in [-1,1], "intrinsics": [b,v,3,3] normali
 `style = {"image": [b,3,h,w]}`.  The parameter registry equals the reference's (SURVEY.md Appendix C;
 tests/golden/encoder_state_manifest.json), so `load_state_dict(strict=True)` works with existing checkpoints.
 
-B200 path: RoPE-2D (in place on the packed qkv) and the fused head-epilogue -> Gaussians kernel are ours; GEMMs,
-convolutions and the attention contraction are library calls in round 1 (DESIGN.md §7 lists the tcgen05 kernels as
-the next rows).  CUDA only — there is no CPU fallback.
+B200 inference layout (`to_inference(torch.bfloat16)` + `GraphedEncoder`): every Linear (+ bias / GELU / residual /
+RoPE-2D) on the tcgen05 GEMM, attention on the tcgen05 attention kernel, DPT convolutions on the tcgen05 implicit-GEMM
+convolution (bf16 NHWC), LayerNorm / bilinear x2 / head-epilogue -> Gaussians as our own kernels, independent branches
+on concurrent streams, the whole forward replayed as one CUDA graph.  With autograd enabled (training)
+the same modules run the reference's torch ops in fp32.  CUDA only — there is no CPU fallback.
 """
 from __future__ import annotations
 
