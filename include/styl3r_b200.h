@@ -245,6 +245,7 @@ int s3r_conv2d_bf16(const void* x, const void* w, const void* bias, const void* 
 #define S3R_TUNE_GEMM_CLUSTER 2
 #define S3R_TUNE_GEMM_BIG_TILE 3
 #define S3R_TUNE_PDL 5 /* != 0: GEMM / conv / attention launches use programmatic dependent launch (prologue overlaps the previous kernel's tail; griddepcontrol.wait before the first global access) */
+#define S3R_TUNE_GEMM_SHALLOW 6 /* != 0: GEMM grids smaller than the machine use the 4-stage 96 KB ring (2 CTAs/SM) instead of the 8-stage 192 KB one, so that kernels of concurrent stream branches can share an SM */
 #define S3R_TUNE_CONV_CLUSTER 4 /* != 0: s3r_conv2d_bf16 runs clusters of 2 pixel tiles that multicast the weight tile */
 int s3r_set_tunable(int32_t key, int32_t value);
 

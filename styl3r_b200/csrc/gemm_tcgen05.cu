@@ -484,6 +484,7 @@ static int g_gemm_big_tile = 0;  // S3R_TUNE_GEMM_BIG_TILE: 0 = auto (wide many-
 // at 514x1024x1024, neutral for grids whose shared memory fills the SMs; results identical.  On by default.
 static int g_pdl = 1;
 int s3r_pdl_enabled() { return g_pdl; }
+static int g_gemm_shallow = 0;   // S3R_TUNE_GEMM_SHALLOW: small grids use the 4-stage (96 KB, 2 CTAs/SM) ring too
 static int g_conv_cluster = 0;   // S3R_TUNE_CONV_CLUSTER: pairs of pixel tiles multicast the weight tile
 
 static PFN_encodeTiled get_encode() {
@@ -654,7 +655,7 @@ extern "C" int s3r_gemm_bf16_rope(const void* A, const void* W, const void* bias
     S3R_GEMM_GO(BN_, ST_, 1, 1);                     \
   } while (0)
   if (BN == 64) {
-    if (tiles64 * splits < 148) S3R_GEMM_CLUSTERS(64, 8);
+    if (tiles64 * splits < 148 && !g_gemm_shallow) S3R_GEMM_CLUSTERS(64, 8);
     S3R_GEMM_CLUSTERS(64, 4);
   }
   splits = 1, ws = nullptr, counters = nullptr;
@@ -686,6 +687,10 @@ extern "C" int s3r_set_tunable(int32_t key, int32_t value) {
     const int cm = value / 10, cn = value % 10;
     if (value != 0 && !((cm == 1 || cm == 2) && (cn == 1 || cn == 2 || cn == 4))) return S3R_ERR_INVALID_ARG;
     g_gemm_cluster = value;
+    return S3R_OK;
+  }
+  if (key == S3R_TUNE_GEMM_SHALLOW) {
+    g_gemm_shallow = value != 0;
     return S3R_OK;
   }
   if (key == S3R_TUNE_PDL) {

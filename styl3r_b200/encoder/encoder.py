@@ -303,12 +303,46 @@ class EncoderNoPoSplatMultiTokenStyle(nn.Module):
                                 img[:, i, :3].float() if with_img else None).contiguous()
             return run
 
-        branches = []
-        for i in range(v):
-            branches += [head_branch(self.downstream_head1 if i == 0 else self.downstream_head2, dec_feat, i, False),
-                         head_branch(self.gaussian_param_head if i == 0 else self.gaussian_param_head2, dec_feat, i, True),
-                         head_branch(self.gaussian_appearance_head, sty_feat, i, False)]
-        raw = fork_join(branches, dev, parallel=par)
+        if nhwc:
+            # views >= 1 share `downstream_head2` / `gaussian_param_head2` and every view shares the appearance head
+            # (encoder...style.py:154-176 runs them view by view): batch those views (view-major) into one pyramid each -
+            # fewer, larger kernels; the graph's node count, not FLOPs, bounds the batch-1 forward
+            from .dpt import HOOKS
+
+            def batched(head, feats, views, with_img):
+                def run():
+                    with torch.autocast("cuda", enabled=False):
+                        toks = [None] * len(feats)
+                        for hk in HOOKS:
+                            t = feats[hk]
+                            toks[hk] = t[:, views[0]] if len(views) == 1 else torch.cat([t[:, i] for i in views], dim=0)
+                        im = None
+                        if with_img:
+                            im = img[:, views[0], :3] if len(views) == 1 else torch.cat([img[:, i, :3] for i in views], dim=0)
+                        return head.forward_nhwc(toks, shape, im)
+                return run
+
+            rest = list(range(1, v))
+            branches = [batched(self.gaussian_appearance_head, sty_feat, list(range(v)), False),
+                        batched(self.downstream_head1, dec_feat, [0], False),
+                        batched(self.gaussian_param_head, dec_feat, [0], True)]
+            if rest:
+                branches += [batched(self.downstream_head2, dec_feat, rest, False),
+                             batched(self.gaussian_param_head2, dec_feat, rest, True)]
+            res = fork_join(branches, dev, parallel=par)
+            rows = b * HW
+            raw = []
+            for i in range(v):
+                pts_i = res[1] if i == 0 else res[3][(i - 1) * rows:i * rows]
+                prm_i = res[2] if i == 0 else res[4][(i - 1) * rows:i * rows]
+                raw += [pts_i, prm_i, res[0][i * rows:(i + 1) * rows]]
+        else:
+            branches = []
+            for i in range(v):
+                branches += [head_branch(self.downstream_head1 if i == 0 else self.downstream_head2, dec_feat, i, False),
+                             head_branch(self.gaussian_param_head if i == 0 else self.gaussian_param_head2, dec_feat, i, True),
+                             head_branch(self.gaussian_appearance_head, sty_feat, i, False)]
+            raw = fork_join(branches, dev, parallel=par)
         if torch.is_grad_enabled() and any(t.requires_grad for t in raw):
             # training: differentiable restatement of the adapter with torch ops (the fused kernel has no backward)
             g = self._adapter_autograd(raw, b, v, h, w, global_step)

@@ -119,12 +119,30 @@ class CrossAttention(nn.Module):
         them concurrently with its self-attention."""
         B, Nk, C = key.shape
         H, D = self.num_heads, C // self.num_heads
+        if _fast(self.projk, key) and D == 64 and key is value:
+            # one GEMM for both projections (N = 2C, RoPE on the K half only): the batch-1 forward is bound by the number
+            # of kernel launches the graph has to dispatch, not by their FLOPs
+            w, b_ = self._kv_operands()
+            kv = _gemm.linear(key, w, b_, rope_pos=kpos, rope_cols=C, rope_base=self.rope_base).view(B, Nk, 2, H, D)
+            return kv[:, :, 0], kv[:, :, 1]
         if _fast(self.projk, key) and D == 64:
             k = _gemm.linear(key, self.projk.weight, self.projk.bias, rope_pos=kpos, rope_cols=C,
                              rope_base=self.rope_base).view(B, Nk, H, D)
         else:
             k = _rope(_lin(self.projk, key).view(B, Nk, H, D), kpos, self.rope_base)
         return k, _lin(self.projv, value).view(B, value.shape[1], H, D)
+
+    def _kv_operands(self):
+        """[projk; projv] stacked weight / bias for the fused K/V projection, rebuilt when the parameters change."""
+        key = (self.projk.weight.data_ptr(), self.projk.weight._version, self.projv.weight.data_ptr(),
+               self.projv.weight._version, self.projk.bias._version, self.projv.bias._version)
+        cache = getattr(self, "_kv_cache", None)
+        if cache is None or cache[0] != key:
+            w = torch.cat((self.projk.weight.detach(), self.projv.weight.detach()), dim=0).contiguous()
+            b_ = torch.cat((self.projk.bias.detach(), self.projv.bias.detach()), dim=0).contiguous()
+            object.__setattr__(self, "_kv_cache", (key, w, b_))
+            cache = self._kv_cache
+        return cache[1], cache[2]
 
     def attend(self, q: Tensor, k: Tensor, v: Tensor, residual: Tensor | None = None) -> Tensor:
         B, Nq, H, D = q.shape
