@@ -16,18 +16,23 @@ stream, which again starts behind a newer parent event.  Callers must keep the *
 """
 from __future__ import annotations
 
+import threading
 from typing import Callable, List, Sequence
 
 import torch
 
 _pools: dict = {}
+_tls = threading.local()
 enabled = True  # set False to run the branches sequentially on the current stream (debugging / A-B timing)
 
 
-def _side_streams(device, parent: torch.cuda.Stream, n: int) -> List[torch.cuda.Stream]:
-    # children are private to their parent stream: a block allocated on a child is only ever handed to work that is
-    # ordered behind the parent (see the module docstring); sharing children between parents would break that
-    key = (torch.device(device).index, parent.cuda_stream)
+def _side_streams(device, parent: torch.cuda.Stream, depth: int, n: int) -> List[torch.cuda.Stream]:
+    # children are private to their (parent stream, nesting depth): a block allocated on a child is only ever handed to
+    # work that is ordered behind the parent (see the module docstring).  The depth matters: branch 0 of a fork runs on
+    # the parent stream itself, so a nested fork inside it has the same parent - without the depth in the key it would
+    # reuse the streams on which the outer fork's sibling branches are still running and queue behind them
+    # (measured: backbone decoder 2.26 ms + stylizer decoder 1.43 ms ran in 3.72 ms "concurrently").
+    key = (torch.device(device).index, parent.cuda_stream, depth)
     pool = _pools.setdefault(key, [])
     while len(pool) < n:
         pool.append(torch.cuda.Stream(device=device))
@@ -37,24 +42,29 @@ def _side_streams(device, parent: torch.cuda.Stream, n: int) -> List[torch.cuda.
 def fork_join(fns: Sequence[Callable[[], object]], device=None, max_streams: int = 8, parallel: bool = True) -> list:
     """Run the callables as concurrent branches: fns[0] on the current stream, the others round-robin on side streams;
     returns their results in order after joining everything back into the current stream.  Re-entrant (a branch may
-    fork again: every stream owns its private child streams)."""
+    fork again: every (stream, nesting depth) owns its private child streams)."""
     fns = list(fns)
     if len(fns) <= 1 or not enabled or not parallel:
         return [fn() for fn in fns]
     device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
     n_side = min(len(fns) - 1, max_streams)
     cur = torch.cuda.current_stream(device)
-    side = _side_streams(device, cur, n_side)
+    depth = getattr(_tls, "depth", 0)
+    side = _side_streams(device, cur, depth, n_side)
     start = torch.cuda.Event()
     start.record(cur)
     for s in side:
         s.wait_event(start)
     results: list = [None] * len(fns)
-    # side branches first so that their kernels are enqueued before the (usually longest) main branch
-    for i in range(1, len(fns)):
-        with torch.cuda.stream(side[(i - 1) % n_side]):
-            results[i] = fns[i]()
-    results[0] = fns[0]()
+    _tls.depth = depth + 1
+    try:
+        # side branches first so that their kernels are enqueued before the (usually longest) main branch
+        for i in range(1, len(fns)):
+            with torch.cuda.stream(side[(i - 1) % n_side]):
+                results[i] = fns[i]()
+        results[0] = fns[0]()
+    finally:
+        _tls.depth = depth
     for s in side:
         done = torch.cuda.Event()
         done.record(s)
