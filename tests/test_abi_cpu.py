@@ -53,6 +53,20 @@ def test_null_arguments_are_rejected_without_touching_the_gpu():
     assert L.s3r_se3_update_w2c(None, None, None, None, 1, None) == -1
     g = _lib.RasterGrads()
     assert L.s3r_raster_backward(prm, None, 0, 0, g, None) == -1
+    # encoder / staging / output entry points: argument validation happens before any CUDA call
+    assert L.s3r_conv2d_bf16(None, None, None, None, None, 1, 16, 16, 64, 64, 3, 3, 1, 0, None) == -1
+    assert L.s3r_conv2d_bf16(None, None, None, None, None, 0, 16, 16, 64, 64, 3, 3, 1, 0, None) == 0      # empty batch
+    assert L.s3r_conv2d_bf16(None, None, None, None, None, 1, 16, 16, 64, 64, 3, 3, 0, 0, None) == -1     # nulls first
+    assert L.s3r_upsample2x_nhwc_bf16(None, None, None, 1, 8, 8, 64, None) == -1
+    assert L.s3r_layernorm_bf16(None, None, None, None, 4, 1024, 1024, 1e-6, None) == -1
+    assert L.s3r_layernorm_bf16(None, None, None, None, 0, 1024, 1024, 1e-6, None) == 0
+    assert L.s3r_ply_pack(None, None, None, None, None, None, 5, 1, 0, None, None) == -1
+    assert L.s3r_ply_pack(None, None, None, None, None, None, 0, 1, 0, None, None) == 0
+    assert L.s3r_rescale_crop(None, 3, 3, 8, 8, 4, 4, None, None, 7, None, None, 7, 0, 0, 4, 4, None, None, None, None, None) == -1
+    assert L.s3r_rescale_crop(None, 3, 3, 8, 8, 4, 4, None, None, 7, None, None, 7, 2, 0, 4, 4, None, None, None, None, None) == -1  # window outside
+    assert L.s3r_gaussian_adapter_nhwc(None, None, None, 8, 8, 8, None, 1, 16, 1, 0, 16, 1.0, None, None, None, None, None, None, None) == -1
+    assert L.s3r_gaussian_adapter_nhwc(None, None, None, 2, 8, 8, None, 1, 16, 1, 0, 16, 1.0, None, None, None, None, None, None, None) == -1  # ld < 3
+    assert L.s3r_set_tunable(99, 0) == -1 and L.s3r_set_tunable(2, 13) == -1 and L.s3r_set_tunable(2, 0) == 0
 
 
 def test_product_path_has_no_cpu_fallback():
