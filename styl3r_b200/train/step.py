@@ -55,6 +55,13 @@ def configure_optimizers(encoder: nn.Module, lr: float = 2e-4, backbone_lr_multi
     return opt, sched
 
 
+@torch.no_grad()
+def compute_psnr(ground_truth: Tensor, predicted: Tensor) -> Tensor:
+    """src/evaluation/metrics.py:12-19: per-image PSNR of [n,c,h,w] tensors clipped to [0,1]."""
+    mse = ((ground_truth.clip(min=0, max=1) - predicted.clip(min=0, max=1)) ** 2).flatten(1).mean(dim=1)
+    return -10 * mse.log10()
+
+
 def training_step(encoder: nn.Module, decoder: nn.Module, losses: Sequence[nn.Module], batch: dict, global_step: int = 0,
                   identity_loss: Optional[nn.Module] = None, data_shim=None, depth_mode=None) -> Tuple[Tensor, dict]:
     """Returns (total_loss, logs).  `batch` follows BatchedExample: context {image [b,v,3,h,w] in [0,1], intrinsics,
@@ -72,6 +79,7 @@ def training_step(encoder: nn.Module, decoder: nn.Module, losses: Sequence[nn.Mo
     output = decoder.forward(gaussians, tgt["extrinsics"], tgt["intrinsics"], tgt["near"], tgt["far"], (h, w),
                              depth_mode=depth_mode)
     logs, total = {}, 0
+    logs["train/psnr_probabilistic"] = compute_psnr(tgt["image"].flatten(0, 1), output.color.flatten(0, 1)).mean()
     for loss_fn in losses:
         val = loss_fn.forward(output, batch, gaussians, global_step)
         logs[f"loss/{getattr(loss_fn, 'name', type(loss_fn).__name__)}"] = val.detach()

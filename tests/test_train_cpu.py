@@ -172,3 +172,11 @@ def test_train_step_world_size_2_gloo_allreduces_gradients():
         singles.append(enc.gaussian_appearance_head.weight.grad.numpy())
     mean = 0.5 * (singles[0] + singles[1])
     assert np.allclose(g0 / np.abs(g0).max(), mean / np.abs(mean).max(), atol=1e-5)   # same direction (clip rescales the norm)
+
+
+def test_compute_psnr_matches_reference_formula():
+    from styl3r_b200.train.step import compute_psnr
+    g = torch.Generator().manual_seed(0)
+    a, b = torch.rand(3, 3, 8, 8, generator=g) * 1.2 - 0.1, torch.rand(3, 3, 8, 8, generator=g)
+    ref = -10 * ((a.clip(0, 1) - b.clip(0, 1)) ** 2).mean(dim=(1, 2, 3)).log10()
+    assert torch.allclose(compute_psnr(a, b), ref)
