@@ -154,3 +154,22 @@ def smooth_time(num_frames: int, device=None, smooth: bool = True) -> Tensor:
     """Frame times of `render_video_generic` (infer_model_re10k.py:193-195): linspace(0,1) with cosine ease in/out."""
     t = torch.linspace(0, 1, num_frames, dtype=torch.float32, device=device)
     return (torch.cos(torch.pi * (t + 1)) + 1) / 2 if smooth else t
+
+
+@torch.no_grad()
+def generate_wobble_transformation(radius: Tensor, t: Tensor, num_rotations: int = 1,
+                                   scale_radius_with_t: bool = True) -> Tensor:
+    """src/visualization/camera_trajectory/wobble.py:7-22: circular translation in the image plane, [*batch, T, 4, 4]."""
+    tf = torch.eye(4, dtype=torch.float32, device=t.device).broadcast_to((*radius.shape, t.shape[0], 4, 4)).clone()
+    radius = radius[..., None]
+    if scale_radius_with_t:
+        radius = radius * t
+    tf[..., 0, 3] = torch.sin(2 * torch.pi * num_rotations * t) * radius
+    tf[..., 1, 3] = -torch.cos(2 * torch.pi * num_rotations * t) * radius
+    return tf
+
+
+@torch.no_grad()
+def generate_wobble(extrinsics: Tensor, radius: Tensor, t: Tensor) -> Tensor:
+    """wobble.py:25-32: camera-to-world poses wobbling around `extrinsics`, [*batch, T, 4, 4]."""
+    return extrinsics[..., None, :, :] @ generate_wobble_transformation(radius, t)

@@ -15,7 +15,8 @@ from typing import Callable, Tuple
 import torch
 from torch import Tensor
 
-from .trajectory import interpolate_extrinsics, interpolate_intrinsics, smooth_time
+from .trajectory import (generate_wobble, generate_wobble_transformation, interpolate_extrinsics, interpolate_intrinsics,
+                         smooth_time)
 
 TrajectoryFn = Callable[[Tensor], Tuple[Tensor, Tensor]]
 
@@ -47,5 +48,39 @@ def render_video_interpolation(gaussians, decoder, batch: dict, num_frames: int 
         extrinsics = interpolate_extrinsics(ctx["extrinsics"][0, 0], ctx["extrinsics"][0, -1], t)
         intrinsics = interpolate_intrinsics(ctx["intrinsics"][0, 0], ctx["intrinsics"][0, -1], t)
         return extrinsics[None], intrinsics[None]
+
+    return render_video_generic(gaussians, decoder, batch, trajectory_fn, num_frames, smooth, loop_reverse)
+
+
+def render_video_wobble(gaussians, decoder, batch: dict, num_frames: int = 60, smooth: bool = True,
+                        loop_reverse: bool = True):
+    """model_wrapper_style.py:632-654: wobble around the first context camera with a quarter of the context baseline as
+    radius (needs exactly two context views, else None like the reference)."""
+    ctx = batch["context"]
+    if ctx["extrinsics"].shape[1] != 2:
+        return None
+
+    def trajectory_fn(t):
+        delta = (ctx["extrinsics"][:, 0, :3, 3] - ctx["extrinsics"][:, 1, :3, 3]).norm(dim=-1)
+        extrinsics = generate_wobble(ctx["extrinsics"][:, 0], delta * 0.25, t)
+        return extrinsics, ctx["intrinsics"][:, 0, None].expand(-1, t.shape[0], -1, -1)
+
+    return render_video_generic(gaussians, decoder, batch, trajectory_fn, num_frames, smooth, loop_reverse)
+
+
+def render_video_interpolation_exaggerated(gaussians, decoder, batch: dict, num_frames: int = 300, smooth: bool = False,
+                                           loop_reverse: bool = False):
+    """model_wrapper_style.py:684-728: interpolation extrapolated to t in [-2, 3] with a 5-turn wobble of half the
+    baseline on top (two context views only)."""
+    ctx = batch["context"]
+    if ctx["extrinsics"].shape[1] != 2:
+        return None
+
+    def trajectory_fn(t):
+        delta = (ctx["extrinsics"][:, 0, :3, 3] - ctx["extrinsics"][:, 1, :3, 3]).norm(dim=-1)
+        tf = generate_wobble_transformation(delta * 0.5, t, 5, scale_radius_with_t=False)
+        extrinsics = interpolate_extrinsics(ctx["extrinsics"][0, 0], ctx["extrinsics"][0, 1], t * 5 - 2)
+        intrinsics = interpolate_intrinsics(ctx["intrinsics"][0, 0], ctx["intrinsics"][0, 1], t * 5 - 2)
+        return extrinsics @ tf, intrinsics[None]
 
     return render_video_generic(gaussians, decoder, batch, trajectory_fn, num_frames, smooth, loop_reverse)

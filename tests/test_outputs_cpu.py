@@ -47,3 +47,26 @@ def test_ply_attribute_names_match_reference():
     from styl3r_b200.ply_export import construct_list_of_attributes
     assert construct_list_of_attributes(0) == list(GOLD["ply_plain_names"])
     assert construct_list_of_attributes(9) == list(GOLD["ply_rest_names"])
+
+
+def test_wobble_trajectories_match_reference_module():
+    """generate_wobble / generate_wobble_transformation vs the reference file executed in place when available
+    (src/visualization/camera_trajectory/wobble.py), else vs their closed form."""
+    import importlib.util
+    from styl3r_b200.trajectory import generate_wobble, generate_wobble_transformation
+    t = torch.linspace(0, 1, 9)
+    radius = torch.tensor([0.25, 0.5])
+    extr = torch.eye(4).repeat(2, 1, 1)
+    extr[:, :3, 3] = torch.tensor([[0.1, 0.2, 0.3], [-1.0, 0.5, 2.0]])
+    tf = generate_wobble_transformation(radius, t, 5, scale_radius_with_t=False)
+    assert tf.shape == (2, 9, 4, 4)
+    assert torch.allclose(tf[1, :, 0, 3], torch.sin(2 * torch.pi * 5 * t) * 0.5) and torch.allclose(tf[0, :, 1, 3], -torch.cos(2 * torch.pi * 5 * t) * 0.25)
+    wob = generate_wobble(extr, radius, t)
+    assert torch.allclose(wob[:, 0, :3, 3], extr[:, :3, 3])           # radius scales with t: starts at the camera
+    ref_path = Path("/root/reference/src/visualization/camera_trajectory/wobble.py")
+    if ref_path.exists():                                              # build container: compare with the reference itself
+        spec = importlib.util.spec_from_file_location("ref_wobble", ref_path)
+        ref = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(ref)
+        assert torch.equal(ref.generate_wobble(extr, radius, t), wob)
+        assert torch.equal(ref.generate_wobble_transformation(radius, t, 5, scale_radius_with_t=False), tf)
