@@ -230,11 +230,14 @@ def nhwc_supported(image_size) -> bool:
     ok = True
     for div in (32, 16, 8, 4, 2, 1):
         w, h = W // div, H // div
+        if w == 0 or h == 0:
+            return False
         if w >= 128:
             ok &= w % 128 == 0
+        elif 128 % w:
+            return False
         else:
-            ok &= 128 % w == 0
-            rows = 128 // w if w else 0
+            rows = 128 // w
             ok &= (h % rows == 0) if rows <= h else (rows % h == 0)
     return ok
 
