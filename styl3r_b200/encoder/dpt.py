@@ -225,7 +225,7 @@ def nhwc_supported(image_size) -> bool:
     """The implicit-GEMM kernel tiles 128 consecutive pixels as a box: every pyramid width must divide or be a multiple
     of 128 (true for the 256x256 production resolution and any power-of-two size >= 128)."""
     H, W = image_size
-    if H % 16 or W % 16:
+    if H % 16 or W % 16 or min(H, W) < 256:   # below the production resolution the fp32 module path is used
         return False
     ok = True
     for div in (32, 16, 8, 4, 2, 1):
