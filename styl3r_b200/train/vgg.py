@@ -42,7 +42,7 @@ def _vgg19_features_to_relu4_1() -> nn.Sequential:
 
 def _fast_supported(H: int, W: int) -> bool:
     """All four pyramid levels must satisfy the implicit-GEMM tiling rule (128-pixel tile = a box of the tensor)."""
-    if H % 8 or W % 8:
+    if H % 8 or W % 8 or min(H, W) < 128:   # small images: fp32 torch path
         return False
     for d in (1, 2, 4, 8):
         h, w = H // d, W // d
