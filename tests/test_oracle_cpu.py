@@ -130,3 +130,38 @@ def test_camera_setup_matches_torch_restating_reference_ops():
         np.testing.assert_allclose(view[v].reshape(16).numpy(), cam["view16"], atol=2e-6)
         np.testing.assert_allclose(full[v].reshape(16).numpy(), cam["proj16"], rtol=2e-6, atol=2e-6)
         np.testing.assert_allclose((0.5 * fov[v]).tan().numpy(), [cam["tanx"], cam["tany"]], rtol=2e-6)
+
+
+def test_raster_oracle_domain_properties():
+    """Size-independent properties of the restated algorithm (the same ones the GPU path is checked for at full size):
+    colour linearity, invariance under a permutation of the Gaussians (up to equal-depth ties, which keep input order),
+    empty / all-culled input."""
+    sc = syn.make_scene(seed=5, v=2, V=1, hw=64)
+    (o,), _ = oracle_scene(sc, use_sh=False)
+    # linearity: precomputed colours scaled by k (no clamp, zero background) scale the image by k, leave T / depth alone
+    sc2 = dict(sc, harmonics=sc["harmonics"] * 0.5)
+    (o2,), _ = oracle_scene(sc2, use_sh=False)
+    np.testing.assert_allclose(o2["color"], 0.5 * o["color"], atol=2e-6)
+    np.testing.assert_array_equal(o2["final_T"], o["final_T"])
+    np.testing.assert_array_equal(o2["depth"], o["depth"])
+    # permutation of the input order: same image (ties in depth are measure-zero for this scene), same per-tile counts
+    perm = np.random.default_rng(0).permutation(sc["means"].shape[0])
+    sc3 = dict(sc, means=sc["means"][perm], covariances=sc["covariances"][perm], harmonics=sc["harmonics"][perm],
+               opacities=sc["opacities"][perm])
+    (o3,), _ = oracle_scene(sc3, use_sh=False)
+    np.testing.assert_array_equal(o3["ranges"], o["ranges"])
+    mapped = perm[o3["point_list"]]
+    tie = np.zeros(len(mapped), bool)                      # equal (tile, depth) keys keep input order: permutation-dependent
+    tie[1:] |= o["keys"][1:] == o["keys"][:-1]
+    tie[:-1] |= o["keys"][1:] == o["keys"][:-1]
+    np.testing.assert_array_equal(mapped[~tie], o["point_list"][~tie])
+    assert tie.mean() < 0.01
+    for a, b in o["ranges"][::7]:                           # per tile the same set of Gaussians
+        np.testing.assert_array_equal(np.sort(mapped[a:b]), np.sort(o["point_list"][a:b]))
+    assert np.abs(o3["color"] - o["color"]).max() <= 2e-2 and np.abs(o3["color"] - o["color"]).mean() <= 1e-5
+    # everything behind the camera: nothing is binned, the image is the background
+    sc4 = dict(sc, means=sc["means"] * np.array([1, 1, -1], np.float32))
+    (o4,), _ = oracle_scene(sc4, use_sh=False, bg=(0.2, 0.4, 0.6))
+    assert o4["R"] == 0 and int(o4["radii"].max()) == 0 and int(o4["ranges"].max()) == 0
+    np.testing.assert_allclose(o4["color"], np.broadcast_to(np.array([0.2, 0.4, 0.6], np.float32)[:, None, None], o4["color"].shape))
+    assert float(o4["opacity"].max()) == 0.0
