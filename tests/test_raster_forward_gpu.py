@@ -6,6 +6,7 @@ Depth is compared with the same 1e-4 bound relative to the scene's depth scale.
 import numpy as np
 import pytest
 
+from oracle import raster_oracle as ro
 from styl3r_b200 import synthetic as syn
 from tests.helpers import gpu_scene, oracle_scene
 
@@ -130,3 +131,20 @@ def test_full_size_cfg2():
 
 def test_batched_views_share_one_gaussian_set():
     compare(syn.make_scene(seed=7, v=2, V=3, hw=128))
+
+
+def test_full_size_colour_linearity_property():
+    """Size-independent property at BASELINE cfg2 size (no oracle involved): compositing is linear in the colours -
+    halving every precomputed colour (exact in fp32) halves the image and leaves depth / opacity / tile structure
+    bit-identical."""
+    import torch
+    sc = syn.make_scene(seed=1234, v=2, V=1, hw=256)
+    cams = [ro.camera_setup(sc["extrinsics"][0], sc["intrinsics"][0], sc["near"][0], sc["far"][0], True)]
+    color_a, depth_a, opac_a, radii_a, _, ctx_a = gpu_scene(sc, cams, use_sh=False, want_n_touched=False)
+    sc2 = dict(sc, harmonics=sc["harmonics"] * np.float32(0.5))
+    color_b, depth_b, opac_b, radii_b, _, ctx_b = gpu_scene(sc2, cams, use_sh=False, want_n_touched=False)
+    torch.cuda.synchronize()
+    assert ctx_a.status()["num_instances"] == ctx_b.status()["num_instances"] > 250000
+    assert torch.equal(radii_a, radii_b) and torch.equal(depth_a, depth_b) and torch.equal(opac_a, opac_b)
+    assert (color_b - 0.5 * color_a).abs().max().item() <= 1e-12
+    assert color_a.abs().max().item() > 0.1
