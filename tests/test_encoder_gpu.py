@@ -67,10 +67,20 @@ def test_encoder_feeds_decoder(encoder):
     encoder.load_state_dict(sd, strict=True)
 
 
-def test_inference_layout_bf16_tcgen05_gemms_close_to_fp32_golden(encoder):
-    """to_inference(): bf16 ViT trunks whose Linear layers run on the tcgen05 GEMM (bias/GELU/residual fused), fp32
-    channels_last heads, replayed as a CUDA graph.  Tolerance vs the reference's fp32 golden: bf16 operands through
-    ~60 layers -> mean |err| <= 3e-2 * scale (measured ~1e-2)."""
+# bf16 tcgen05 path vs the reference's fp32 golden, in units of the golden tensor's std: (max, mean) bars per output =
+# ~2x the values measured on B200 (scripts/parity_probe.py: means 0.13 / 0.0074, covariances 0.46 / 0.038, harmonics
+# 0.088 / 0.023, opacities 0.048 / 0.014, scales 0.074 / 0.015, rotations 0.25 / 0.014).  bf16 operands have 8 mantissa
+# bits (the reference's TF32 matmuls 11) through ~60 layers; `means = dir * expm1(|xyz|)` and `cov = R S S^T R^T`
+# amplify head error, which is why those two carry the widest max bars.  The name-derived random weights are a worst
+# case (unit-gain, no trained structure).
+BF16_BARS = {"means": (0.30, 0.015), "covariances": (1.0, 0.08), "harmonics": (0.20, 0.05), "opacities": (0.10, 0.03),
+             "scales": (0.15, 0.03), "rotations": (0.50, 0.03)}
+
+
+def test_inference_layout_bf16_tcgen05_all_outputs_close_to_fp32_golden(encoder):
+    """to_inference(): bf16 ViT trunks on the tcgen05 GEMM / attention / LayerNorm kernels, bf16 NHWC DPT heads on the
+    tcgen05 implicit-GEMM convolution, fused adapter - replayed as a CUDA graph.  Max AND mean error bars on all six
+    outputs against the golden produced by the reference encoder (fp32, CPU)."""
     import copy
     import torch
     from styl3r_b200.encoder import GraphedEncoder
@@ -78,15 +88,58 @@ def test_inference_layout_bf16_tcgen05_gemms_close_to_fp32_golden(encoder):
     g = np.load(GOLD / "encoder_golden.npz")
     enc = copy.deepcopy(encoder).to_inference(torch.bfloat16)
     context, style = make_inputs(1, 2, 256, seed=1234, device="cuda")
+    dump = {}
+    with torch.no_grad():
+        eager = enc(context, style, visualization_dump=dump)
     fast = GraphedEncoder(enc)
     out = fast(context, style)
     out2 = fast(context, style)  # replay
     torch.cuda.synchronize()
-    assert torch.equal(out.means, out2.means)
-    for name, t in [("means", out.means), ("harmonics", out.harmonics), ("opacities", out.opacities)]:
+    assert torch.equal(out.means, out2.means) and torch.equal(out.means, eager.means)
+    for name, t in [("means", out.means), ("covariances", out.covariances), ("harmonics", out.harmonics),
+                    ("opacities", out.opacities), ("scales", dump["scales"]), ("rotations", dump["rotations"])]:
         ref, scale = g[f"b1v2_{name}"], float(g[f"b1v2_{name}_stats"][2])
         err = np.abs(sample(t) - ref)
-        assert err.mean() <= 3e-2 * scale, f"{name}: mean err {err.mean():.3e} scale {scale:.3e}"
+        mx, mean = BF16_BARS[name]
+        assert err.max() <= mx * scale and err.mean() <= mean * scale, \
+            f"{name}: max {err.max() / scale:.3e} mean {err.mean() / scale:.3e} (x sigma)"
+
+
+def test_rendered_rgb_drift_of_the_bf16_path(encoder):
+    """What the bf16 encoder error means for the product: Gaussians of the bf16 tcgen05 path and of the fp32 path (pinned
+    on the reference golden to 2e-3 sigma above) rendered through the rasterizer from three cameras.  Measured on B200:
+    PSNR 31 dB, mean |dRGB| 2e-3 with the worst-case random weights; bars: PSNR >= 27 dB, mean |dRGB| <= 5e-3."""
+    import copy
+    import torch
+    from styl3r_b200.decoder import render_cuda
+    from tests.encoder_weights import make_inputs
+    context, style = make_inputs(1, 2, 256, seed=1234, device="cuda")
+    with torch.no_grad():
+        o32 = encoder(context, style)
+        ob = copy.deepcopy(encoder).to_inference(torch.bfloat16)(context, style)
+    z = o32.means[0, :, 2]
+    zmed = float(z.median())
+    V = 3
+    extr = torch.eye(4, device="cuda").repeat(V, 1, 1)
+    if zmed < 0:  # random weights put most points behind the first context camera: look down -z instead
+        extr[:, 0, 0] = extr[:, 2, 2] = -1.0
+    extr[1, 0, 3], extr[2, 0, 3], extr[2, 1, 3] = 0.1 * abs(zmed), -0.05 * abs(zmed), 0.05 * abs(zmed)
+    K = context["intrinsics"][0, :1].float().expand(V, 3, 3).contiguous()
+    near = torch.full((V,), max(1e-3, 0.05 * abs(zmed)), device="cuda")
+    far = torch.full((V,), 1000 * abs(zmed), device="cuda")
+    bg, vs = torch.zeros(V, 3, device="cuda"), torch.zeros(V, dtype=torch.int32, device="cuda")
+    with torch.no_grad():
+        ca, _ = render_cuda(extr, K, near, far, (256, 256), bg, o32.means, o32.covariances, o32.harmonics, o32.opacities,
+                            view_set=vs)
+        cb, _ = render_cuda(extr, K, near, far, (256, 256), bg, ob.means.float(), ob.covariances.float(),
+                            ob.harmonics.float(), ob.opacities.float(), view_set=vs)
+    d = (ca - cb).abs()
+    peak = float(ca.abs().max())
+    psnr = 10 * np.log10(peak * peak / max(float(((ca - cb) ** 2).mean()), 1e-30))
+    coverage = float((ca.abs().sum(1) > 0).float().mean())
+    print(f"bf16-vs-fp32 rendered drift: max|d| {float(d.max()):.3e} mean|d| {float(d.mean()):.3e} PSNR {psnr:.1f} dB "
+          f"coverage {coverage:.3f}")
+    assert coverage > 0.01 and psnr >= 27.0 and float(d.mean()) <= 5e-3
 
 
 def test_stream_branches_do_not_change_results(encoder):

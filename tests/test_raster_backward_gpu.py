@@ -117,3 +117,8 @@ def test_autograd_through_render_cuda():
                              view_set=torch.zeros(2, dtype=torch.int32, device="cuda"))
         loss2 = ((c2 - target) ** 2).mean() + 0.01 * d2.mean()
     assert loss2 < loss, (float(loss), float(loss2))
+
+
+def test_backward_full_size_cfg2():
+    """BASELINE cfg2 size: 131 072 Gaussians, one 256x256 view - every gradient (incl. dL/dtau) against the oracle."""
+    run(syn.make_scene(seed=1234, v=2, V=1, hw=256), bg=(0.0, 0.0, 0.0), seed=3)

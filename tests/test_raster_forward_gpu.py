@@ -58,21 +58,23 @@ def compare(scene, deg=0, bg=(0.0, 0.0, 0.0), use_sh=True, cov_packed=False, cap
         np.testing.assert_array_equal(plist[start:start + R], o["point_list"])
         np.testing.assert_array_equal(pkeys[start:start + R] - (np.uint64(v * T) << np.uint64(32)), o["keys"])
         start += R
-        # ---- image
+        # ---- image: the 1e-4 bar holds on EVERY pixel (measured: max 1.2e-6 at cfg2, scripts/parity_probe.py).  `sens`
+        # marks the pixels where the oracle itself saw a decision within 1e-5 / 1e-9 of a threshold (16 of 65 536 at
+        # cfg2): only there may the early-termination point - and with it n_contrib - legitimately differ by one splat,
+        # whose weight is below 1e-4 by construction.
         sens = o["sens"] > 0
         dc = np.abs(color[v].cpu().numpy() - o["color"])
-        assert dc[:, ~sens].max(initial=0) <= RGB_TOL, f"view {v}: RGB max err {dc[:, ~sens].max()}"
-        assert sens.mean() < 2e-3
-        assert dc.max() <= 2e-2
+        assert dc.max(initial=0) <= RGB_TOL, f"view {v}: RGB max err {dc.max()}"
         dscale = max(1.0, float(np.abs(o["depth"]).max()))
         dd = np.abs(depth[v].cpu().numpy() - o["depth"])
-        assert dd[~sens].max(initial=0) <= RGB_TOL * dscale
+        assert dd.max(initial=0) <= RGB_TOL * dscale
         do = np.abs(opacity[v].cpu().numpy() - o["opacity"])
-        assert do[~sens].max(initial=0) <= RGB_TOL
+        assert do.max(initial=0) <= RGB_TOL
         fT = g("final_T").reshape(V, H, W)[v]
-        assert np.abs(fT - o["final_T"])[~sens].max(initial=0) <= RGB_TOL
+        assert np.abs(fT - o["final_T"]).max(initial=0) <= RGB_TOL
         nc = g("n_contrib").reshape(V, H, W)[v].view(np.uint32)
-        assert (nc != o["n_contrib"])[~sens].sum() == 0
+        nc_diff = nc != o["n_contrib"]
+        assert nc_diff[~sens].sum() == 0 and nc_diff.sum() <= max(1, int(1e-4 * nc.size))
         nt = n_touched[v].cpu().numpy()
         assert (nt != o["n_touched"]).mean() < 1e-3 and np.abs(nt - o["n_touched"]).max(initial=0) <= 2
     return ctx
@@ -148,3 +150,44 @@ def test_full_size_colour_linearity_property():
     assert torch.equal(radii_a, radii_b) and torch.equal(depth_a, depth_b) and torch.equal(opac_a, opac_b)
     assert (color_b - 0.5 * color_a).abs().max().item() <= 1e-12
     assert color_a.abs().max().item() > 0.1
+
+
+def test_full_size_cfg3_two_scenes_six_views_each():
+    """BASELINE cfg3 shape at size: scenes of 4x256x256 = 262 144 Gaussians with 6 target views each, two scenes in ONE
+    launch chain through `view_set` (12 views; cfg3 proper is four such scenes).  Tile ranges / sort order bit-exact and
+    RGB <= 1e-4 against the per-view oracle."""
+    import torch
+    from styl3r_b200 import rasterizer as rz
+    scenes = [syn.make_scene(seed=4321 + s, v=4, V=6, hw=256) for s in range(2)]
+    P, V = scenes[0]["means"].shape[0], 6
+    assert P == 262144
+    t = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float32, device="cuda")
+    cams, outs = [], []
+    for sc in scenes:
+        o, c = oracle_scene(sc)
+        outs += o
+        cams += c
+    st = lambda k: t(np.stack([sc[k] for sc in scenes]))
+    shs = t(np.stack([sc["harmonics"].transpose(0, 2, 1) for sc in scenes]))
+    cat = lambda k, shape: t(np.stack([c[k] for c in cams])).reshape(len(cams), *shape)
+    view_set = torch.arange(2, dtype=torch.int32, device="cuda").repeat_interleave(V)
+    color, depth, opacity, radii, _, ctx = rz.forward_raw(
+        st("means"), st("covariances"), st("opacities"), cat("view16", (4, 4)), cat("proj16", (4, 4)),
+        t(np.stack([[c["tanx"], c["tany"]] for c in cams])), torch.zeros(2 * V, 3, device="cuda"), 256, 256,
+        shs=shs, sh_degree=0, campos=cat("campos", (3,)), projmatrix_raw=cat("projraw16", (4, 4)),
+        scales=t(np.array([c["scale"] for c in cams], np.float32)), view_set=view_set)
+    torch.cuda.synchronize()
+    stt = ctx.status()
+    assert not stt["overflow"] and stt["num_instances"] == sum(o["R"] for o in outs)
+    T = ctx.layout.tiles
+    ranges = ctx.view("ranges").cpu().numpy().reshape(2 * V, T, 2).view(np.uint32).astype(np.int64)
+    plist = ctx.view("point_list").cpu().numpy().view(np.uint32)
+    start = 0
+    for v, o in enumerate(outs):
+        np.testing.assert_array_equal(radii[v].cpu().numpy(), o["radii"])
+        ne = o["ranges"][:, 1] > o["ranges"][:, 0]
+        np.testing.assert_array_equal((ranges[v] - start)[ne], o["ranges"].astype(np.int64)[ne])
+        np.testing.assert_array_equal(plist[start:start + o["R"]], o["point_list"])
+        start += o["R"]
+        dc = np.abs(color[v].cpu().numpy() - o["color"])
+        assert dc.max() <= RGB_TOL, f"view {v}: RGB max err {dc.max()}"
