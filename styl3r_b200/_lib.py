@@ -7,11 +7,14 @@ from __future__ import annotations
 import ctypes as C
 from pathlib import Path
 
-_LIB_PATH = Path(__file__).resolve().parent / "lib" / "libstyl3r_b200.so"
+import os as _os
+
+_TAG = _os.environ.get("S3R_LIB_TAG", "")  # development aid: A/B-timing of kernel variants (styl3r_b200/build.py)
+_LIB_PATH = Path(__file__).resolve().parent / "lib" / (f"libstyl3r_b200_{_TAG}.so" if _TAG else "libstyl3r_b200.so")
 _lib = None
 
 S3R_OK = 0
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class RasterParams(C.Structure):
@@ -34,7 +37,7 @@ class RasterLayout(C.Structure):
     _fields_ = [(n, C.c_int64) for n in (
         "total_bytes", "status", "counters", "depths", "xy", "conic_opacity", "rgb", "rect", "chunk_hist",
         "chunk_base", "tile_count", "ranges", "keys_unsorted", "keys_tmp", "point_list", "point_keys", "records",
-        "final_T", "n_contrib")] + [(n, C.c_int32) for n in ("tiles_x", "tiles_y", "tiles", "chunks")]
+        "final_T", "n_contrib", "grecords", "work_order")] + [(n, C.c_int32) for n in ("tiles_x", "tiles_y", "tiles", "chunks")]
 
 
 class RasterGrads(C.Structure):

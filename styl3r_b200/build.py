@@ -15,8 +15,11 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent
 CSRC = ROOT / "csrc"
 LIBDIR = ROOT / "lib"
-LIB = LIBDIR / "libstyl3r_b200.so"
-OBJDIR = ROOT.parent / "build" / "obj"
+# development aid: S3R_BUILD_TAG=x builds lib/libstyl3r_b200_x.so (objects under build/obj_x) with S3R_NVCC_FLAGS, so that
+# kernel variants can be A/B-timed in one GPU session (S3R_LIB_TAG=x selects it in _lib.py); the product is the untagged one
+_TAG = os.environ.get("S3R_BUILD_TAG", "")
+LIB = LIBDIR / (f"libstyl3r_b200_{_TAG}.so" if _TAG else "libstyl3r_b200.so")
+OBJDIR = ROOT.parent / "build" / (f"obj_{_TAG}" if _TAG else "obj")
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",

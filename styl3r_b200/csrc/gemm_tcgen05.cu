@@ -706,6 +706,15 @@ extern "C" int s3r_set_tunable(int32_t key, int32_t value) {
     g_gemm_big_tile = value;
     return S3R_OK;
   }
+  if (key == S3R_TUNE_RASTER_PDL) {
+    s3r_raster_pdl_mask() = value & 31;
+    return S3R_OK;
+  }
+  if (key == S3R_TUNE_BLEND_ONLY_TILE) {
+    if (value < 0) return S3R_ERR_INVALID_ARG;
+    s3r_blend_only_tile() = value;
+    return S3R_OK;
+  }
   if (key == S3R_TUNE_CONV_VARIANT) {
     if (value < -1 || value > 2) return S3R_ERR_INVALID_ARG;
     g_conv_variant = value;

@@ -1,7 +1,8 @@
 // Rasterizer stages 2-3: tile binning = the most-significant radix digit (view, tile) of upstream's
 // 64-bit (tile | depth) key sort, done as a stable counting sort in global memory.
 //
-//   bin_scan : column prefix sums over the per-chunk tile histograms written by preprocess
+//   bin_scan : column prefix sums over the per-chunk tile histograms written by preprocess (one warp per (view, tile),
+//              8 tiles per CTA so that the u16 histogram rows are read 16 bytes at a time)
 //              (chunk_hist[view][chunk][tile]) -> chunk_base, then (last CTA) an exclusive scan over all
 //              (view, tile) totals -> ranges[view*T+tile] = (start, end)  == upstream identifyTileRanges,
 //              R_total / overflow / max tile count -> status.            (replaces cub::InclusiveSum + D2H)
@@ -13,10 +14,13 @@
 //              (oracle/raster_oracle.c:s3r_oracle_bin_sort).
 #include "s3r_common.cuh"
 
-// grid (ceil(T/32), n_views), 1024 threads = 32 warps x 32 tiles; warp w scans a slice of the chunks.
-#define SCAN_THREADS 1024
-#define SCAN_WARPS 32
-__global__ void __launch_bounds__(SCAN_THREADS) s3r_bin_scan_kernel(int tiles, int chunks, int n_views,
+// grid (ceil(T/8), n_views), 256 threads = 8 warps: the CTA owns 8 adjacent tiles of one view, warp w scans tile w
+// over all chunks.  The [chunks x 8] u16 slab is read with one 16-byte load per chunk row and transposed through shared
+// memory; the [chunks x 8] u32 bases are written back as two 16-byte stores per chunk row.  dynamic smem:
+// chunks_pad * 8 * 4 bytes (u32 [8][chunks_pad], reused in place: counts in, exclusive prefixes out).
+#define SCAN_THREADS 256
+#define SCAN_TILES 8
+__global__ void __launch_bounds__(SCAN_THREADS) s3r_bin_scan_kernel(int tiles, int chunks, int chunks_pad, int n_views,
                                                                     const uint16_t* __restrict__ chunk_hist,
                                                                     uint32_t* __restrict__ chunk_base,
                                                                     uint32_t* __restrict__ tile_count,
@@ -24,40 +28,74 @@ __global__ void __launch_bounds__(SCAN_THREADS) s3r_bin_scan_kernel(int tiles, i
                                                                     long long* __restrict__ status,
                                                                     unsigned* __restrict__ counters,
                                                                     long long capacity) {
-  __shared__ uint32_t s_part[SCAN_WARPS][32];
-  __shared__ unsigned long long s_wsum[SCAN_WARPS];
-  __shared__ uint32_t s_wmax[SCAN_WARPS];
+  extern __shared__ uint32_t s_cnt[];  // [SCAN_TILES][chunks_pad + 32]: slot of chunk c = c + c / per (one pad word per lane slice: conflict-free)
+  __shared__ unsigned long long s_wsum[SCAN_THREADS / 32];
+  __shared__ uint32_t s_wmax[SCAN_THREADS / 32];
   __shared__ unsigned long long s_carry;
   __shared__ unsigned s_last;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int view = blockIdx.y;
-  const int t = blockIdx.x * 32 + lane;
-  const int cpw = (chunks + SCAN_WARPS - 1) / SCAN_WARPS;
-  const int c0 = min(chunks, w * cpw), c1 = min(chunks, c0 + cpw);
+  const int t0 = blockIdx.x * SCAN_TILES;
   const uint16_t* hist = chunk_hist + (size_t)view * chunks * tiles;
   uint32_t* base = chunk_base + (size_t)view * chunks * tiles;
-  uint32_t sum = 0;
-  if (t < tiles) {
-#pragma unroll 16
-    for (int c = c0; c < c1; c++) sum += hist[(size_t)c * tiles + t];
-  }
-  s_part[w][lane] = sum;
-  __syncthreads();
-  uint32_t run = 0, total = 0;
+  const int per = chunks_pad / 32;  // chunks scanned serially by one lane (chunks_pad is a multiple of 32)
+  const int pitch = chunks_pad + 32;
+  const bool vec = (tiles % SCAN_TILES) == 0;  // 16-byte rows (always true for images whose tile count is a multiple of 8)
+  s3r_grid_dependency_sync();
+  // ---- load + transpose
+  for (int c = threadIdx.x; c < chunks_pad; c += SCAN_THREADS) {
+    uint32_t v[SCAN_TILES];
 #pragma unroll
-  for (int k = 0; k < SCAN_WARPS; k++) {
-    const uint32_t v = s_part[k][lane];
-    if (k < w) run += v;
-    total += v;
+    for (int k = 0; k < SCAN_TILES; k++) v[k] = 0u;
+    if (c < chunks) {
+      if (vec) {
+        const uint4 q = *reinterpret_cast<const uint4*>(hist + (size_t)c * tiles + t0);
+        v[0] = q.x & 0xffffu, v[1] = q.x >> 16, v[2] = q.y & 0xffffu, v[3] = q.y >> 16;
+        v[4] = q.z & 0xffffu, v[5] = q.z >> 16, v[6] = q.w & 0xffffu, v[7] = q.w >> 16;
+      } else {
+#pragma unroll
+        for (int k = 0; k < SCAN_TILES; k++)
+          if (t0 + k < tiles) v[k] = hist[(size_t)c * tiles + t0 + k];
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < SCAN_TILES; k++) s_cnt[k * pitch + c + c / per] = v[k];
   }
-  if (t < tiles) {
-#pragma unroll 16
-    for (int c = c0; c < c1; c++) {
-      const uint32_t h = hist[(size_t)c * tiles + t];
-      base[(size_t)c * tiles + t] = run;
+  __syncthreads();
+  // ---- warp w: exclusive scan of tile t0 + w over the chunks (lane owns a contiguous slice)
+  {
+    uint32_t* row = s_cnt + w * pitch + lane * (per + 1);
+    uint32_t sum = 0;
+    for (int i = 0; i < per; i++) sum += row[i];
+    uint32_t incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += u;
+    }
+    uint32_t run = incl - sum;
+    for (int i = 0; i < per; i++) {
+      const uint32_t h = row[i];
+      row[i] = run;
       run += h;
     }
-    if (w == 0) tile_count[(size_t)view * tiles + t] = total;
+    if (lane == 31 && t0 + w < tiles) tile_count[(size_t)view * tiles + t0 + w] = incl;
+  }
+  __syncthreads();
+  // ---- write the bases back, one chunk row (8 tiles = 32 bytes) per thread
+  for (int c = threadIdx.x; c < chunks; c += SCAN_THREADS) {
+    uint32_t v[SCAN_TILES];
+#pragma unroll
+    for (int k = 0; k < SCAN_TILES; k++) v[k] = s_cnt[k * pitch + c + c / per];
+    if (vec) {
+      uint4* dst = reinterpret_cast<uint4*>(base + (size_t)c * tiles + t0);
+      dst[0] = make_uint4(v[0], v[1], v[2], v[3]);
+      dst[1] = make_uint4(v[4], v[5], v[6], v[7]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < SCAN_TILES; k++)
+        if (t0 + k < tiles) base[(size_t)c * tiles + t0 + k] = v[k];
+    }
   }
   // ---- last CTA: exclusive scan over all (view, tile) totals -> ranges
   __threadfence();
@@ -88,7 +126,8 @@ __global__ void __launch_bounds__(SCAN_THREADS) s3r_bin_scan_kernel(int tiles, i
     if (lane == 31) s_wsum[w] = incl;
     __syncthreads();
     unsigned long long woff = s_carry, blk = 0;
-    for (int k = 0; k < SCAN_WARPS; k++) {
+#pragma unroll
+    for (int k = 0; k < SCAN_THREADS / 32; k++) {
       const unsigned long long x = s_wsum[k];
       if (k < w) woff += x;
       blk += x;
@@ -112,7 +151,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) s3r_bin_scan_kernel(int tiles, i
   __syncthreads();
   if (threadIdx.x == 0) {
     uint32_t gmx = 0;
-    for (int k = 0; k < SCAN_WARPS; k++) gmx = max(gmx, s_wmax[k]);
+    for (int k = 0; k < SCAN_THREADS / 32; k++) gmx = max(gmx, s_wmax[k]);
     const unsigned long long grand = s_carry;
     status[0] = (long long)grand;
     status[1] = grand > cap ? 1 : 0;
@@ -133,10 +172,15 @@ __global__ void __launch_bounds__(S3R_CHUNK) s3r_bin_emit_kernel(int P, int tile
   unsigned char* s_pre = reinterpret_cast<unsigned char*>(s_mem + (size_t)tiles * 8);  // [tiles][8]
   const int view = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x;
   for (int i = tid; i < tiles * 8; i += S3R_CHUNK) s_mask[i] = 0u;
+  s3r_grid_dependency_sync();
   __syncthreads();
   const int g = chunk * S3R_CHUNK + tid;
   uint32_t rect = 0u;
-  if (g < P) rect = rect_in[(size_t)view * P + g];
+  uint32_t dbits = 0u;  // requested together with the rect: one global round trip instead of two
+  if (g < P) {
+    rect = rect_in[(size_t)view * P + g];
+    dbits = __float_as_uint(depths[(size_t)view * P + g]);
+  }
   const int xmin = rect & 255, ymin = (rect >> 8) & 255, xmax = (rect >> 16) & 255, ymax = rect >> 24;
   const uint32_t bit = 1u << (tid & 31);
   const int w = tid >> 5;
@@ -155,7 +199,6 @@ __global__ void __launch_bounds__(S3R_CHUNK) s3r_bin_emit_kernel(int P, int tile
   }
   __syncthreads();
   if (rect == 0u) return;
-  const uint32_t dbits = __float_as_uint(depths[(size_t)view * P + g]);
   const unsigned long long key = ((unsigned long long)dbits << 32) | (uint32_t)g;
   const uint32_t* cb = chunk_base + ((size_t)view * chunks + chunk) * tiles;
   const uint2* rg = ranges + (size_t)view * tiles;
@@ -172,24 +215,25 @@ __global__ void __launch_bounds__(S3R_CHUNK) s3r_bin_emit_kernel(int P, int tile
 
 int s3r_launch_bin(const s3r_raster_params& p, const s3r_raster_layout& L, char* state, int64_t capacity,
                    cudaStream_t st) {
-  dim3 g1((L.tiles + 31) / 32, p.n_views);
-  s3r_bin_scan_kernel<<<g1, SCAN_THREADS, 0, st>>>(L.tiles, L.chunks, p.n_views, (const uint16_t*)(state + L.chunk_hist),
-                                          (uint32_t*)(state + L.chunk_base), (uint32_t*)(state + L.tile_count),
-                                          (uint2*)(state + L.ranges), (long long*)(state + L.status),
-                                          (unsigned*)(state + L.counters), (long long)capacity);
-  S3R_CUDA_CHECK(cudaGetLastError());
+  dim3 g1((L.tiles + SCAN_TILES - 1) / SCAN_TILES, p.n_views);
+  const int chunks_pad = (L.chunks + 31) / 32 * 32;
+  const size_t smem1 = (size_t)(chunks_pad + 32) * SCAN_TILES * sizeof(uint32_t);
+  static size_t configured1[64] = {};
+  int rc = s3r_ensure_dynamic_smem(s3r_bin_scan_kernel, smem1, configured1);
+  if (rc != S3R_OK) return rc;
+  if (smem1 > 200 * 1024) return S3R_ERR_UNSUPPORTED;  // > 6400 chunks = 1.6 M Gaussians per set
+  S3R_CUDA_CHECK(s3r_launch_pdl(s3r_bin_scan_kernel, g1, dim3(SCAN_THREADS), smem1, st, (s3r_raster_pdl_mask() >> 1) & 1, L.tiles, L.chunks, chunks_pad,
+                                p.n_views, (const uint16_t*)(state + L.chunk_hist), (uint32_t*)(state + L.chunk_base),
+                                (uint32_t*)(state + L.tile_count), (uint2*)(state + L.ranges),
+                                (long long*)(state + L.status), (unsigned*)(state + L.counters), (long long)capacity));
   const size_t smem = (size_t)L.tiles * 8 * sizeof(uint32_t) + (size_t)L.tiles * 8;
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    S3R_CUDA_CHECK(cudaFuncSetAttribute(s3r_bin_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  static size_t configured2[64] = {};
+  rc = s3r_ensure_dynamic_smem(s3r_bin_emit_kernel, smem, configured2);
+  if (rc != S3R_OK) return rc;
   dim3 g2(L.chunks, p.n_views);
-  s3r_bin_emit_kernel<<<g2, S3R_CHUNK, smem, st>>>(p.P, L.tiles_x, L.tiles, L.chunks, (const uint32_t*)(state + L.rect),
-                                                  (const float*)(state + L.depths),
-                                                  (const uint32_t*)(state + L.chunk_base),
-                                                  (const uint2*)(state + L.ranges),
-                                                  (unsigned long long*)(state + L.keys_unsorted));
-  S3R_CUDA_CHECK(cudaGetLastError());
+  S3R_CUDA_CHECK(s3r_launch_pdl(s3r_bin_emit_kernel, g2, dim3(S3R_CHUNK), smem, st, (s3r_raster_pdl_mask() >> 2) & 1, p.P, L.tiles_x, L.tiles, L.chunks,
+                                (const uint32_t*)(state + L.rect), (const float*)(state + L.depths),
+                                (const uint32_t*)(state + L.chunk_base), (const uint2*)(state + L.ranges),
+                                (unsigned long long*)(state + L.keys_unsorted)));
   return S3R_OK;
 }

@@ -69,15 +69,19 @@ __device__ __noinline__ float exact_alpha(float power, float opacity) {
 #ifndef BLEND_SPLIT
 #define BLEND_SPLIT 1     // CTAs per 16x16 tile (1: 8 consumer warps, 2: half tiles of 16x8 px with 4 consumer warps)
 #endif
+#ifndef BLEND_CTAS_PER_SM
+#define BLEND_CTAS_PER_SM BLEND_MINB  // persistent CTAs per SM (fewer resident CTAs than work units => dynamic balancing)
+#endif
 #define BLEND_CWARPS (8 / BLEND_SPLIT)  // consumer warps (one 8x4 pixel block each); the last warp is the TMA producer
 #define BLEND_THREADS (32 * (BLEND_CWARPS + 1))
 
 struct __align__(128) BlendSmem {
   float4 rec[BLEND_STAGES][(BLEND_CHUNK + 1) * 3];  // + one dummy record per stage (never hits): pads survivor batches
-  uint8_t list[BLEND_CWARPS][BLEND_CHUNK + 16];  // per-warp compacted survivor indices
+  uint8_t list[BLEND_CWARPS][BLEND_CHUNK + 2 * BLEND_U + 8];  // per-warp compacted survivor indices
   uint64_t full[BLEND_STAGES];                   // producer -> consumers (expect_tx / complete_tx)
   uint64_t empty[BLEND_STAGES];                  // consumers -> producer (one arrival per consumer warp)
   int done_warps;
+  uint32_t unit;  // work unit fetched by thread 0 for the whole CTA
 };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -117,34 +121,53 @@ __device__ __noinline__ bool exact_decide(const float4 co, float dx, float dy, f
 
 template <bool kHasNT>
 __global__ void __launch_bounds__(BLEND_THREADS, BLEND_MINB) s3r_blend_fwd_kernel(
-    int W, int H, int P, int tiles_x, int tiles, const uint2* __restrict__ ranges, const float4* __restrict__ records,
+    int W, int H, int P, int tiles_x, int tiles, int only_tile, uint32_t n_units, const uint32_t* __restrict__ work_order,
+    unsigned* __restrict__ counters, const uint2* __restrict__ ranges, const float4* __restrict__ records,
     const uint32_t* __restrict__ point_list, const float4* __restrict__ conic_opacity,
     const float* __restrict__ background, float* __restrict__ out_color,
     float* __restrict__ out_depth, float* __restrict__ out_opacity, float* __restrict__ final_T,
     uint32_t* __restrict__ n_contrib, int32_t* __restrict__ n_touched) {
   __shared__ BlendSmem sm;
-  const int view = blockIdx.y, tile = blockIdx.x / BLEND_SPLIT, part = blockIdx.x % BLEND_SPLIT, tid = threadIdx.x;
-  const int lane = tid & 31, w = tid >> 5;
-  const uint2 rg = ranges[(size_t)view * tiles + tile];
-  const uint32_t n = rg.y - rg.x;
-  const uint32_t nchunks = (n + BLEND_CHUNK - 1) / BLEND_CHUNK;
-  const float4* src = records + (size_t)rg.x * 3;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
 
+  if (tid < BLEND_STAGES) {  // dummy record: so far away that log2 G = -1.8e19 -> alpha = 0 (no range predicates in the loop)
+    sm.rec[tid][BLEND_CHUNK * 3] = make_float4(3e9f, 3e9f, -1.0f, 0.0f);
+    sm.rec[tid][BLEND_CHUNK * 3 + 1] = make_float4(-1.0f, 0.0f, 0.0f, 0.0f);
+    sm.rec[tid][BLEND_CHUNK * 3 + 2] = make_float4(0.0f, 0.0f, -1.0f, -1.0f);
+  }
+  s3r_grid_dependency_sync();  // the prologue above is shared-memory only
+
+  // Persistent CTA: work units (view, tile, part) are fetched from a device-side queue in the order bin_scan wrote to
+  // `work_order` - heaviest tiles first (longest-processing-time-first list scheduling), so the SMs finish together even
+  // though tiles differ 7x in instance count.
+  for (bool first_unit = true;; first_unit = false) {
   if (tid == 0) {
+    if (!first_unit) {
+#pragma unroll
+      for (int s = 0; s < BLEND_STAGES; s++) {
+        asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(&sm.full[s])) : "memory");
+        asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(&sm.empty[s])) : "memory");
+      }
+    }
 #pragma unroll
     for (int s = 0; s < BLEND_STAGES; s++) {
       mbar_init(&sm.full[s], 1);
       mbar_init(&sm.empty[s], BLEND_CWARPS);
     }
     sm.done_warps = 0;
+    sm.unit = atomicAdd(&counters[1], 1u);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (tid < BLEND_STAGES) {  // dummy record: so far away that log2 G = -1.8e19 -> alpha = 0 (no range predicates in the loop)
-    sm.rec[tid][BLEND_CHUNK * 3] = make_float4(3e9f, 3e9f, -1.0f, 0.0f);
-    sm.rec[tid][BLEND_CHUNK * 3 + 1] = make_float4(-1.0f, 0.0f, 0.0f, 0.0f);
-    sm.rec[tid][BLEND_CHUNK * 3 + 2] = make_float4(0.0f, 0.0f, -1.0f, -1.0f);
-  }
   __syncthreads();
+  const uint32_t unit = sm.unit;
+  if (unit >= n_units) break;
+  const uint32_t vt = only_tile >= 0 ? (uint32_t)only_tile : work_order[unit / BLEND_SPLIT];
+  const int part = unit % BLEND_SPLIT;
+  const int view = vt / tiles, tile = vt % tiles;
+  const uint2 rg = ranges[vt];
+  const uint32_t n = rg.y - rg.x;
+  const uint32_t nchunks = (n + BLEND_CHUNK - 1) / BLEND_CHUNK;
+  const float4* src = records + (size_t)rg.x * 3;
 
   if (w == BLEND_CWARPS) {
     // ===== TMA producer (one elected lane)
@@ -154,8 +177,9 @@ __global__ void __launch_bounds__(BLEND_THREADS, BLEND_MINB) s3r_blend_fwd_kerne
         const int s = c % BLEND_STAGES;
         if (c >= BLEND_STAGES) {
           const uint32_t par = ((c / BLEND_STAGES) - 1) & 1;
-          while (!mbar_try(&sm.empty[s], par)) {
+          while (!mbar_try(&sm.empty[s], par)) {  // back off between polls: the producer must not steal issue slots
             if (*(volatile int*)&sm.done_warps == BLEND_CWARPS) break;
+            __nanosleep(100);
           }
         }
         if (*(volatile int*)&sm.done_warps == BLEND_CWARPS) break;
@@ -168,9 +192,7 @@ __global__ void __launch_bounds__(BLEND_THREADS, BLEND_MINB) s3r_blend_fwd_kerne
       const uint32_t first = issued > BLEND_STAGES ? issued - BLEND_STAGES : 0;
       for (uint32_t c = first; c < issued; c++) mbar_wait(&sm.full[c % BLEND_STAGES], (c / BLEND_STAGES) & 1);
     }
-    return;
-  }
-
+  } else {
   // ===== consumers
   const int tx = tile % tiles_x, ty = tile / tiles_x;
   const int wt = part * BLEND_CWARPS + w;                                            // warp index inside the tile
@@ -182,10 +204,14 @@ __global__ void __launch_bounds__(BLEND_THREADS, BLEND_MINB) s3r_blend_fwd_kerne
   const uint32_t lt = (1u << lane) - 1u;
   uint8_t* list = sm.list[w];
 
+  // A pixel that has terminated (test_T < 1e-4), or lies outside the image, is "dead": its lane keeps running in
+  // lockstep with a poisoned pixel coordinate (+inf), so every later alpha evaluates to exactly 0 and its T, colour and
+  // n_contrib stay frozen without any `done` predicate in the loop.
   float T = 1.0f, Cr = 0.f, Cg = 0.f, Cb = 0.f, D = 0.f;
+  float pxe = inside ? pxf : __int_as_float(0x7f800000);  // x coordinate used for evaluation
+  bool alive = inside;
   uint32_t last = 0;
-  bool done = !inside;
-  bool warp_done = !__any_sync(0xffffffffu, !done);
+  bool warp_done = !__any_sync(0xffffffffu, inside);
   if (warp_done && lane == 0) atomicAdd(&sm.done_warps, 1);
 
   for (uint32_t c = 0; c < nchunks; c++) {
@@ -198,6 +224,7 @@ __global__ void __launch_bounds__(BLEND_THREADS, BLEND_MINB) s3r_blend_fwd_kerne
         bool all = false;
         while (!mbar_try(&sm.empty[s], par)) {
           if (*(volatile int*)&sm.done_warps == BLEND_CWARPS) { all = true; break; }
+          __nanosleep(100);
         }
         if (all) break;
       }
@@ -228,82 +255,120 @@ __global__ void __launch_bounds__(BLEND_THREADS, BLEND_MINB) s3r_blend_fwd_kerne
     if (lane < BLEND_U) list[count + lane] = (uint8_t)BLEND_CHUNK;  // pad the last batch with the dummy record
     __syncwarp();
     const uint32_t base_idx = c * BLEND_CHUNK;
+    int lastpos = -1;
+    uint32_t packed_next[(BLEND_U + 3) / 4];  // survivor indices of the next batch, fetched one batch ahead
+#pragma unroll
+    for (int q4 = 0; q4 < (BLEND_U + 3) / 4; q4++) packed_next[q4] = *reinterpret_cast<const uint32_t*>(list + 4 * q4);
 #pragma unroll 1
     for (int k = 0; k < count; k += BLEND_U) {
       uint32_t packed[(BLEND_U + 3) / 4];
 #pragma unroll
-      for (int q4 = 0; q4 < (BLEND_U + 3) / 4; q4++) packed[q4] = *reinterpret_cast<const uint32_t*>(list + k + 4 * q4);
-      float alpha[BLEND_U], cr[BLEND_U], cg[BLEND_U], cb[BLEND_U], dp[BLEND_U];
-      bool keep[BLEND_U];
-      int idx[BLEND_U];
-      unsigned near_thr = 0u;  // (bitwise flag arithmetic below: short-circuit && / || would compile to divergent branches)
+      for (int q4 = 0; q4 < (BLEND_U + 3) / 4; q4++) {
+        packed[q4] = packed_next[q4];
+        packed_next[q4] = *reinterpret_cast<const uint32_t*>(list + k + BLEND_U + 4 * q4);
+      }
+      float alpha[BLEND_U], cr[BLEND_U], cg[BLEND_U], cb[BLEND_U], dp[BLEND_U];  // alpha: 0 unless the splat is kept
+      float t[BLEND_U + 1];
+      const int lastpos_in = lastpos;
+      bool near_thr = false;
       // ---- BLEND_U independent alpha chains (branch-free)
 #pragma unroll
       for (int u = 0; u < BLEND_U; u++) {
         const int i = (packed[u >> 2] >> (8 * (u & 3))) & 0xff;  // entries past `count` are the dummy record
-        idx[u] = i;
         const float4 r0 = sm.rec[s][i * 3];
         const float4 r1 = sm.rec[s][i * 3 + 1];
         const float2 r2 = *reinterpret_cast<const float2*>(&sm.rec[s][i * 3 + 2]);
-        const float dx = r0.x - pxf, dy = r0.y - pyf;
+        const float dx = r0.x - pxe, dy = r0.y - pyf;
         // log2 G = dx*(A'*dx + B'*dy) + C'*dy*dy on the pre-scaled conic: 2 FMUL + 2 FFMA + 1 FMUL, then MUFU.EX2
         const float l2g = fmaf(dx, fmaf(r0.z, dx, r0.w * dy), (r1.x * dy) * dy);
         const float a = fminf(0.99f, r1.y * fast_exp2(l2g));
-        const unsigned hi = (unsigned)(a >= ALPHA_HI);
-        keep[u] = ((unsigned)(l2g <= 0.0f) & hi) != 0u;
-        // guard bands: alpha within 1e-4 (relative) of 1/255, or an exponent so close to 0 that its sign is in doubt
-        near_thr |= ((unsigned)(a >= ALPHA_LO) & (hi ^ 1u)) | (unsigned)(fabsf(l2g) < S3R_PZERO_BAND);
-        alpha[u] = a;
+        const bool keep = a >= ALPHA_HI;
+        // guard bands: alpha within 1e-4 (relative) below 1/255, or an exponent that is positive / so close to 0 that
+        // its sign is in doubt (the oracle skips `power > 0`): those evaluations are decided exactly below
+        near_thr = near_thr || ((a >= ALPHA_LO) && !keep) || (l2g > -S3R_PZERO_BAND);
+        alpha[u] = keep ? a : 0.0f;
+        lastpos = keep ? (k + u) : lastpos;
         cr[u] = r1.z;
         cg[u] = r1.w;
         cb[u] = r2.x;
         dp[u] = r2.y;
       }
       // ---- rare: some evaluation landed in a guard band -> decide it like the oracle, from the exact conic
-      if (__any_sync(0xffffffffu, near_thr != 0u)) {
+      if (__any_sync(0xffffffffu, near_thr)) {
+        lastpos = lastpos_in;
 #pragma unroll
         for (int u = 0; u < BLEND_U; u++) {
           if (k + u < count) {
-            const int i = idx[u];
+            const int i = (packed[u >> 2] >> (8 * (u & 3))) & 0xff;
             const float4 r0 = sm.rec[s][i * 3];
             const float4 r1 = sm.rec[s][i * 3 + 1];
-            const float dx = r0.x - pxf, dy = r0.y - pyf;
+            const float dx = r0.x - pxe, dy = r0.y - pyf;
             const float l2g = fmaf(dx, fmaf(r0.z, dx, r0.w * dy), (r1.x * dy) * dy);
-            const float a = alpha[u];
-            if ((a >= ALPHA_LO && a < ALPHA_HI) || fabsf(l2g) < S3R_PZERO_BAND) {
+            const float a = fminf(0.99f, r1.y * fast_exp2(l2g));
+            if ((a >= ALPHA_LO && a < ALPHA_HI) || l2g > -S3R_PZERO_BAND) {
               const uint32_t gid = point_list[(size_t)rg.x + base_idx + i];
               float ax = a;
-              keep[u] = exact_decide(conic_opacity[(size_t)view * P + gid], dx, dy, &ax);
-              alpha[u] = ax;
+              const bool kx = exact_decide(conic_opacity[(size_t)view * P + gid], dx, dy, &ax);
+              alpha[u] = (kx && alive) ? ax : 0.0f;
+            }
+          }
+          lastpos = alpha[u] > 0.0f ? (k + u) : lastpos;
+        }
+      }
+      // ---- transmittance chain of the batch; T only decreases, so the batch contains a termination iff t[U] < 1e-4
+      t[0] = T;
+#pragma unroll
+      for (int u = 0; u < BLEND_U; u++) t[u + 1] = t[u] * (1.0f - alpha[u]);
+      if (!__any_sync(0xffffffffu, t[BLEND_U] < 0.0001f)) {
+        // common case: front-to-back compositing of the whole batch without a single predicate
+#pragma unroll
+        for (int u = 0; u < BLEND_U; u++) {
+          const float wgt = alpha[u] * t[u];
+          Cr = fmaf(cr[u], wgt, Cr);
+          Cg = fmaf(cg[u], wgt, Cg);
+          Cb = fmaf(cb[u], wgt, Cb);
+          D = fmaf(dp[u], wgt, D);
+          if (kHasNT) {
+            if (alpha[u] > 0.0f && t[u + 1] > 0.5f) {
+              const int i = (packed[u >> 2] >> (8 * (u & 3))) & 0xff;
+              atomicAdd(&n_touched[(size_t)view * P + point_list[(size_t)rg.x + base_idx + i]], 1);
             }
           }
         }
-      }
-      // ---- sequential front-to-back compositing, predicated (no divergent branches)
+        T = t[BLEND_U];
+      } else {
+        // some pixel of the warp terminates inside this batch (at most once per pixel): predicated version
+        lastpos = lastpos_in;
 #pragma unroll
-      for (int u = 0; u < BLEND_U; u++) {
-        const bool active = keep[u] && !done;
-        const float test_T = T * (1.0f - alpha[u]);
-        const bool term = active && (test_T < 0.0001f);
-        const bool acc = active && !term;
-        const float wgt = acc ? alpha[u] * T : 0.0f;
-        Cr = fmaf(cr[u], wgt, Cr);
-        Cg = fmaf(cg[u], wgt, Cg);
-        Cb = fmaf(cb[u], wgt, Cb);
-        D = fmaf(dp[u], wgt, D);
-        if (kHasNT) {
-          if (acc && test_T > 0.5f)
-            atomicAdd(&n_touched[(size_t)view * P + point_list[(size_t)rg.x + base_idx + idx[u]]], 1);
+        for (int u = 0; u < BLEND_U; u++) {
+          const bool stop = t[u + 1] < 0.0001f;  // stays true for the rest of the batch
+          const bool acc = !stop && alpha[u] > 0.0f;
+          const float wgt = stop ? 0.0f : alpha[u] * t[u];
+          Cr = fmaf(cr[u], wgt, Cr);
+          Cg = fmaf(cg[u], wgt, Cg);
+          Cb = fmaf(cb[u], wgt, Cb);
+          D = fmaf(dp[u], wgt, D);
+          if (kHasNT) {
+            if (acc && t[u + 1] > 0.5f) {
+              const int i = (packed[u >> 2] >> (8 * (u & 3))) & 0xff;
+              atomicAdd(&n_touched[(size_t)view * P + point_list[(size_t)rg.x + base_idx + i]], 1);
+            }
+          }
+          T = stop ? T : t[u + 1];
+          lastpos = acc ? (k + u) : lastpos;
         }
-        T = acc ? test_T : T;
-        last = acc ? (base_idx + idx[u] + 1) : last;
-        done = done || term;
-      }
-      if (!__any_sync(0xffffffffu, !done)) {
-        warp_done = true;
-        break;
+        if (t[BLEND_U] < 0.0001f) {
+          alive = false;
+          pxe = __int_as_float(0x7f800000);
+        }
+        if (!__any_sync(0xffffffffu, alive)) {
+          warp_done = true;
+          break;
+        }
       }
     }
+    // n_contrib = 1-based index of the last composited splat: resolve this chunk's list position while the list is live
+    if (lastpos >= 0) last = base_idx + list[lastpos] + 1u;
     __syncwarp();
     if (lane == 0) {
       if (warp_done) atomicAdd(&sm.done_warps, 1);
@@ -323,17 +388,58 @@ __global__ void __launch_bounds__(BLEND_THREADS, BLEND_MINB) s3r_blend_fwd_kerne
     final_T[(size_t)view * HW + pix] = T;
     n_contrib[(size_t)view * HW + pix] = last;
   }
+  }  // consumers
+  __syncthreads();  // the unit is finished: every bulk copy has landed, nobody touches the ring or the barriers any more
+  }  // unit loop
+  // the last CTA to leave rewinds the queue for the next launch on this state buffer
+  if (tid == 0) {
+    __threadfence();
+    if (atomicAdd(&counters[2], 1u) == gridDim.x - 1) {
+      counters[1] = 0u;
+      counters[2] = 0u;
+    }
+  }
+}
+
+int& s3r_raster_pdl_mask() {
+  // measured on B200 (scripts/raster_probe.py): PDL shortens the chain only in front of preprocess and bin_emit
+  // (-1.4 us); in front of bin_scan / tile_sort / blend it costs 4-16 us
+  static int v = 5;
+  return v;
+}
+
+int& s3r_blend_only_tile() {
+  static int v = 0;
+  return v;
 }
 
 int s3r_launch_blend(const s3r_raster_params& p, const s3r_raster_outputs& o, const s3r_raster_layout& L,
                      char* state, cudaStream_t st) {
-  dim3 grid(L.tiles * BLEND_SPLIT, p.n_views);
   auto kern = o.n_touched ? s3r_blend_fwd_kernel<true> : s3r_blend_fwd_kernel<false>;
-  kern<<<grid, BLEND_THREADS, 0, st>>>(
-      p.width, p.height, p.P, L.tiles_x, L.tiles, (const uint2*)(state + L.ranges),
-      (const float4*)(state + L.records), (const uint32_t*)(state + L.point_list),
-      (const float4*)(state + L.conic_opacity), p.background, o.color, o.depth,
-      o.opacity, (float*)(state + L.final_T), (uint32_t*)(state + L.n_contrib), o.n_touched);
-  S3R_CUDA_CHECK(cudaGetLastError());
+  // persistent grid: as many CTAs as the device holds at once (per device, cached), never more than there are units
+  static int slots[64] = {};
+  int dev = 0;
+  S3R_CUDA_CHECK(cudaGetDevice(&dev));
+  dev &= 63;
+  if (slots[dev] == 0) {
+    int sms = 0, per_sm = 0;
+    S3R_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    S3R_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, s3r_blend_fwd_kernel<false>, BLEND_THREADS, 0));
+    if (per_sm > BLEND_CTAS_PER_SM) per_sm = BLEND_CTAS_PER_SM;
+    slots[dev] = sms * (per_sm > 0 ? per_sm : 1);
+  }
+  uint32_t n_units = (uint32_t)L.tiles * (uint32_t)p.n_views * BLEND_SPLIT;
+  int only_tile = -1;
+  if (s3r_blend_only_tile() > 0 && s3r_blend_only_tile() <= L.tiles) {  // development probe: one tile of view 0
+    only_tile = s3r_blend_only_tile() - 1;
+    n_units = BLEND_SPLIT;
+  }
+  dim3 grid(n_units < (uint32_t)slots[dev] ? n_units : (uint32_t)slots[dev]);
+  S3R_CUDA_CHECK(s3r_launch_pdl(kern, grid, dim3(BLEND_THREADS), 0, st, (s3r_raster_pdl_mask() >> 4) & 1, p.width, p.height,
+                                p.P, L.tiles_x, L.tiles, only_tile, n_units, (const uint32_t*)(state + L.work_order),
+                                (unsigned*)(state + L.counters), (const uint2*)(state + L.ranges),
+                                (const float4*)(state + L.records), (const uint32_t*)(state + L.point_list),
+                                (const float4*)(state + L.conic_opacity), p.background, o.color, o.depth, o.opacity,
+                                (float*)(state + L.final_T), (uint32_t*)(state + L.n_contrib), o.n_touched));
   return S3R_OK;
 }

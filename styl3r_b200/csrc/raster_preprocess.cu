@@ -56,17 +56,20 @@ __device__ __forceinline__ float3 sh_to_rgb(int deg, int M, const float* __restr
 }
 
 // grid (chunks, n_views), 256 threads. dynamic smem: tiles * 8 words.
-__global__ void __launch_bounds__(S3R_CHUNK) s3r_preprocess_kernel(
+// 4 CTAs per SM (<= 64 registers): the 512 chunks of a 131 072-Gaussian view fit one wave of the 148 SMs.
+__global__ void __launch_bounds__(S3R_CHUNK, 4) s3r_preprocess_kernel(
     s3r_raster_params prm, int tiles_x, int tiles_y, int chunks, float* __restrict__ depths,
     float2* __restrict__ xy_out, float4* __restrict__ conic_opacity, float4* __restrict__ rgb_out,
     uint32_t* __restrict__ rect_out, uint16_t* __restrict__ chunk_hist, int32_t* __restrict__ radii,
-    long long* __restrict__ status, unsigned* __restrict__ counters) {
+    float4* __restrict__ grecords, long long* __restrict__ status, unsigned* __restrict__ counters) {
   extern __shared__ uint32_t s_mask[];  // [tiles][8]
   __shared__ S3rViewConst vc;
   const int view = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x;
   const int tiles = tiles_x * tiles_y;
   const int P = prm.P, W = prm.width, H = prm.height;
 
+  for (int i = tid; i < tiles * 8; i += S3R_CHUNK) s_mask[i] = 0u;
+  s3r_grid_dependency_sync();  // everything above touches only parameters / shared memory
   if (tid < 16) {
     vc.vm[tid] = prm.viewmatrix[view * 16 + tid];
     vc.pm[tid] = prm.projmatrix[view * 16 + tid];
@@ -85,10 +88,9 @@ __global__ void __launch_bounds__(S3R_CHUNK) s3r_preprocess_kernel(
     vc.limx = 1.3f * vc.tanx;
     vc.limy = 1.3f * vc.tany;
   }
-  for (int i = tid; i < tiles * 8; i += S3R_CHUNK) s_mask[i] = 0u;
   if (view == 0 && chunk == 0 && tid < 4) {
     status[tid] = 0;  // R_total, overflow, max_tile_count, reserved — rewritten by the bin stage
-    if (tid < 2) counters[tid] = 0u;
+    counters[tid] = 0u;  // [0] bin_scan ticket, [1] blend work queue, [2] blend exit ticket
   }
   __syncthreads();
 
@@ -210,6 +212,26 @@ __global__ void __launch_bounds__(S3R_CHUNK) s3r_preprocess_kernel(
     conic_opacity[vi] = co;
     rgb_out[vi] = col;
     rect_out[vi] = rect;
+    if (rect != 0u) {
+      // 48-byte blend record of this (view, Gaussian), gathered into sorted order by the tile sort:
+      //   (x, y, A', B' | C', opacity, r, g | b, depth, ex, ey)   A' = -0.5*log2(e)*A ... (s3r_common.cuh)
+      // (ex, ey) = half-extent in pixels of { alpha >= 1/255 }: quadratic form q <= 2 ln(255 o);
+      // |dx| <= sqrt(q C / det), |dy| <= sqrt(q A / det).  Not a parity quantity (a conservative cull box).
+      float ex = -1.f, ey = -1.f;
+      const float q = 2.0f * __logf(255.0f * co.w);
+      const float det = co.x * co.z - co.y * co.y;
+      if (q >= 0.f && det > 0.f) {
+        const float qi = q * 1.0001f / det;
+        ex = sqrtf(qi * co.z) + 0.01f;
+        ey = sqrtf(qi * co.x) + 0.01f;
+      } else if (!(det > 0.f) && q >= 0.f) {
+        ex = ey = 1e30f;  // degenerate conic: never cull
+      }
+      float4* r = grecords + vi * 3;
+      r[0] = make_float4(pix.x, pix.y, co.x * S3R_KA, co.y * S3R_KB);
+      r[1] = make_float4(co.z * S3R_KA, co.w, col.x, col.y);
+      r[2] = make_float4(col.z, depth, ex, ey);
+    }
   }
   __syncthreads();
   uint16_t* hist = chunk_hist + ((size_t)view * chunks + chunk) * tiles;
@@ -224,16 +246,14 @@ __global__ void __launch_bounds__(S3R_CHUNK) s3r_preprocess_kernel(
 int s3r_launch_preprocess(const s3r_raster_params& p, const s3r_raster_layout& L, char* state, int32_t* radii,
                           cudaStream_t st) {
   const size_t smem = (size_t)L.tiles * 8 * sizeof(uint32_t);
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    S3R_CUDA_CHECK(cudaFuncSetAttribute(s3r_preprocess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  static size_t configured[64] = {};
+  int rc = s3r_ensure_dynamic_smem(s3r_preprocess_kernel, smem, configured);
+  if (rc != S3R_OK) return rc;
   dim3 grid(L.chunks, p.n_views);
-  s3r_preprocess_kernel<<<grid, S3R_CHUNK, smem, st>>>(
-      p, L.tiles_x, L.tiles_y, L.chunks, (float*)(state + L.depths), (float2*)(state + L.xy),
-      (float4*)(state + L.conic_opacity), (float4*)(state + L.rgb), (uint32_t*)(state + L.rect),
-      (uint16_t*)(state + L.chunk_hist), radii, (long long*)(state + L.status), (unsigned*)(state + L.counters));
-  S3R_CUDA_CHECK(cudaGetLastError());
+  S3R_CUDA_CHECK(s3r_launch_pdl(
+      s3r_preprocess_kernel, grid, dim3(S3R_CHUNK), smem, st, (s3r_raster_pdl_mask() >> 0) & 1, p, L.tiles_x, L.tiles_y, L.chunks,
+      (float*)(state + L.depths), (float2*)(state + L.xy), (float4*)(state + L.conic_opacity),
+      (float4*)(state + L.rgb), (uint32_t*)(state + L.rect), (uint16_t*)(state + L.chunk_hist), radii,
+      (float4*)(state + L.grecords), (long long*)(state + L.status), (unsigned*)(state + L.counters)));
   return S3R_OK;
 }

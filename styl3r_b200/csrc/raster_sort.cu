@@ -1,15 +1,22 @@
-// Rasterizer stage 4: the remaining radix digits.  After bin_emit every tile owns a contiguous segment of
-// (depth_bits << 32 | gaussian) keys in ascending-gaussian order; one CTA per (view, tile) runs a stable
-// LSD radix sort over the 32 depth bits (4 passes x 8 bits, passes whose digit is uniform are skipped).
-// Segments of up to S3R_SORT_SMEM_CAP keys are sorted entirely in shared memory; larger ones ping-pong
-// between two global-memory buffers with the same code.  The result equals upstream's
-// cub::DeviceRadixSort::SortPairs over ((tile << 32) | depth_bits, gaussian) bit for bit
-// (oracle/raster_oracle.c:s3r_oracle_bin_sort).
+// Rasterizer stage 4: depth order inside every tile.  After bin_emit every tile owns a contiguous segment of
+// (depth_bits << 32 | gaussian) keys in ascending-gaussian order.  Upstream sorts ((tile << 32) | depth_bits, gaussian)
+// with a STABLE radix sort whose input is in ascending-gaussian order, so its result inside a tile is exactly the
+// ascending order of the full 64-bit key (depth_bits, gaussian) - a strict total order (gaussian ids are unique in a
+// tile).  Any correct sort of those 64-bit keys therefore reproduces upstream's order bit for bit
+// (oracle/raster_oracle.c:s3r_oracle_bin_sort).  One CTA per (view, tile), three paths:
 //
-// The epilogue writes point_list (sorted gaussian ids), optionally the 64-bit upstream-format keys, and
-// the 48-byte sorted-gathered blend records (conic pre-scaled to the log2 domain) that the blend kernels stream with TMA bulk copies:
-//   (x, y, conicA, conicB | conicC, opacity, r, g | b, depth, ex, ey)
-// where (ex, ey) is the half-extent in pixels of the region where alpha can reach 1/255.
+//   bucket path  (n <= S3R_SORT_SMEM_CAP, the normal case): ONE most-significant-digit pass - 1024 buckets over the
+//                tile's own depth range [min, max] of the float bits (monotone in depth for the positive depths that
+//                survive the near cull) - followed by an exact rank-by-counting inside each bucket on the full 64-bit
+//                key (buckets hold ~1-3 keys for pixel-aligned scenes; 5 CTA barriers in total instead of ~28 for four
+//                LSD passes).  If some bucket holds more than SORT_MAX_BUCKET keys (many equal / clustered depths with far
+//                outliers) the tile falls back to
+//   LSD path     stable LSD radix sort over the 32 depth bits (4 passes x 8 bits, uniform digits skipped) in shared memory,
+//   global path  the same LSD code ping-ponging between two global buffers for tiles above S3R_SORT_SMEM_CAP keys.
+//
+// The epilogue writes point_list (sorted gaussian ids), the upstream-format 64-bit keys, and gathers the 48-byte blend
+// records that the preprocess stage wrote per Gaussian into sorted order (three 16-byte loads + stores per instance),
+// ready for the blend kernel's TMA bulk copies.
 #include "s3r_common.cuh"
 
 #define SORT_THREADS 256
@@ -95,93 +102,223 @@ __device__ bool radix_pass(const unsigned long long* src, unsigned long long* ds
   return true;
 }
 
-// grid (tiles, n_views)
+#define SORT_NB 1024        // buckets of the most-significant-digit pass
+#define SORT_MAX_BUCKET 48  // above this the rank-by-counting step could go quadratic: use the LSD path
+#define SORT_KPT ((S3R_SORT_SMEM_CAP + SORT_THREADS - 1) / SORT_THREADS)  // keys per thread in the bucket path
+
+__device__ __forceinline__ void write_sorted(uint32_t o, unsigned long long k, unsigned long long tile_hi, size_t vbase,
+                                             const float4* __restrict__ grecords, uint32_t* __restrict__ point_list,
+                                             unsigned long long* __restrict__ point_keys, float4* __restrict__ records) {
+  const uint32_t id = (uint32_t)k, dbits = (uint32_t)(k >> 32);
+  point_list[o] = id;
+  if (point_keys) point_keys[o] = tile_hi | dbits;
+  const float4* g = grecords + (vbase + id) * 3;
+  const float4 a = __ldg(g), b = __ldg(g + 1), c = __ldg(g + 2);
+  float4* r = records + (size_t)o * 3;
+  r[0] = a;
+  r[1] = b;
+  r[2] = c;
+}
+
+// The blend stage's work queue: (view, tile) indices by descending instance count (256-bucket counting sort; the order
+// inside a bucket is arbitrary - it only affects scheduling, never results).  Runs as ONE extra CTA of the tile-sort grid
+// (block (tiles, 0)), i.e. concurrently with the sorts and off the critical path of the chain.
+__device__ void build_work_order(int n, const uint32_t* __restrict__ tile_count, const long long* __restrict__ status,
+                                 uint32_t* __restrict__ work_order, uint32_t* s_bucket /* [256] */, uint32_t* s_w /* [8] */) {
+  static_assert(SORT_THREADS == 256, "one bucket per thread");
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  s_bucket[tid] = 0u;
+  __syncthreads();
+  const uint32_t width = (uint32_t)status[2] / 255u + 1u;  // status[2] = largest tile count (bin_scan)
+  for (int i = tid; i < n; i += SORT_THREADS) atomicAdd(&s_bucket[255u - min(255u, tile_count[i] / width)], 1u);
+  __syncthreads();
+  const uint32_t c = s_bucket[tid];
+  uint32_t incl = c;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += u;
+  }
+  if (lane == 31) s_w[w] = incl;
+  __syncthreads();
+  uint32_t off = incl - c;
+  for (int k = 0; k < w; k++) off += s_w[k];
+  s_bucket[tid] = off;
+  __syncthreads();
+  for (int i = tid; i < n; i += SORT_THREADS)
+    work_order[atomicAdd(&s_bucket[255u - min(255u, tile_count[i] / width)], 1u)] = (uint32_t)i;
+}
+
+// grid (tiles + 1, n_views): block (tiles, 0) builds the blend work queue, blocks (tiles, v > 0) exit
 __global__ void __launch_bounds__(SORT_THREADS) s3r_tile_sort_kernel(
     int P, int tiles, const uint2* __restrict__ ranges, unsigned long long* __restrict__ keys_a,
-    unsigned long long* __restrict__ keys_b, const float2* __restrict__ xy, const float4* __restrict__ conic_opacity,
-    const float4* __restrict__ rgb, uint32_t* __restrict__ point_list, unsigned long long* __restrict__ point_keys,
-    float4* __restrict__ records) {
-  extern __shared__ unsigned long long s_keys[];  // [2][S3R_SORT_SMEM_CAP]
+    unsigned long long* __restrict__ keys_b, const float4* __restrict__ grecords, uint32_t* __restrict__ point_list,
+    unsigned long long* __restrict__ point_keys, float4* __restrict__ records, const uint32_t* __restrict__ tile_count,
+    const long long* __restrict__ status, uint32_t* __restrict__ work_order) {
+  extern __shared__ unsigned long long s_keys[];  // [2][S3R_SORT_SMEM_CAP]; bucket path: [0] = grouped keys, [1] = bucket table
   __shared__ uint32_t s_hist[SORT_WARPS][256];
   __shared__ uint32_t s_scan[SORT_WARPS];
   __shared__ int s_flag;
-  const int view = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x;
+  __shared__ uint32_t s_min, s_max, s_maxb;
+  const int view = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  uint32_t* s_start = reinterpret_cast<uint32_t*>(s_keys + S3R_SORT_SMEM_CAP);  // [SORT_NB + 1]
+  for (int i = tid; i <= SORT_NB; i += SORT_THREADS) s_start[i] = 0u;
+  if (tid == 0) {
+    s_min = 0xffffffffu;
+    s_max = 0u;
+    s_maxb = 0u;
+  }
+  s3r_grid_dependency_sync();
+  if (tile == tiles) {
+    if (view == 0) build_work_order((int)gridDim.y * tiles, tile_count, status, work_order, &s_hist[0][0], s_scan);
+    return;
+  }
   const uint2 rg = ranges[(size_t)view * tiles + tile];
   const uint32_t n = rg.y - rg.x;
   if (n == 0) return;
   unsigned long long* ga = keys_a + rg.x;
   unsigned long long* gb = keys_b + rg.x;
-  const unsigned long long* sorted;
-  if (n <= S3R_SORT_SMEM_CAP) {
-    unsigned long long* cur = s_keys;
-    unsigned long long* nxt = s_keys + S3R_SORT_SMEM_CAP;
-    for (uint32_t i = tid; i < n; i += SORT_THREADS) cur[i] = __ldcs(ga + i);
-    __syncthreads();
-    if (n > 1) {
-#pragma unroll 1
-      for (int pass = 0; pass < 4; pass++) {
-        if (radix_pass<false>(cur, nxt, n, 32 + 8 * pass, s_hist, s_scan, &s_flag)) {
-          unsigned long long* t = cur; cur = nxt; nxt = t;
-        }
-      }
-    }
-    sorted = cur;
-  } else {
-    unsigned long long* cur = ga;
-    unsigned long long* nxt = gb;
-#pragma unroll 1
-    for (int pass = 0; pass < 4; pass++) {
-      if (radix_pass<true>(cur, nxt, n, 32 + 8 * pass, s_hist, s_scan, &s_flag)) {
-        unsigned long long* t = cur; cur = nxt; nxt = t;
-      }
-      __threadfence_block();
-    }
-    sorted = cur;
-  }
-  // epilogue: ids, keys, gathered records
   const size_t vbase = (size_t)view * P;
   const unsigned long long tile_hi = ((unsigned long long)((uint32_t)view * (uint32_t)tiles + (uint32_t)tile)) << 32;
-#pragma unroll 4
-  for (uint32_t i = tid; i < n; i += SORT_THREADS) {
-    const unsigned long long k = (n <= S3R_SORT_SMEM_CAP) ? sorted[i] : __ldcg(sorted + i);
-    const uint32_t id = (uint32_t)k, dbits = (uint32_t)(k >> 32);
-    const size_t o = (size_t)rg.x + i;
-    point_list[o] = id;
-    if (point_keys) point_keys[o] = tile_hi | dbits;
-    const float2 p = __ldg(&xy[vbase + id]);
-    const float4 co = __ldg(&conic_opacity[vbase + id]);
-    const float4 c = __ldg(&rgb[vbase + id]);
-    // half-extent of { alpha >= 1/255 }: quadratic form q <= 2*ln(255*o); |dx| <= sqrt(q*C/det), |dy| <= sqrt(q*A/det)
-    float ex = -1.f, ey = -1.f;
-    const float q = 2.0f * __logf(255.0f * co.w);
-    const float det = co.x * co.z - co.y * co.y;
-    if (q >= 0.f && det > 0.f) {
-      const float qi = q * 1.0001f / det;
-      ex = sqrtf(qi * co.z) + 0.01f;
-      ey = sqrtf(qi * co.x) + 0.01f;
-    } else if (!(det > 0.f) && q >= 0.f) {
-      ex = ey = 1e30f;  // degenerate conic: never cull
+
+  if (n <= S3R_SORT_SMEM_CAP) {
+    // ================= bucket path
+    unsigned long long k[SORT_KPT];
+    uint32_t slot[SORT_KPT];
+    uint32_t mn = 0xffffffffu, mx = 0u;
+#pragma unroll
+    for (int j = 0; j < SORT_KPT; j++) {
+      const uint32_t i = tid + j * SORT_THREADS;
+      k[j] = 0ull;
+      if (i < n) {
+        k[j] = __ldcs(ga + i);
+        const uint32_t hi = (uint32_t)(k[j] >> 32);
+        mn = min(mn, hi);
+        mx = max(mx, hi);
+      }
     }
-    float4* r = records + o * 3;
-    r[0] = make_float4(p.x, p.y, co.x * S3R_KA, co.y * S3R_KB);   // log2-domain conic (s3r_common.cuh)
-    r[1] = make_float4(co.z * S3R_KA, co.w, c.x, c.y);
-    r[2] = make_float4(c.z, __uint_as_float(dbits), ex, ey);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+      mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    __syncthreads();  // s_start zeroed, s_min / s_max initialised
+    if (lane == 0) {
+      atomicMin(&s_min, mn);
+      atomicMax(&s_max, mx);
+    }
+    __syncthreads();
+    const uint32_t lo = s_min, span = s_max - lo;
+    // digit = (depth_bits - lo) >> shift < SORT_NB, monotone in depth_bits
+    const int shift = max(0, (32 - __clz(span)) - 10);
+    static_assert(SORT_NB == 1024, "shift assumes 10 digit bits");
+#pragma unroll
+    for (int j = 0; j < SORT_KPT; j++) {
+      const uint32_t i = tid + j * SORT_THREADS;
+      slot[j] = 0u;
+      if (i < n) slot[j] = atomicAdd(&s_start[(((uint32_t)(k[j] >> 32)) - lo) >> shift], 1u);
+    }
+    __syncthreads();
+    // exclusive scan of the SORT_NB counts (4 per thread) -> bucket starts, and the largest bucket
+    {
+      uint32_t c[SORT_NB / SORT_THREADS];
+      uint32_t sum = 0, big = 0;
+#pragma unroll
+      for (int q = 0; q < SORT_NB / SORT_THREADS; q++) {
+        c[q] = s_start[tid * (SORT_NB / SORT_THREADS) + q];
+        sum += c[q];
+        big = max(big, c[q]);
+      }
+      uint32_t incl = sum;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += u;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) big = max(big, __shfl_xor_sync(0xffffffffu, big, o));
+      if (lane == 31) s_scan[w] = incl;
+      if (lane == 0) atomicMax(&s_maxb, big);
+      __syncthreads();
+      uint32_t run = incl - sum;
+#pragma unroll
+      for (int q = 0; q < SORT_WARPS; q++)
+        if (q < w) run += s_scan[q];
+#pragma unroll
+      for (int q = 0; q < SORT_NB / SORT_THREADS; q++) {
+        s_start[tid * (SORT_NB / SORT_THREADS) + q] = run;
+        run += c[q];
+      }
+      if (tid == SORT_THREADS - 1) s_start[SORT_NB] = run;  // = n
+    }
+    __syncthreads();
+    if (s_maxb <= SORT_MAX_BUCKET) {
+      // scatter into bucket-grouped order (order inside a bucket is arbitrary: the ranks below fix it)
+#pragma unroll
+      for (int j = 0; j < SORT_KPT; j++) {
+        const uint32_t i = tid + j * SORT_THREADS;
+        if (i < n) s_keys[s_start[(((uint32_t)(k[j] >> 32)) - lo) >> shift] + slot[j]] = k[j];
+      }
+      __syncthreads();
+      // exact rank inside the bucket on the full (depth_bits, gaussian) key, then straight to the outputs (a separate,
+      // fully unrolled gather phase with 12 loads in flight per thread was measured slower: 15.3 vs 14.4 us)
+#pragma unroll 2
+      for (uint32_t p = tid; p < n; p += SORT_THREADS) {
+        const unsigned long long key = s_keys[p];
+        const uint32_t d = (((uint32_t)(key >> 32)) - lo) >> shift;
+        const uint32_t b0 = s_start[d], b1 = s_start[d + 1];
+        uint32_t rank = 0;
+        for (uint32_t q = b0; q < b1; q++) rank += (s_keys[q] < key) ? 1u : 0u;
+        write_sorted(rg.x + b0 + rank, key, tile_hi, vbase, grecords, point_list, point_keys, records);
+      }
+      return;
+    }
+    // ================= LSD path (rare): stable radix passes in shared memory, keys re-staged from registers
+    __syncthreads();
+    unsigned long long* cur = s_keys;
+    unsigned long long* nxt = s_keys + S3R_SORT_SMEM_CAP;
+#pragma unroll
+    for (int j = 0; j < SORT_KPT; j++) {
+      const uint32_t i = tid + j * SORT_THREADS;
+      if (i < n) cur[i] = k[j];
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int pass = 0; pass < 4; pass++) {
+      if (radix_pass<false>(cur, nxt, n, 32 + 8 * pass, s_hist, s_scan, &s_flag)) {
+        unsigned long long* t = cur; cur = nxt; nxt = t;
+      }
+    }
+    for (uint32_t i = tid; i < n; i += SORT_THREADS)
+      write_sorted(rg.x + i, cur[i], tile_hi, vbase, grecords, point_list, point_keys, records);
+    return;
   }
+  // ================= global path: tiles above the shared-memory capacity
+  unsigned long long* cur = ga;
+  unsigned long long* nxt = gb;
+#pragma unroll 1
+  for (int pass = 0; pass < 4; pass++) {
+    if (radix_pass<true>(cur, nxt, n, 32 + 8 * pass, s_hist, s_scan, &s_flag)) {
+      unsigned long long* t = cur; cur = nxt; nxt = t;
+    }
+    __threadfence_block();
+  }
+  for (uint32_t i = tid; i < n; i += SORT_THREADS)
+    write_sorted(rg.x + i, __ldcg(cur + i), tile_hi, vbase, grecords, point_list, point_keys, records);
 }
 
 int s3r_launch_sort(const s3r_raster_params& p, const s3r_raster_layout& L, char* state, cudaStream_t st) {
   const size_t smem = 2 * (size_t)S3R_SORT_SMEM_CAP * sizeof(unsigned long long);
-  static bool configured = false;
-  if (!configured) {
-    S3R_CUDA_CHECK(cudaFuncSetAttribute(s3r_tile_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
-  }
-  dim3 grid(L.tiles, p.n_views);
-  s3r_tile_sort_kernel<<<grid, SORT_THREADS, smem, st>>>(
-      p.P, L.tiles, (const uint2*)(state + L.ranges), (unsigned long long*)(state + L.keys_unsorted),
-      (unsigned long long*)(state + L.keys_tmp), (const float2*)(state + L.xy),
-      (const float4*)(state + L.conic_opacity), (const float4*)(state + L.rgb), (uint32_t*)(state + L.point_list),
-      (unsigned long long*)(state + L.point_keys), (float4*)(state + L.records));
-  S3R_CUDA_CHECK(cudaGetLastError());
+  static_assert((size_t)S3R_SORT_SMEM_CAP * 8 >= (SORT_NB + 1) * 4, "bucket table lives in the second key buffer");
+  static size_t configured[64] = {};
+  int rc = s3r_ensure_dynamic_smem(s3r_tile_sort_kernel, smem, configured);
+  if (rc != S3R_OK) return rc;
+  dim3 grid(L.tiles + 1, p.n_views);
+  S3R_CUDA_CHECK(s3r_launch_pdl(s3r_tile_sort_kernel, grid, dim3(SORT_THREADS), smem, st, (s3r_raster_pdl_mask() >> 3) & 1, p.P, L.tiles,
+                                (const uint2*)(state + L.ranges), (unsigned long long*)(state + L.keys_unsorted),
+                                (unsigned long long*)(state + L.keys_tmp), (const float4*)(state + L.grecords),
+                                (uint32_t*)(state + L.point_list), (unsigned long long*)(state + L.point_keys),
+                                (float4*)(state + L.records), (const uint32_t*)(state + L.tile_count),
+                                (const long long*)(state + L.status), (uint32_t*)(state + L.work_order)));
   return S3R_OK;
 }

@@ -52,5 +52,55 @@ int s3r_launch_sort(const s3r_raster_params& p, const s3r_raster_layout& L, char
 int s3r_launch_blend(const s3r_raster_params& p, const s3r_raster_outputs& o, const s3r_raster_layout& L,
                      char* state, cudaStream_t st);
 
-// Programmatic dependent launch switch shared by the encoder kernels (S3R_TUNE_PDL; defined in gemm_tcgen05.cu)
+// Programmatic dependent launch switch shared by all kernels (S3R_TUNE_PDL; defined in gemm_tcgen05.cu)
 int s3r_pdl_enabled();
+int& s3r_blend_only_tile();  // S3R_TUNE_BLEND_ONLY_TILE (defined in raster_blend.cu)
+
+// Launch with the programmatic-stream-serialization attribute: the grid may become resident while the previous kernel
+// of the stream drains; the kernel runs its global-memory-free prologue (shared-memory zeroing, mbarrier init), then
+// s3r_grid_dependency_sync() blocks until the previous kernel has completed and flushed.  Captured as a programmatic
+// edge by CUDA graphs.  Without the attribute the device-side instructions are no-ops.
+int& s3r_raster_pdl_mask();  // S3R_TUNE_RASTER_PDL: bit k = stage k (preprocess, scan, emit, sort, blend) launches with PDL
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t s3r_launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                         bool pdl, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  int na = 0;
+  if (pdl && s3r_pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    na++;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
+#ifdef __CUDACC__
+__device__ __forceinline__ void s3r_grid_dependency_sync() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+#endif
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute: remember what was configured per device
+// (a process-wide flag would leave a second GPU at the 48 KB default).
+template <typename F>
+static inline int s3r_ensure_dynamic_smem(F* func, size_t bytes, size_t (&configured)[64]) {
+  if (bytes <= 48 * 1024) return S3R_OK;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return S3R_ERR_CUDA;
+  dev &= 63;
+  if (bytes > configured[dev]) {
+    if (cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess)
+      return S3R_ERR_CUDA;
+    configured[dev] = bytes;
+  }
+  return S3R_OK;
+}
