@@ -9,8 +9,11 @@ alpha blend.  A step is one pass of that path over one scene; the encoder is not
 SURVEY §8 rows a11-a14).  Steps rotate over several resident scenes so that consecutive steps do not reuse L2.
 
   value      views/s with inputs resident in HBM (CUDA-graph replay of the kernel chain), max-over-ranks time
-  e2e        same metric through the public `render_cuda` call with pinned HOST buffers: H2D of the Gaussians and
-             cameras and D2H of the image inside the timed region
+  e2e        same metric through the serving API `RenderSession.run()` with pinned HOST buffers: H2D of the Gaussians and
+             cameras and D2H of the image inside the timed region (`e2e_render_cuda`: the same request through the
+             reference-signature eager `render_cuda` call, for comparison)
+  cfg2_full / cfg3 / cfg4 / cfg5 / encoder_comparator / pose_align: the other BASELINE.json configurations and
+             comparators (bench_legs.py), reported as supplementary keys of the same JSON line
   roofline   blend kernel: algorithmic bytes (40 R + 20 HW + 8 T) / CUDA-event time of that kernel, vs measured HBM peak
   cpu_baseline / --impl reference: the CPU oracle (oracle/raster_oracle.c, a port: the upstream rasterizer is
              un-vendored and has no CPU path) on all host threads.
@@ -460,6 +463,59 @@ def run_ours(args):
         except Exception as e:
             standin = {"error": repr(e)[:200]}
 
+    # ---- supplementary legs: the other BASELINE.json configurations (bench_legs.py); every leg is bounded
+    import bench_legs as bl
+    extra = {}
+
+    def leg(name, fn, *a, **k):
+        if args.legs != "all" and name not in args.legs.split(","):
+            return None
+        try:
+            t_leg = time.perf_counter()
+            r = fn(*a, **k)
+            r["leg_wall_s"] = round(time.perf_counter() - t_leg, 1)
+            return r
+        except Exception as e:  # supplementary only: never lose the headline line
+            import traceback
+            return {"error": repr(e)[:300], "trace": traceback.format_exc()[-600:]}
+
+    if args.legs != "none":
+        del graphs, blend_graphs
+        for s_ in slots[1:]:
+            s_["plan"] = None
+        torch.cuda.empty_cache()
+        if rank == 0 and world == 1:
+            extra["e2e_render_cuda"] = leg("e2e_render_cuda", bl.e2e_render_cuda, dev, host)
+            extra["pose_align"] = leg("pose_align", bl.pose_align_leg, dev)
+            extra["cfg2_full"] = leg("cfg2_full", bl.full_pipeline, dev, 1, 2, 1, 20,
+                                     "cfg2 re10k_2v forward: 2x256x256 in, 131072 Gaussians, 1 target view, 1 scene per pass")
+            extra["encoder_comparator"] = leg("encoder_comparator", bl.encoder_comparator, dev)
+        # cfg3 / cfg4 / cfg5 run on every rank (cfg4 = cfg3's shape per GPU; cfg5 = DDP training step)
+        c3 = leg("cfg3", bl.full_pipeline, dev, 4, 4, 6, 5,
+                 "cfg3 re10k_dl3dv_4v forward: 4 scenes x 4x256x256 in, 262144 Gaussians per scene, 6 target views each (24 views per pass)")
+        if c3 is not None and "error" not in c3 and dist is not None:
+            tms = torch.tensor([c3["ms_per_pass"]], device=dev)
+            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+            c3["ms_per_pass_max_over_ranks"] = float(tms.item())
+        if c3 is not None:
+            extra["cfg3"] = c3
+            if "error" not in c3:
+                ms3 = c3.get("ms_per_pass_max_over_ranks", c3["ms_per_pass"])
+                extra["cfg4"] = {"workload": f"batched stylized inference: {4 * world} scenes x 6 target views, scene-sharded over {world} GPU(s) "
+                                             "(4 scenes = 24 views per GPU per pass, encoder included)", "n_gpus": world,
+                                 "views_per_s": world * 24 / (ms3 * 1e-3), "ms_per_pass": ms3}
+        barrier()
+        c5 = leg("cfg5", bl.train_step_leg, dev, args.train_batch, 3, world)
+        if c5 is not None and "error" not in c5 and dist is not None:
+            tms = torch.tensor([c5["ms_per_step"]], device=dev)
+            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+            c5["ms_per_step"] = float(tms.item())
+        if c5 is not None:
+            if "error" not in c5:
+                c5["scenes_per_s"] = world * c5["batch_per_gpu"] / (c5["ms_per_step"] * 1e-3)
+                c5["n_gpus"] = world
+            extra["cfg5"] = c5
+
     if rank == 0:
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": "views/s", "n_gpus": world, "steps": K, "warmup": Wm,
@@ -486,6 +542,7 @@ def run_ours(args):
             "cpu_baseline": cb,
             "encoder": enc_info,
             "upstream_style_standin": standin,
+            **{k: v for k, v in extra.items() if v is not None},
         }))
     if dist is not None:
         dist.destroy_process_group()
@@ -504,6 +561,9 @@ def main():
     ap.add_argument("--no-standin", action="store_true", help="skip the upstream-style GPU comparator leg")
     ap.add_argument("--with-encoder", action="store_true", help="(default now) time the encoder as a supplementary key")
     ap.add_argument("--no-encoder", action="store_true", help="skip the supplementary encoder leg")
+    ap.add_argument("--legs", default="all", help="supplementary legs (bench_legs.py): all | none | comma list of "
+                    "e2e_render_cuda,pose_align,cfg2_full,encoder_comparator,cfg3,cfg5")
+    ap.add_argument("--train-batch", type=int, default=10, help="scenes per GPU of the cfg5 training-step leg")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

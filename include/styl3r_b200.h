@@ -201,6 +201,7 @@ int s3r_rope2d(void* tokens, const int64_t* pos, int32_t B, int32_t N, int32_t H
 #define S3R_EPI_OUT_F32 8
 #define S3R_EPI_ROPE 16
 #define S3R_EPI_RELU 32
+#define S3R_EPI_DGELU 128 /* C = acc * gelu'(aux): backward of a fused GELU, aux = the saved pre-activation [M, N] bf16 */
 #define S3R_EPI_PDL 64 /* internal: set by the launcher when programmatic dependent launch is enabled (S3R_TUNE_PDL) */
 int s3r_gemm_bf16(const void* A, const void* W, const void* bias, const void* residual, void* C, int32_t M,
                   int32_t N, int32_t K, int32_t lda, int32_t ldw, int32_t ldc, int32_t ldr, int32_t flags,
@@ -219,6 +220,18 @@ int s3r_gemm_bf16_rope(const void* A, const void* W, const void* bias, const voi
  * split-K for grids smaller than the machine — first 16 KiB are self-resetting tile counters, the rest holds fp32
  * partial tiles.  NULL => never split. */
 int s3r_rope_table(float* table /* [(max_pos+1)*16*2] */, int32_t max_pos, float base, void* stream);
+
+/* The same GEMM with either operand MN-major, i.e. handed over as stored by the forward pass - the backward of
+ * nn.Linear (autograd of blocks.py:61-82,97-134; cuBLAS in the reference) without transposed copies:
+ *   C[M,N] = act( opA . opB^T + bias ) (+ aux | * gelu'(aux))
+ *   a_mn_major = 0: A is [M, K] row-major (lda);  1: A is [K, M] row-major (lda)
+ *   b_mn_major = 0: B is [N, K] row-major (ldb);  1: B is [K, N] row-major (ldb)
+ * dgrad: dX = dY . W        -> A = dY [M, Nout] (0), B = W [Nout, Kin] (1), K = Nout, N = Kin
+ * wgrad: dW = dY^T . X      -> A = dY [tokens, Nout] (1), B = X [tokens, Kin] (1), M = Nout, N = Kin, K = tokens
+ * flags: BIAS | GELU | RELU | OUT_F32 | RESIDUAL (aux added) | DGELU (multiply by gelu'(aux), aux = pre-activation). */
+int s3r_gemm_bf16_majors(const void* A, const void* B, const void* bias, const void* aux, void* C, int32_t M, int32_t N,
+                         int32_t K, int32_t lda, int32_t ldb, int32_t ldc, int32_t ldaux, int32_t flags,
+                         int32_t a_mn_major, int32_t b_mn_major, void* stream);
 
 /* ------------------------------------------------------------------------
  * Stride-1 "same" 2-D convolution as an implicit GEMM on tcgen05/TMEM - the

@@ -97,9 +97,25 @@ __device__ __forceinline__ uint64_t g_make_desc(const void* smem_ptr) {
   d |= (uint64_t)2 << 61;
   return d;
 }
-// kind::f16 instruction descriptor: c=F32 (1<<4), a=b=BF16 (1<<7, 1<<10), both K-major, N>>3 at [17,23), M>>4 at [24,29)
-__device__ __forceinline__ uint32_t g_make_idesc(int m, int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+// MN-major operand (the contraction index is the slow one in global memory: X^T, dY^T, W^T - the backward GEMMs) under
+// SWIZZLE_128B: the tile is stored as [MN/64 atoms][64 contraction rows][64 elements = 128 B]; canonical layout
+// ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units (cute::UMMA make_umma_desc<Major::MN>): LBO = byte offset between
+// two 64-element MN atoms = 64 rows x 128 B, SBO = byte offset between two 8-row contraction groups = 1024 B.
+__device__ __forceinline__ uint64_t g_make_desc_mn(const void* smem_ptr) {
+  const uint32_t addr = g_smem_u32(smem_ptr);
+  uint64_t d = 0;
+  d |= (uint64_t)((addr >> 4) & 0x3FFF);
+  d |= (uint64_t)(8192 >> 4) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// kind::f16 instruction descriptor: c=F32 (1<<4), a=b=BF16 (1<<7, 1<<10), a/b major at bits 15/16 (0 = K-major,
+// 1 = MN-major), N>>3 at [17,23), M>>4 at [24,29)
+__device__ __forceinline__ uint32_t g_make_idesc(int m, int n, int a_mn = 0, int b_mn = 0) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(n >> 3) << 17) |
+         ((uint32_t)(m >> 4) << 24);
 }
 __device__ __forceinline__ void g_umma(uint32_t tmem_c, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
   asm volatile(
@@ -167,7 +183,9 @@ struct ConvArgs {
 // the M = 257/514-row GEMMs of the batch-1 encoder are bound by exactly that traffic (every SM pulls ~45-64 B/cycle).
 // Ring slots are released cluster-wide: a CTA's `empty` barrier collects one tcgen05.commit from every CTA it
 // multicasts into (its cluster row and column, CM + CN - 1 CTAs).
-template <int BN, int STAGES_, bool kConv, int CM = 1, int CN = 1>
+// MAJ: bit 0 = A is MN-major (given as [K, M] row-major), bit 1 = B is MN-major (given as [K, N] row-major) - the
+// dgrad (B = W as stored) and wgrad (A = dY, B = X as stored) GEMMs of the encoder's backward, no transposed copies.
+template <int BN, int STAGES_, bool kConv, int CM = 1, int CN = 1, int MAJ = 0>
 __global__ void __launch_bounds__(GEMM_THREADS, (STAGES_ * (GEMM_BM + BN) * GEMM_BK * 2 <= 100 * 1024) ? 2 : 1)
 s3r_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const __nv_bfloat16* __restrict__ bias, const __nv_bfloat16* __restrict__ residual, void* __restrict__ Cout,
@@ -254,10 +272,18 @@ s3r_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         } else if (CN > 1) {  // my 128/CN-row slice of the A tile, to every CTA that shares this M tile
           constexpr int AR = GEMM_BM / CN;
           g_tma_load_2d_mc(a_dst + yr * AR * 128, &tmA, (kb0 + kb) * GEMM_BK, m0 + yr * AR, &full[s], mask_a);
+        } else if (MAJ & 1) {  // two 64-row atoms of the MN-major A tile: box = 64 contraction rows x 64 M elements
+#pragma unroll
+          for (int h = 0; h < GEMM_BM / 64; h++)
+            g_tma_load_2d(a_dst + h * 8192, &tmA, m0 + h * 64, (kb0 + kb) * GEMM_BK, &full[s]);
         } else {
           g_tma_load_2d(a_dst, &tmA, (kb0 + kb) * GEMM_BK, m0, &full[s]);
         }
-        if (CM > 1) {         // my BN/CM-row slice of the W tile, to every CTA that shares this N tile
+        if (MAJ & 2) {
+#pragma unroll
+          for (int h = 0; h < BN / 64; h++)
+            g_tma_load_2d(b_dst + h * 8192, &tmB, n0 + h * 64, (kb0 + kb) * GEMM_BK, &full[s]);
+        } else if (CM > 1) {         // my BN/CM-row slice of the W tile, to every CTA that shares this N tile
           constexpr int BR = BN / CM;
           g_tma_load_2d_mc(b_dst + xr * BR * 128, &tmB, (kb0 + kb) * GEMM_BK, n0 + xr * BR, &full[s], mask_b);
         } else {
@@ -267,16 +293,20 @@ s3r_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc = g_make_idesc(GEMM_BM, BN);
+      const uint32_t idesc = g_make_idesc(GEMM_BM, BN, MAJ & 1, (MAJ >> 1) & 1);
       for (int kb = 0; kb < num_kb; kb++) {
         const int s = kb % GEMM_STAGES;
         g_mbar_wait(&full[s], (kb / GEMM_STAGES) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint64_t adesc = g_make_desc(smem + s * S::STAGE_BYTES);
-        const uint64_t bdesc = g_make_desc(smem + s * S::STAGE_BYTES + S::A_BYTES);
+        const uint64_t adesc = (MAJ & 1) ? g_make_desc_mn(smem + s * S::STAGE_BYTES) : g_make_desc(smem + s * S::STAGE_BYTES);
+        const uint64_t bdesc = (MAJ & 2) ? g_make_desc_mn(smem + s * S::STAGE_BYTES + S::A_BYTES)
+                                         : g_make_desc(smem + s * S::STAGE_BYTES + S::A_BYTES);
+        // one k-step = 16 contraction elements: K-major +32 B inside the 128-B swizzle atom (+2 in >>4 units);
+        // MN-major +16 rows of 128 B (+128)
+        constexpr int AK = (MAJ & 1) ? 128 : 2, BK_ = (MAJ & 2) ? 128 : 2;
 #pragma unroll
-        for (int k = 0; k < GEMM_BK / 16; k++)  // advance 16 bf16 = 32 B inside the 128-B swizzle atom: +2 in >>4 units
-          g_umma(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+        for (int k = 0; k < GEMM_BK / 16; k++)
+          g_umma(tmem_base, adesc + (uint64_t)(AK * k), bdesc + (uint64_t)(BK_ * k), idesc, (kb | k) ? 1u : 0u);
         // frees the ring slot once these MMAs have read it (in every CTA that multicasts into it)
         if (kCluster) g_umma_commit_mc(&empty[s], mask_rel);
         else g_umma_commit(&empty[s]);
@@ -363,6 +393,18 @@ s3r_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       if (relu) {
 #pragma unroll
         for (int j = 0; j < 4; j++) f[j] = fmaxf(f[j], 0.0f);
+      }
+      if ((flags & S3R_EPI_DGELU) && row < M && col < N) {
+        // backward of y = gelu(h): f = dL/dy (accumulator) -> dL/dh = f * gelu'(h), h = pre-activation in `residual`
+        const __nv_bfloat16* hp = residual + (size_t)row * ldr + col;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          if (col + j < N) {
+            const float h = __bfloat162float(hp[j]);
+            const float cdf = 0.5f * (1.0f + erff(h * 0.70710678118654752f));
+            f[j] *= cdf + h * 0.39894228040143268f * __expf(-0.5f * h * h);
+          }
+        }
       }
       if (row < M && col < N) {
         if (has_res) {
@@ -514,13 +556,13 @@ static int make_map(CUtensorMap* map, const void* ptr, int rows, int cols, int l
   return r == CUDA_SUCCESS ? S3R_OK : S3R_ERR_CUDA;
 }
 
-template <int BN, int STAGES_, bool kConv = false, int CM = 1, int CN = 1>
+template <int BN, int STAGES_, bool kConv = false, int CM = 1, int CN = 1, int MAJ = 0>
 static int launch_gemm(const CUtensorMap& a, const CUtensorMap& b, const void* bias, const void* residual, void* C, int M,
                        int N, int K, int ldc, int ldr, int flags, const RopeArgs& rope, int splits, float* ws, unsigned* counters,
                        cudaStream_t st, const ConvArgs& conv = ConvArgs{}) {
   static bool configured = false;
   const int smem = GemmSmem<BN, STAGES_>::TOTAL;
-  auto kern = s3r_gemm_bf16_kernel<BN, STAGES_, kConv, CM, CN>;
+  auto kern = s3r_gemm_bf16_kernel<BN, STAGES_, kConv, CM, CN, MAJ>;
   if (!configured) {
     S3R_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
@@ -671,6 +713,37 @@ extern "C" int s3r_gemm_bf16(const void* A, const void* W, const void* bias, con
   if (flags & S3R_EPI_ROPE) return S3R_ERR_INVALID_ARG;
   return s3r_gemm_bf16_rope(A, W, bias, residual, C, M, N, K, lda, ldw, ldc, ldr, flags, nullptr, nullptr, 0, 0, nullptr, 0,
                             stream);
+}
+
+// Backward GEMMs of nn.Linear on the same pipeline, operands in the layouts the forward left them in (no transposes):
+//   dgrad  dX[M,Kin]    = dY[M,Nout] . W[Nout,Kin]          A K-major, B MN-major (W is [contraction, N] row-major)
+//   wgrad  dW[Nout,Kin] = dY[M,Nout]^T . X[M,Kin]           A and B MN-major (both are [contraction, MN] row-major)
+extern "C" int s3r_gemm_bf16_majors(const void* A, const void* B, const void* bias, const void* aux, void* C, int32_t M,
+                                    int32_t N, int32_t K, int32_t lda, int32_t ldb, int32_t ldc, int32_t ldaux,
+                                    int32_t flags, int32_t a_mn_major, int32_t b_mn_major, void* stream) {
+  if (M < 0 || N <= 0 || K <= 0) return S3R_ERR_INVALID_ARG;
+  if (M == 0) return S3R_OK;
+  if (!A || !B || !C) return S3R_ERR_INVALID_ARG;
+  if (flags & S3R_EPI_ROPE) return S3R_ERR_INVALID_ARG;
+  if ((flags & S3R_EPI_BIAS) && !bias) return S3R_ERR_INVALID_ARG;
+  if ((flags & (S3R_EPI_RESIDUAL | S3R_EPI_DGELU)) && !aux) return S3R_ERR_INVALID_ARG;
+  if ((flags & S3R_EPI_RESIDUAL) && (flags & S3R_EPI_DGELU)) return S3R_ERR_INVALID_ARG;  // one aux operand
+  if (lda % 8 || ldb % 8 || ldc % 8 || ((flags & (S3R_EPI_RESIDUAL | S3R_EPI_DGELU)) && ldaux % 8)) return S3R_ERR_UNSUPPORTED;
+  if (((uintptr_t)A | (uintptr_t)B | (uintptr_t)C) & 15) return S3R_ERR_UNSUPPORTED;
+  if (!a_mn_major && !b_mn_major)
+    return s3r_gemm_bf16_rope(A, B, bias, aux, C, M, N, K, lda, ldb, ldc, ldaux, flags, nullptr, nullptr, 0, 0, nullptr, 0, stream);
+  CUtensorMap ta, tb;
+  int rc;
+  // K-major operand: rows = M (or N), inner = K, box 64 x 128; MN-major operand: rows = K, inner = M (or N), box 64 x 64
+  if ((rc = a_mn_major ? make_map(&ta, A, K, M, lda, 64) : make_map(&ta, A, M, K, lda, GEMM_BM)) != S3R_OK) return rc;
+  if ((rc = b_mn_major ? make_map(&tb, B, K, N, ldb, 64) : make_map(&tb, B, N, K, ldb, 128)) != S3R_OK) return rc;
+  RopeArgs rope{nullptr, nullptr, 0, 0};
+  cudaStream_t st = (cudaStream_t)stream;
+  if (a_mn_major && b_mn_major)
+    return launch_gemm<128, 3, false, 1, 1, 3>(ta, tb, bias, aux, C, M, N, K, ldc, ldaux, flags, rope, 1, nullptr, nullptr, st);
+  if (a_mn_major)
+    return launch_gemm<128, 3, false, 1, 1, 1>(ta, tb, bias, aux, C, M, N, K, ldc, ldaux, flags, rope, 1, nullptr, nullptr, st);
+  return launch_gemm<128, 3, false, 1, 1, 2>(ta, tb, bias, aux, C, M, N, K, ldc, ldaux, flags, rope, 1, nullptr, nullptr, st);
 }
 
 // ---------------------------------------------------------------------------------------------------------- conv2d

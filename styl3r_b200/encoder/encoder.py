@@ -434,17 +434,18 @@ class GraphedEncoder:
 
     def __call__(self, context: dict, style: dict) -> Gaussians:
         img, K, sty = context["image"], context["intrinsics"], style["image"]
-        key = (tuple(img.shape), tuple(sty.shape), img.device)
+        dev = next(self.encoder.parameters()).device  # inputs may live in (pinned) host memory: they are copied in
+        key = (tuple(img.shape), tuple(sty.shape))
         if key not in self._graphs:
-            static = dict(img=img.clone(), K=K.clone(), sty=sty.clone())
+            static = dict(img=img.to(dev, copy=True), K=K.to(dev, copy=True), sty=sty.to(dev, copy=True))
             ctx, st = {"image": static["img"], "intrinsics": static["K"]}, {"image": static["sty"]}
-            side = torch.cuda.Stream(device=img.device)
-            side.wait_stream(torch.cuda.current_stream(img.device))
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
             with torch.cuda.stream(side):
                 for _ in range(2):  # warm-up outside capture: lazy inits, cuDNN/cuBLAS plan selection, index caches
                     self._run(ctx, st)
-            torch.cuda.current_stream(img.device).wait_stream(side)
-            torch.cuda.synchronize(img.device)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize(dev)
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
                 out = self._run(ctx, st)

@@ -16,6 +16,7 @@ from torch import Tensor, nn
 
 from .. import gemm as _gemm
 from ..curope import cuRoPE2D_func
+from .. import ops as _ops
 from ..ops import memory_efficient_attention
 from ..streams import fork_join
 
@@ -29,7 +30,8 @@ def _rope(t_bnhd: Tensor, pos: Tensor, base: float) -> Tensor:
 
 def _fast(layer: nn.Linear, x: Tensor) -> bool:
     """bf16 inference layout (to_inference) without autograd: the tcgen05 kernels are used."""
-    return x.dtype == torch.bfloat16 and layer.weight.dtype == torch.bfloat16 and not torch.is_grad_enabled()
+    return (x.dtype == torch.bfloat16 and layer.weight.dtype == torch.bfloat16 and not torch.is_grad_enabled()
+            and not _ops.FORCE_LIBRARY)
 
 
 def _lin(layer: nn.Linear, x: Tensor, residual: Tensor | None = None, gelu: bool = False) -> Tensor:
@@ -47,7 +49,8 @@ def _ln(norm: nn.LayerNorm, x: Tensor) -> Tensor:
     """LayerNorm: bf16 inference layout -> `s3r_layernorm_bf16` (one warp per row, fp32 statistics, launched with
     programmatic dependent launch); otherwise the torch module."""
     C_ = x.shape[-1]
-    if (x.dtype == torch.bfloat16 and norm.weight.dtype == torch.bfloat16 and not torch.is_grad_enabled() and x.is_cuda
+    if (not _ops.FORCE_LIBRARY and x.dtype == torch.bfloat16 and norm.weight.dtype == torch.bfloat16
+            and not torch.is_grad_enabled() and x.is_cuda
             and C_ % 256 == 0 and C_ <= 2048):
         import ctypes as C
         from .. import _lib
@@ -213,7 +216,7 @@ class PatchEmbed(nn.Module):
         ys, xs = torch.meshgrid(torch.arange(gh, device=img.device), torch.arange(gw, device=img.device), indexing="ij")
         pos = torch.stack((ys.reshape(-1), xs.reshape(-1)), dim=-1)[None].expand(B, -1, -1).contiguous()
         w = self.proj.weight
-        if img.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and not torch.is_grad_enabled():
+        if img.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and not torch.is_grad_enabled() and not _ops.FORCE_LIBRARY:
             # kernel == stride: the convolution is a GEMM over non-overlapping patches, columns ordered (c, kh, kw)
             # like weight.flatten(1) - one gather copy + the tcgen05 GEMM instead of a cuDNN conv with layout transposes
             cols = img.reshape(B, -1, gh, ph, gw, pw).permute(0, 2, 4, 1, 3, 5).reshape(B * gh * gw, -1)

@@ -104,3 +104,52 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] =
                                              C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)),
                "s3r_gemm_bf16")
     return out.reshape(*lead, N)
+
+
+EPI_DGELU = 128
+
+
+def gemm_majors(a: torch.Tensor, b: torch.Tensor, M: int, N: int, K: int, a_mn_major: bool, b_mn_major: bool,
+                bias: Optional[torch.Tensor] = None, aux: Optional[torch.Tensor] = None, dgelu: bool = False,
+                out_dtype: torch.dtype = torch.bfloat16) -> torch.Tensor:
+    """C[M,N] = opA . opB^T (+ bias) (+ aux | * gelu'(aux)) with either operand MN-major (`s3r_gemm_bf16_majors`):
+    a is [M,K] (a_mn_major False) or [K,M] (True); b is [N,K] or [K,N].  2-D bf16 tensors with unit inner stride."""
+    if a.dtype != torch.bfloat16 or b.dtype != torch.bfloat16 or a.device.type != "cuda":
+        raise _lib.S3RError("gemm_majors expects bf16 CUDA operands")
+    if a.stride(1) != 1:
+        a = a.contiguous()
+    if b.stride(1) != 1:
+        b = b.contiguous()
+    out = torch.empty((M, N), dtype=out_dtype, device=a.device)
+    flags = 0
+    bp = xp = None
+    ldx = 0
+    if bias is not None:
+        flags |= EPI_BIAS
+        bias = bias if bias.dtype == torch.bfloat16 else bias.to(torch.bfloat16)
+        bp = C.c_void_p(bias.data_ptr())
+    if aux is not None:
+        flags |= EPI_DGELU if dgelu else EPI_RESIDUAL
+        if aux.stride(1) != 1 or aux.dtype != torch.bfloat16:
+            aux = aux.to(torch.bfloat16).contiguous()
+        xp, ldx = C.c_void_p(aux.data_ptr()), aux.stride(0)
+    if out_dtype == torch.float32:
+        flags |= EPI_OUT_F32
+    _lib.check(_lib.lib().s3r_gemm_bf16_majors(C.c_void_p(a.data_ptr()), C.c_void_p(b.data_ptr()), bp, xp,
+                                               C.c_void_p(out.data_ptr()), M, N, K, a.stride(0), b.stride(0), out.stride(0),
+                                               ldx, flags, int(a_mn_major), int(b_mn_major),
+                                               C.c_void_p(torch.cuda.current_stream(a.device).cuda_stream)),
+               "s3r_gemm_bf16_majors")
+    return out
+
+
+def linear_dgrad(dy: torch.Tensor, weight: torch.Tensor, pre_gelu: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """dX[M,Kin] = dY[M,Nout] . W[Nout,Kin]  (optionally * gelu'(pre_gelu): the layer in front ended in a fused GELU)."""
+    M, Nout = dy.shape
+    return gemm_majors(dy, weight, M, weight.shape[1], Nout, False, True, aux=pre_gelu, dgelu=pre_gelu is not None)
+
+
+def linear_wgrad(dy: torch.Tensor, x: torch.Tensor, out_dtype: torch.dtype = torch.float32) -> torch.Tensor:
+    """dW[Nout,Kin] = dY[M,Nout]^T . X[M,Kin], fp32 by default (it lands in an fp32 .grad)."""
+    M, Nout = dy.shape
+    return gemm_majors(dy, x, Nout, x.shape[1], M, True, True, out_dtype=out_dtype)

@@ -14,12 +14,17 @@ import torch.nn.functional as F
 
 from . import _lib
 
+# Benchmark comparator switch (baseline/library_encoder.py): True routes the bf16 inference layout through the torch
+# library ops (cuBLAS / SDPA / ATen LayerNorm) instead of the tcgen05 kernels, so that bench.py can time "the same module
+# tree on the libraries" next to ours on the same box.  Never set by the product.
+FORCE_LIBRARY = False
+
 
 def memory_efficient_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, attn_bias=None, p: float = 0.0,
                                scale: float | None = None) -> torch.Tensor:
     if attn_bias is not None:
         raise NotImplementedError("attn_bias is not used by Styl3R")
-    if (q.dtype == torch.bfloat16 and q.shape[-1] == 64 and p == 0.0 and q.is_cuda and not torch.is_grad_enabled()
+    if (not FORCE_LIBRARY and q.dtype == torch.bfloat16 and q.shape[-1] == 64 and p == 0.0 and q.is_cuda and not torch.is_grad_enabled()
             and all(t.stride(-1) == 1 and all(s % 8 == 0 for s in t.stride()[:3]) for t in (q, k, v))):
         return attention_bf16(q, k, v, scale if scale is not None else q.shape[-1] ** -0.5)
     out = F.scaled_dot_product_attention(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2), dropout_p=p,

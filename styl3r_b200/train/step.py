@@ -130,6 +130,11 @@ class TrainStep:
                 _EncoderForDDP(encoder), device_ids=[dev.index] if dev.type == "cuda" else None,
                 find_unused_parameters=True)
 
+    def backward_kind(self) -> str:
+        """Which kernels run the encoder's backward (reported by bench.py next to the cfg5 number)."""
+        from ..encoder import vit
+        return getattr(vit, "TRAIN_BACKWARD_KIND", "torch autograd over the reference's fp32/TF32 ops (cuBLAS / cuDNN / SDPA)")
+
     def _encode(self, context, style, global_step=0):
         if self.ddp is None:
             return self.encoder(context, style, global_step)

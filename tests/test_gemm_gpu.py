@@ -162,3 +162,33 @@ def test_layernorm_matches_fp32_reference(M, C, strided):
     torch.cuda.synchronize()
     assert y.dtype == torch.bfloat16 and y.shape == x.shape
     assert (y.float() - ref).abs().max().item() <= 2.0 ** -8 * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("M,N,K", [(514, 1024, 3072), (5140, 768, 768), (257, 3072, 1024), (300, 136, 200), (64, 64, 72)])
+def test_backward_gemms_mn_major_operands(M, N, K):
+    """dgrad / wgrad of nn.Linear on the tcgen05 GEMM with MN-major operands (no transposed copies) vs fp32 torch.
+    Tolerance: bf16 operands, fp32 accumulation -> |err| <= 2e-2 * sqrt(K) * rms(a) * rms(b) (bf16 output rounding
+    included), the same bar as the forward GEMM tests."""
+    import torch
+    from styl3r_b200.gemm import gemm_majors, linear_dgrad, linear_wgrad
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    dy = torch.randn(M, N, device="cuda", generator=g).to(torch.bfloat16)
+    w = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5).to(torch.bfloat16)
+    x = torch.randn(M, K, device="cuda", generator=g).to(torch.bfloat16)
+    pre = torch.randn(M, K, device="cuda", generator=g).to(torch.bfloat16)
+    dx = linear_dgrad(dy, w)
+    ref = dy.float() @ w.float()
+    assert (dx.float() - ref).abs().max() <= 2e-2 * ref.abs().max() + 1e-3
+    dxg = linear_dgrad(dy, w, pre_gelu=pre)
+    h = pre.float()
+    gp = 0.5 * (1 + torch.erf(h / 2 ** 0.5)) + h * torch.exp(-0.5 * h * h) / (2 * torch.pi) ** 0.5
+    assert (dxg.float() - ref * gp).abs().max() <= 2e-2 * (ref * gp).abs().max() + 1e-3
+    dw = linear_wgrad(dy, x)
+    refw = dy.float().t() @ x.float()
+    assert dw.dtype == torch.float32 and (dw - refw).abs().max() <= 2e-3 * refw.abs().max() + 1e-3
+    # A MN-major alone: C = A^T-stored . B^T
+    at = torch.zeros(K, (M + 7) // 8 * 8, device="cuda", dtype=torch.bfloat16)[:, :M]  # [K, M], 16-byte row pitch
+    at.copy_(x.t())
+    c = gemm_majors(at, w, M, N, K, True, False, out_dtype=torch.float32)
+    refc = x.float() @ w.float().t()
+    assert (c - refc).abs().max() <= 2e-3 * refc.abs().max() + 1e-3
