@@ -505,7 +505,9 @@ def run_ours(args):
                                              "(4 scenes = 24 views per GPU per pass, encoder included)", "n_gpus": world,
                                  "views_per_s": world * 24 / (ms3 * 1e-3), "ms_per_pass": ms3}
         barrier()
-        c5 = leg("cfg5", bl.train_step_leg, dev, args.train_batch, 3, world)
+        c5 = leg("cfg5", bl.train_step_leg, dev, args.train_batch, 3, world, "bf16")
+        if world == 1:  # comparator on the same box: the reference's own autograd path (fp32 / TF32 torch ops)
+            extra["cfg5_torch_autograd"] = leg("cfg5", bl.train_step_leg, dev, args.train_batch, 3, world, "torch")
         if c5 is not None and "error" not in c5 and dist is not None:
             tms = torch.tensor([c5["ms_per_step"]], device=dev)
             dist.all_reduce(tms, op=dist.ReduceOp.MAX)

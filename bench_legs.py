@@ -205,13 +205,14 @@ def pose_align_leg(dev, steps=50):
                     "wall time incl. the capacity probe and graph capture"}
 
 
-def train_step_leg(dev, batch, steps=3, world=1):
+def train_step_leg(dev, batch, steps=3, world=1, layout="bf16"):
     """BASELINE cfg5: 2 context views + style image, `batch` scenes per GPU, 4 target views, style loss + identity pass."""
     from styl3r_b200 import synthetic as syn
     from styl3r_b200.decoder import DecoderSplattingCUDA, DecoderSplattingCUDACfg
     from styl3r_b200.train import IdentityLoss, LossStyle, LossStyleCfg, LossStyleCfgWrapper, TrainStep
     V = 4
     enc = make_encoder(dev, inference=False)
+    enc.to_training(torch.bfloat16 if layout == "bf16" else None)
     dec = DecoderSplattingCUDA(DecoderSplattingCUDACfg("splatting_cuda", [0.0, 0.0, 0.0], True)).to(dev)
     style_loss = LossStyle(LossStyleCfgWrapper(LossStyleCfg(10.0))).to(dev)
     ident = IdentityLoss().to(dev)
@@ -248,7 +249,8 @@ def train_step_leg(dev, batch, steps=3, world=1):
            "what": "stage-2 step: encoder fwd x2 (style + identity pass) -> rasterizer fwd+bwd (our kernels) -> VGG style / identity "
                    "losses (tcgen05 convolutions, fwd + dgrad) -> encoder backward -> "
                    + ("DDP bucketed NCCL all-reduce -> " if world > 1 else "") + "clip -> AdamW",
-           "encoder_backward": step.backward_kind()}
+           "layout": layout, "encoder_backward": step.backward_kind()}
+    enc.to_training(None)
     del step, enc
     torch.cuda.empty_cache()
     return res

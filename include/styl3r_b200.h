@@ -202,6 +202,7 @@ int s3r_rope2d(void* tokens, const int64_t* pos, int32_t B, int32_t N, int32_t H
 #define S3R_EPI_ROPE 16
 #define S3R_EPI_RELU 32
 #define S3R_EPI_DGELU 128 /* C = acc * gelu'(aux): backward of a fused GELU, aux = the saved pre-activation [M, N] bf16 */
+#define S3R_EPI_SAVE_PRE 256 /* internal: set when s3r_gemm_bf16_majors is given pre_out */
 #define S3R_EPI_PDL 64 /* internal: set by the launcher when programmatic dependent launch is enabled (S3R_TUNE_PDL) */
 int s3r_gemm_bf16(const void* A, const void* W, const void* bias, const void* residual, void* C, int32_t M,
                   int32_t N, int32_t K, int32_t lda, int32_t ldw, int32_t ldc, int32_t ldr, int32_t flags,
@@ -231,7 +232,14 @@ int s3r_rope_table(float* table /* [(max_pos+1)*16*2] */, int32_t max_pos, float
  * flags: BIAS | GELU | RELU | OUT_F32 | RESIDUAL (aux added) | DGELU (multiply by gelu'(aux), aux = pre-activation). */
 int s3r_gemm_bf16_majors(const void* A, const void* B, const void* bias, const void* aux, void* C, int32_t M, int32_t N,
                          int32_t K, int32_t lda, int32_t ldb, int32_t ldc, int32_t ldaux, int32_t flags,
-                         int32_t a_mn_major, int32_t b_mn_major, void* stream);
+                         int32_t a_mn_major, int32_t b_mn_major, void* pre_out, void* stream);
+/* `batch` independent GEMMs in one launch (grid.z = batch): operand z starts stride_* ELEMENTS after operand z-1.  No
+ * epilogue besides S3R_EPI_OUT_F32.  Used by the attention backward (per image x head contractions). */
+int s3r_gemm_bf16_batched(const void* A, const void* B, void* C, int32_t M, int32_t N, int32_t K, int32_t lda, int32_t ldb,
+                          int32_t ldc, int64_t stride_a, int64_t stride_b, int64_t stride_c, int32_t batch, int32_t flags,
+                          int32_t a_mn_major, int32_t b_mn_major, void* stream);
+/* pre_out (optional, K-major operands only): bf16 [M, N] with pitch ldc that receives the value BEFORE the activation
+ * (after the bias) - what the backward of a fused GELU needs. */
 
 /* ------------------------------------------------------------------------
  * Stride-1 "same" 2-D convolution as an implicit GEMM on tcgen05/TMEM - the
@@ -279,6 +287,11 @@ int s3r_upsample2x_nhwc_bf16(const void* x, const void* add, void* y, int32_t n,
  * ------------------------------------------------------------------------ */
 int s3r_layernorm_bf16(const void* x, const void* weight, const void* bias, void* y, int32_t M, int32_t C, int64_t ldx,
                        float eps, void* stream);
+/* Backward of the same LayerNorm (autograd of nn.LayerNorm in the reference): dx [M, C] bf16 from x (row pitch ldx),
+ * weight and dy [M, C] (contiguous); dweight / dbias [C] fp32 are ACCUMULATED with atomicAdd (caller zero-fills; either
+ * may be NULL).  Statistics are recomputed from x.  C % 256 == 0, C <= 1024. */
+int s3r_layernorm_bwd_bf16(const void* x, const void* weight, const void* dy, void* dx, float* dweight, float* dbias,
+                           int32_t M, int32_t C, int64_t ldx, float eps, void* stream);
 
 /* ------------------------------------------------------------------------
  * Attention softmax(q k^T * scale) v on tcgen05/TMEM, head_dim 64, bf16 —
@@ -290,6 +303,14 @@ int s3r_layernorm_bf16(const void* x, const void* weight, const void* bias, void
 int s3r_attention_bf16(const void* q, const void* k, const void* v, void* o, int32_t B, int32_t H, int32_t Nq,
                        int32_t Nk, int32_t D, const int64_t* q_strides, const int64_t* k_strides,
                        const int64_t* v_strides, const int64_t* o_strides, float scale, void* stream);
+
+/* Row kernels of the attention backward (styl3r_b200/attention_bwd.py; autograd of memory_efficient_attention,
+ * blocks.py:126-130,192-196) between the batched GEMMs: P = softmax(scale * S) (fp32 [rows, ld] -> bf16 [rows, ldp],
+ * pad columns zeroed) and dS = scale * P o (dP - rowsum(dO o O)) with O / dO [rows, 64] bf16. */
+int s3r_softmax_rows_bf16(const float* S, void* P, int64_t rows, int32_t n, int32_t ld, int32_t ldp, float scale,
+                          void* stream);
+int s3r_attention_ds_bf16(const void* P, const float* dP, const void* O, const void* dO, void* dS, int64_t rows, int32_t n,
+                          int32_t ld, int32_t ldp, float scale, void* stream);
 
 /* ------------------------------------------------------------------------
  * Fused head epilogue -> Gaussians for one context view of a batch

@@ -54,6 +54,13 @@ __device__ __forceinline__ void g_tma_load_2d(void* dst, const CUtensorMap* map,
       "l"(map), "r"(c0), "r"(c1), "r"(g_smem_u32(bar))
       : "memory");
 }
+__device__ __forceinline__ void g_tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+          g_smem_u32(dst)),
+      "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(g_smem_u32(bar))
+      : "memory");
+}
 __device__ __forceinline__ void g_tma_load_4d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint64_t* bar) {
   asm volatile(
       "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(
@@ -190,7 +197,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, (STAGES_ * (GEMM_BM + BN) * GEMM
 s3r_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const __nv_bfloat16* __restrict__ bias, const __nv_bfloat16* __restrict__ residual, void* __restrict__ Cout,
                      int M, int N, int K, int ldc, int ldr, int flags, RopeArgs rope, int splits, float* __restrict__ ws,
-                     unsigned* __restrict__ counters, ConvArgs conv) {
+                     unsigned* __restrict__ counters, ConvArgs conv, long long batch_stride_c) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);  // SWIZZLE_128B atoms need 1024-B alignment
   using S = GemmSmem<BN, STAGES_>;
@@ -206,8 +213,15 @@ s3r_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   const int total_kb = (K + GEMM_BK - 1) / GEMM_BK;
   // split-K: CTA z owns k-blocks [kb0, kb0 + num_kb); partial tiles meet in an fp32 workspace and the last CTA to
   // arrive for an output tile sums them (fixed order => deterministic) and runs the fused epilogue
-  const int kb0 = (int)((long long)blockIdx.z * total_kb / splits);
-  const int num_kb = (int)((long long)(blockIdx.z + 1) * total_kb / splits) - kb0;
+  // batched mode (batch_stride_c > 0, splits == 1): blockIdx.z is the batch index - 3-D tensor maps {inner, rows, batch},
+  // C advances by batch_stride_c elements per batch (the per-head GEMMs of the attention backward)
+  const bool batched = batch_stride_c > 0;
+  const int zsplit = batched ? 0 : (int)blockIdx.z;
+  const int kb0 = (int)((long long)zsplit * total_kb / splits);
+  const int num_kb = (int)((long long)(zsplit + 1) * total_kb / splits) - kb0;
+  if (batched)
+    Cout = (flags & S3R_EPI_OUT_F32) ? (void*)((float*)Cout + (long long)blockIdx.z * batch_stride_c)
+                                     : (void*)((__nv_bfloat16*)Cout + (long long)blockIdx.z * batch_stride_c);
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -274,15 +288,23 @@ s3r_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           g_tma_load_2d_mc(a_dst + yr * AR * 128, &tmA, (kb0 + kb) * GEMM_BK, m0 + yr * AR, &full[s], mask_a);
         } else if (MAJ & 1) {  // two 64-row atoms of the MN-major A tile: box = 64 contraction rows x 64 M elements
 #pragma unroll
-          for (int h = 0; h < GEMM_BM / 64; h++)
-            g_tma_load_2d(a_dst + h * 8192, &tmA, m0 + h * 64, (kb0 + kb) * GEMM_BK, &full[s]);
+          for (int h = 0; h < GEMM_BM / 64; h++) {
+            if (batched) g_tma_load_3d(a_dst + h * 8192, &tmA, m0 + h * 64, (kb0 + kb) * GEMM_BK, blockIdx.z, &full[s]);
+            else g_tma_load_2d(a_dst + h * 8192, &tmA, m0 + h * 64, (kb0 + kb) * GEMM_BK, &full[s]);
+          }
+        } else if (batched) {
+          g_tma_load_3d(a_dst, &tmA, (kb0 + kb) * GEMM_BK, m0, blockIdx.z, &full[s]);
         } else {
           g_tma_load_2d(a_dst, &tmA, (kb0 + kb) * GEMM_BK, m0, &full[s]);
         }
         if (MAJ & 2) {
 #pragma unroll
-          for (int h = 0; h < BN / 64; h++)
-            g_tma_load_2d(b_dst + h * 8192, &tmB, n0 + h * 64, (kb0 + kb) * GEMM_BK, &full[s]);
+          for (int h = 0; h < BN / 64; h++) {
+            if (batched) g_tma_load_3d(b_dst + h * 8192, &tmB, n0 + h * 64, (kb0 + kb) * GEMM_BK, blockIdx.z, &full[s]);
+            else g_tma_load_2d(b_dst + h * 8192, &tmB, n0 + h * 64, (kb0 + kb) * GEMM_BK, &full[s]);
+          }
+        } else if (batched) {
+          g_tma_load_3d(b_dst, &tmB, (kb0 + kb) * GEMM_BK, n0, blockIdx.z, &full[s]);
         } else if (CM > 1) {         // my BN/CM-row slice of the W tile, to every CTA that shares this N tile
           constexpr int BR = BN / CM;
           g_tma_load_2d_mc(b_dst + xr * BR * 128, &tmB, (kb0 + kb) * GEMM_BK, n0 + xr * BR, &full[s], mask_b);
@@ -384,6 +406,17 @@ s3r_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             const float2 cs = __ldg(rope.table + pp * 16 + d0 + j);
             f[j] = lower ? (f[j] * cs.x - o[j] * cs.y) : (f[j] * cs.x + o[j] * cs.y);
           }
+        }
+      }
+      if ((flags & S3R_EPI_SAVE_PRE) && row < M && col < N) {  // training forward: keep the pre-activation for gelu'
+        __nv_bfloat16* pp = reinterpret_cast<__nv_bfloat16*>(ws) + (size_t)row * ldc + col;
+        if (full4) {
+          uint2 u;
+          *reinterpret_cast<__nv_bfloat162*>(&u.x) = __floats2bfloat162_rn(f[0], f[1]);
+          *reinterpret_cast<__nv_bfloat162*>(&u.y) = __floats2bfloat162_rn(f[2], f[3]);
+          *reinterpret_cast<uint2*>(pp) = u;
+        } else {
+          for (int j = 0; j < 4 && col + j < N; j++) pp[j] = __float2bfloat16_rn(f[j]);
         }
       }
       if (gelu) {
@@ -559,19 +592,19 @@ static int make_map(CUtensorMap* map, const void* ptr, int rows, int cols, int l
 template <int BN, int STAGES_, bool kConv = false, int CM = 1, int CN = 1, int MAJ = 0>
 static int launch_gemm(const CUtensorMap& a, const CUtensorMap& b, const void* bias, const void* residual, void* C, int M,
                        int N, int K, int ldc, int ldr, int flags, const RopeArgs& rope, int splits, float* ws, unsigned* counters,
-                       cudaStream_t st, const ConvArgs& conv = ConvArgs{}) {
-  static bool configured = false;
+                       cudaStream_t st, const ConvArgs& conv = ConvArgs{}, int batch = 0, long long batch_stride_c = 0) {
+  static size_t configured[64] = {};  // per device: cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute
   const int smem = GemmSmem<BN, STAGES_>::TOTAL;
   auto kern = s3r_gemm_bf16_kernel<BN, STAGES_, kConv, CM, CN, MAJ>;
-  if (!configured) {
-    S3R_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
+  {
+    const int rc_ = s3r_ensure_dynamic_smem(kern, (size_t)smem, configured);
+    if (rc_ != S3R_OK) return rc_;
   }
   // grid padded to whole clusters: CTAs past the last tile still take part in the multicast (their own loads are fully
   // out of bounds = zero fill, their epilogue is masked)
   const unsigned gx = ((M + GEMM_BM - 1) / GEMM_BM + CM - 1) / CM * CM, gy = ((N + BN - 1) / BN + CN - 1) / CN * CN;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(gx, gy, splits);
+  cfg.gridDim = dim3(gx, gy, batch > 0 ? batch : splits);
   cfg.blockDim = dim3(GEMM_THREADS, 1, 1);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
@@ -593,7 +626,7 @@ static int launch_gemm(const CUtensorMap& a, const CUtensorMap& b, const void* b
   cfg.attrs = attr;
   cfg.numAttrs = na;
   S3R_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, a, b, (const __nv_bfloat16*)bias, (const __nv_bfloat16*)residual, C, M, N, K,
-                                    ldc, ldr, flags, rope, splits, ws, counters, conv));
+                                    ldc, ldr, flags, rope, splits, ws, counters, conv, batch > 0 ? batch_stride_c : 0LL));
   return S3R_OK;
 }
 
@@ -629,6 +662,10 @@ extern "C" int s3r_rope_table(float* table, int32_t max_pos, float base, void* s
   S3R_CUDA_CHECK(cudaGetLastError());
   return S3R_OK;
 }
+
+// set by s3r_gemm_bf16_majors around its call into s3r_gemm_bf16_rope: bf16 [M, N] (pitch ldc) buffer that receives the
+// pre-activation (S3R_EPI_SAVE_PRE); travels in the kernel's (then unused) split-K workspace argument
+static thread_local void* t_pre_out = nullptr;
 
 extern "C" int s3r_gemm_bf16_rope(const void* A, const void* W, const void* bias, const void* residual, void* C, int32_t M,
                                   int32_t N, int32_t K, int32_t lda, int32_t ldw, int32_t ldc, int32_t ldr, int32_t flags,
@@ -684,6 +721,11 @@ extern "C" int s3r_gemm_bf16_rope(const void* A, const void* W, const void* bias
       ws = (float*)((char*)workspace + 16384);
     }
   }
+  if (t_pre_out) {
+    splits = 1, counters = nullptr;
+    ws = (float*)t_pre_out;
+    flags |= S3R_EPI_SAVE_PRE;
+  }
 #define S3R_GEMM_GO(BN_, ST_, CM_, CN_)                                                                             \
   return launch_gemm<BN_, ST_, false, CM_, CN_>(ta, tb, bias, residual, C, M, N, K, ldc, ldr, flags, rope, splits, ws, \
                                                  counters, st)
@@ -700,7 +742,8 @@ extern "C" int s3r_gemm_bf16_rope(const void* A, const void* W, const void* bias
     if (tiles64 * splits < 148 && !g_gemm_shallow) S3R_GEMM_CLUSTERS(64, 8);
     S3R_GEMM_CLUSTERS(64, 4);
   }
-  splits = 1, ws = nullptr, counters = nullptr;
+  splits = 1, counters = nullptr;
+  if (!t_pre_out) ws = nullptr;
   if (BN == 256) S3R_GEMM_CLUSTERS(256, 2);
   S3R_GEMM_CLUSTERS(128, 3);
 #undef S3R_GEMM_CLUSTERS
@@ -720,7 +763,7 @@ extern "C" int s3r_gemm_bf16(const void* A, const void* W, const void* bias, con
 //   wgrad  dW[Nout,Kin] = dY[M,Nout]^T . X[M,Kin]           A and B MN-major (both are [contraction, MN] row-major)
 extern "C" int s3r_gemm_bf16_majors(const void* A, const void* B, const void* bias, const void* aux, void* C, int32_t M,
                                     int32_t N, int32_t K, int32_t lda, int32_t ldb, int32_t ldc, int32_t ldaux,
-                                    int32_t flags, int32_t a_mn_major, int32_t b_mn_major, void* stream) {
+                                    int32_t flags, int32_t a_mn_major, int32_t b_mn_major, void* pre_out, void* stream) {
   if (M < 0 || N <= 0 || K <= 0) return S3R_ERR_INVALID_ARG;
   if (M == 0) return S3R_OK;
   if (!A || !B || !C) return S3R_ERR_INVALID_ARG;
@@ -730,8 +773,13 @@ extern "C" int s3r_gemm_bf16_majors(const void* A, const void* B, const void* bi
   if ((flags & S3R_EPI_RESIDUAL) && (flags & S3R_EPI_DGELU)) return S3R_ERR_INVALID_ARG;  // one aux operand
   if (lda % 8 || ldb % 8 || ldc % 8 || ((flags & (S3R_EPI_RESIDUAL | S3R_EPI_DGELU)) && ldaux % 8)) return S3R_ERR_UNSUPPORTED;
   if (((uintptr_t)A | (uintptr_t)B | (uintptr_t)C) & 15) return S3R_ERR_UNSUPPORTED;
-  if (!a_mn_major && !b_mn_major)
-    return s3r_gemm_bf16_rope(A, B, bias, aux, C, M, N, K, lda, ldb, ldc, ldaux, flags, nullptr, nullptr, 0, 0, nullptr, 0, stream);
+  if (pre_out && (a_mn_major || b_mn_major || (flags & S3R_EPI_OUT_F32) || ((uintptr_t)pre_out & 15))) return S3R_ERR_INVALID_ARG;
+  if (!a_mn_major && !b_mn_major) {
+    t_pre_out = pre_out;
+    const int rc0 = s3r_gemm_bf16_rope(A, B, bias, aux, C, M, N, K, lda, ldb, ldc, ldaux, flags, nullptr, nullptr, 0, 0, nullptr, 0, stream);
+    t_pre_out = nullptr;
+    return rc0;
+  }
   CUtensorMap ta, tb;
   int rc;
   // K-major operand: rows = M (or N), inner = K, box 64 x 128; MN-major operand: rows = K, inner = M (or N), box 64 x 64
@@ -744,6 +792,48 @@ extern "C" int s3r_gemm_bf16_majors(const void* A, const void* B, const void* bi
   if (a_mn_major)
     return launch_gemm<128, 3, false, 1, 1, 1>(ta, tb, bias, aux, C, M, N, K, ldc, ldaux, flags, rope, 1, nullptr, nullptr, st);
   return launch_gemm<128, 3, false, 1, 1, 2>(ta, tb, bias, aux, C, M, N, K, ldc, ldaux, flags, rope, 1, nullptr, nullptr, st);
+}
+
+static int make_map_3d(CUtensorMap* map, const void* ptr, int rows, int cols, long long ld, long long batch_stride, int batch,
+                       int box_rows) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return S3R_ERR_CUDA;
+  const cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)batch};
+  const cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)batch_stride * 2};
+  const cuuint32_t box[3] = {GEMM_BK, (cuuint32_t)box_rows, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? S3R_OK : S3R_ERR_CUDA;
+}
+
+// Batched variant: `batch` independent GEMMs C_z = opA_z . opB_z^T with element strides between consecutive problems -
+// the per-(image, head) contractions of the attention backward (S = Q K^T, dP = dO V^T, dV = P^T dO, dK = dS^T Q,
+// dQ = dS K), one launch each.  No bias / activation; flags: S3R_EPI_OUT_F32 only.
+extern "C" int s3r_gemm_bf16_batched(const void* A, const void* B, void* C, int32_t M, int32_t N, int32_t K, int32_t lda,
+                                     int32_t ldb, int32_t ldc, int64_t stride_a, int64_t stride_b, int64_t stride_c,
+                                     int32_t batch, int32_t flags, int32_t a_mn_major, int32_t b_mn_major, void* stream) {
+  if (M < 0 || N <= 0 || K <= 0 || batch < 0) return S3R_ERR_INVALID_ARG;
+  if (M == 0 || batch == 0) return S3R_OK;
+  if (!A || !B || !C || (flags & ~S3R_EPI_OUT_F32)) return S3R_ERR_INVALID_ARG;
+  if (lda % 8 || ldb % 8 || ldc % 8 || stride_a % 8 || stride_b % 8 || stride_c % 8 || stride_c <= 0 || batch > 65535)
+    return S3R_ERR_UNSUPPORTED;
+  if (((uintptr_t)A | (uintptr_t)B | (uintptr_t)C) & 15) return S3R_ERR_UNSUPPORTED;
+  CUtensorMap ta, tb;
+  int rc;
+  if ((rc = a_mn_major ? make_map_3d(&ta, A, K, M, lda, stride_a, batch, 64) : make_map_3d(&ta, A, M, K, lda, stride_a, batch, GEMM_BM)) != S3R_OK) return rc;
+  if ((rc = b_mn_major ? make_map_3d(&tb, B, K, N, ldb, stride_b, batch, 64) : make_map_3d(&tb, B, N, K, ldb, stride_b, batch, 128)) != S3R_OK) return rc;
+  RopeArgs rope{nullptr, nullptr, 0, 0};
+  cudaStream_t st = (cudaStream_t)stream;
+  const ConvArgs cv{};
+#define S3R_BGEMM(MAJ_) \
+  return launch_gemm<128, 3, false, 1, 1, MAJ_>(ta, tb, nullptr, nullptr, C, M, N, K, ldc, 0, flags, rope, 1, nullptr, nullptr, st, cv, batch, stride_c)
+  if (a_mn_major && b_mn_major) S3R_BGEMM(3);
+  if (a_mn_major) S3R_BGEMM(1);
+  if (b_mn_major) S3R_BGEMM(2);
+  S3R_BGEMM(0);
+#undef S3R_BGEMM
 }
 
 // ---------------------------------------------------------------------------------------------------------- conv2d

@@ -255,6 +255,23 @@ class EncoderNoPoSplatMultiTokenStyle(nn.Module):
             head.dpt._prep = None  # bf16 operands are rebuilt from the (possibly reloaded) parameters on first use
         return self
 
+    def to_training(self, vit_dtype: torch.dtype = torch.bfloat16):
+        """bf16 TRAINING layout (BASELINE cfg5): fp32 parameters (the optimiser's master copy), bf16 activations in the
+        ViT trunks, forward and backward of every trunk Linear / LayerNorm / attention on our kernels through the
+        autograd functions of `train_ops.py` (tcgen05 GEMM dgrad / wgrad with MN-major operands, batched-GEMM attention
+        backward, LayerNorm backward).  The DPT heads and the adapter keep the reference's fp32 torch ops under autograd
+        (convolution wgrad is not written yet - DESIGN.md §7).  `to_training(None)` restores the fp32 / TF32 torch path
+        that the golden tests pin.  Process-wide switch (vit.TRAIN_BF16)."""
+        from . import vit
+        if vit_dtype not in (None, torch.bfloat16):
+            raise ValueError("to_training supports torch.bfloat16 or None")
+        vit.TRAIN_BF16 = vit_dtype is not None
+        vit.TRAIN_BACKWARD_KIND = (
+            "ours: tcgen05 GEMM dgrad / wgrad (MN-major operands) + gelu' epilogue, tcgen05 attention forward + batched-GEMM "
+            "attention backward, LayerNorm forward / backward kernels for the ViT trunks; DPT heads on cuDNN autograd"
+            if vit.TRAIN_BF16 else "torch autograd over the reference's fp32/TF32 ops (cuBLAS / cuDNN / SDPA)")
+        return self
+
     def opacity_exponent(self, global_step: int) -> float:
         m = self.cfg.opacity_mapping
         return 2.0 ** (m.initial + min(global_step / m.warm_up, 1) * (m.final - m.initial))

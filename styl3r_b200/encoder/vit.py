@@ -19,8 +19,24 @@ from ..curope import cuRoPE2D_func
 from .. import ops as _ops
 from ..ops import memory_efficient_attention
 from ..streams import fork_join
+from . import train_ops as _tops
 
 LN_EPS = 1e-6  # croco.py:34
+
+# bf16 TRAINING layout (`EncoderNoPoSplatMultiTokenStyle.to_training()`): with autograd enabled the ViT trunks run the
+# autograd functions of train_ops.py - forward AND backward on the tcgen05 GEMM (dgrad / wgrad with MN-major operands),
+# the tcgen05 attention kernel + batched-GEMM attention backward and our LayerNorm kernels; parameters stay fp32.
+# False (default): autograd runs the reference's fp32 / TF32 torch ops (the numerics the golden tests pin).
+TRAIN_BF16 = False
+TRAIN_BACKWARD_KIND = "torch autograd over the reference's fp32/TF32 ops (cuBLAS / cuDNN / SDPA)"
+
+
+def _train(x: Tensor) -> bool:
+    return TRAIN_BF16 and torch.is_grad_enabled() and x.is_cuda
+
+
+def _bf16(x: Tensor) -> Tensor:
+    return x if x.dtype == torch.bfloat16 else x.to(torch.bfloat16)
 
 
 def _rope(t_bnhd: Tensor, pos: Tensor, base: float) -> Tensor:
@@ -39,6 +55,8 @@ def _lin(layer: nn.Linear, x: Tensor, residual: Tensor | None = None, gelu: bool
     GELU and residual add fused in its epilogue; otherwise (fp32 / training) the torch ops of the reference."""
     if _fast(layer, x):
         return _gemm.linear(x, layer.weight, layer.bias, residual=residual, gelu=gelu)
+    if _train(x) and not gelu and layer.in_features % 8 == 0 and layer.out_features % 8 == 0:
+        return _tops.linear(_bf16(x), layer, residual=None if residual is None else _bf16(residual))
     y = layer(x)
     if gelu:
         y = torch.nn.functional.gelu(y)
@@ -49,6 +67,8 @@ def _ln(norm: nn.LayerNorm, x: Tensor) -> Tensor:
     """LayerNorm: bf16 inference layout -> `s3r_layernorm_bf16` (one warp per row, fp32 statistics, launched with
     programmatic dependent launch); otherwise the torch module."""
     C_ = x.shape[-1]
+    if _train(x) and C_ % 256 == 0 and C_ <= 1024:
+        return _tops.layer_norm(_bf16(x), norm)
     if (not _ops.FORCE_LIBRARY and x.dtype == torch.bfloat16 and norm.weight.dtype == torch.bfloat16
             and not torch.is_grad_enabled() and x.is_cuda
             and C_ % 256 == 0 and C_ <= 2048):
@@ -75,6 +95,8 @@ class Mlp(nn.Module):
         self.fc2 = nn.Linear(hidden, dim)
 
     def forward(self, x: Tensor, residual: Tensor | None = None) -> Tensor:
+        if _train(x):
+            return _tops.mlp(_bf16(x), self.fc1, self.fc2, residual=None if residual is None else _bf16(residual))
         return _lin(self.fc2, _lin(self.fc1, x, gelu=True), residual=residual)
 
 
@@ -87,6 +109,11 @@ class Attention(nn.Module):
 
     def forward(self, x: Tensor, xpos: Tensor, residual: Tensor | None = None) -> Tensor:
         B, N, C = x.shape
+        if _train(x) and C // self.num_heads == 64:
+            qkv = _tops.linear(_bf16(x), self.qkv, rope_pos=xpos, rope_cols=2 * C, rope_base=self.rope_base)
+            qkv = qkv.view(B, N, 3, self.num_heads, C // self.num_heads)
+            o = _tops.attention(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], self.scale)
+            return _lin(self.proj, o.reshape(B, N, C), residual=residual)
         if _fast(self.qkv, x) and C // self.num_heads == 64:
             # RoPE on the q and k thirds happens in the GEMM epilogue (fp32, before the bf16 rounding)
             qkv = _gemm.linear(x, self.qkv.weight, self.qkv.bias, rope_pos=xpos, rope_cols=2 * C, rope_base=self.rope_base)
@@ -112,6 +139,8 @@ class CrossAttention(nn.Module):
     def project_q(self, query: Tensor, qpos: Tensor) -> Tensor:
         B, Nq, C = query.shape
         H, D = self.num_heads, C // self.num_heads
+        if _train(query) and D == 64:
+            return _tops.linear(_bf16(query), self.projq, rope_pos=qpos, rope_cols=C, rope_base=self.rope_base).view(B, Nq, H, D)
         if _fast(self.projq, query) and D == 64:
             return _gemm.linear(query, self.projq.weight, self.projq.bias, rope_pos=qpos, rope_cols=C,
                                 rope_base=self.rope_base).view(B, Nq, H, D)
@@ -122,6 +151,9 @@ class CrossAttention(nn.Module):
         them concurrently with its self-attention."""
         B, Nk, C = key.shape
         H, D = self.num_heads, C // self.num_heads
+        if _train(key) and D == 64:
+            k = _tops.linear(_bf16(key), self.projk, rope_pos=kpos, rope_cols=C, rope_base=self.rope_base).view(B, Nk, H, D)
+            return k, _lin(self.projv, value).view(B, value.shape[1], H, D)
         if _fast(self.projk, key) and D == 64 and key is value:
             # one GEMM for both projections (N = 2C, RoPE on the K half only): the batch-1 forward is bound by the number
             # of kernel launches the graph has to dispatch, not by their FLOPs
@@ -149,7 +181,10 @@ class CrossAttention(nn.Module):
 
     def attend(self, q: Tensor, k: Tensor, v: Tensor, residual: Tensor | None = None) -> Tensor:
         B, Nq, H, D = q.shape
-        o = memory_efficient_attention(q, k, v, scale=self.scale)
+        if _train(q) and D == 64:
+            o = _tops.attention(q, k, v, self.scale)
+        else:
+            o = memory_efficient_attention(q, k, v, scale=self.scale)
         return _lin(self.proj, o.reshape(B, Nq, H * D), residual=residual)
 
     def forward(self, query: Tensor, key: Tensor, value: Tensor, qpos: Tensor, kpos: Tensor,
@@ -221,6 +256,10 @@ class PatchEmbed(nn.Module):
             # like weight.flatten(1) - one gather copy + the tcgen05 GEMM instead of a cuDNN conv with layout transposes
             cols = img.reshape(B, -1, gh, ph, gw, pw).permute(0, 2, 4, 1, 3, 5).reshape(B * gh * gw, -1)
             return _gemm.linear(cols, w.flatten(1), self.proj.bias).view(B, gh * gw, -1), pos
+        if _train(img):
+            cols = _bf16(img).reshape(B, -1, gh, ph, gw, pw).permute(0, 2, 4, 1, 3, 5).reshape(B * gh * gw, -1)
+            y = _tops.LinearFn.apply(cols, w.flatten(1), self.proj.bias, None, None, 0, 100.0)
+            return y.view(B, gh * gw, -1), pos
         x = self.proj(img)
         return x.flatten(2).transpose(1, 2), pos
 

@@ -111,7 +111,7 @@ EPI_DGELU = 128
 
 def gemm_majors(a: torch.Tensor, b: torch.Tensor, M: int, N: int, K: int, a_mn_major: bool, b_mn_major: bool,
                 bias: Optional[torch.Tensor] = None, aux: Optional[torch.Tensor] = None, dgelu: bool = False,
-                out_dtype: torch.dtype = torch.bfloat16) -> torch.Tensor:
+                out_dtype: torch.dtype = torch.bfloat16, gelu: bool = False, pre_out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """C[M,N] = opA . opB^T (+ bias) (+ aux | * gelu'(aux)) with either operand MN-major (`s3r_gemm_bf16_majors`):
     a is [M,K] (a_mn_major False) or [K,M] (True); b is [N,K] or [K,N].  2-D bf16 tensors with unit inner stride."""
     if a.dtype != torch.bfloat16 or b.dtype != torch.bfloat16 or a.device.type != "cuda":
@@ -135,9 +135,14 @@ def gemm_majors(a: torch.Tensor, b: torch.Tensor, M: int, N: int, K: int, a_mn_m
         xp, ldx = C.c_void_p(aux.data_ptr()), aux.stride(0)
     if out_dtype == torch.float32:
         flags |= EPI_OUT_F32
+    if gelu:
+        flags |= EPI_GELU
+    if pre_out is not None and (pre_out.shape != (M, N) or pre_out.stride() != out.stride() or pre_out.dtype != torch.bfloat16):
+        raise _lib.S3RError("pre_out must be a contiguous bf16 [M, N] tensor")
     _lib.check(_lib.lib().s3r_gemm_bf16_majors(C.c_void_p(a.data_ptr()), C.c_void_p(b.data_ptr()), bp, xp,
                                                C.c_void_p(out.data_ptr()), M, N, K, a.stride(0), b.stride(0), out.stride(0),
                                                ldx, flags, int(a_mn_major), int(b_mn_major),
+                                               None if pre_out is None else C.c_void_p(pre_out.data_ptr()),
                                                C.c_void_p(torch.cuda.current_stream(a.device).cuda_stream)),
                "s3r_gemm_bf16_majors")
     return out

@@ -139,3 +139,36 @@ def test_render_cuda_orthographic_and_sh_degree_4_layout():
                                      dump=dump, view_set=vs)
     assert ortho.shape == (2, 3, 64, 64) and torch.isfinite(ortho).all() and ortho.abs().sum() > 0
     assert set(dump) == {"extrinsics", "fov_x", "fov_y", "near", "far"}
+
+
+def test_xformers_ops_shim_forward_and_backward():
+    """`compat.install()` registers an `xformers.ops` module (blocks.py:25 imports it unconditionally) whose
+    memory_efficient_attention runs on our kernels, fp32 in / out like the reference's call, differentiable."""
+    import sys
+    import torch
+    from styl3r_b200 import compat
+    saved = {k: sys.modules.pop(k) for k in ("xformers", "xformers.ops") if k in sys.modules}
+    try:
+        compat.install()
+        import xformers.ops as xops
+        assert xops.__name__.startswith("styl3r_b200.compat")
+        g = torch.Generator(device="cuda").manual_seed(0)
+        q, k, v = (torch.randn(2, n, 16, 64, device="cuda", generator=g, requires_grad=True) for n in (257, 300, 300))
+        out = xops.memory_efficient_attention(q, k, v, scale=0.125, p=0.0)
+        assert out.dtype == torch.float32 and out.shape == q.shape
+        w = torch.randn_like(out)
+        (out * w).sum().backward()
+        got = [t.grad.clone() for t in (q, k, v)]
+        for t in (q, k, v):
+            t.grad = None
+        ref = torch.nn.functional.scaled_dot_product_attention(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2),
+                                                               scale=0.125).transpose(1, 2)
+        (ref * w).sum().backward()
+        rel = lambda a, b: ((a - b).norm() / b.norm()).item()
+        assert rel(out, ref) <= 1e-2
+        for a, t in zip(got, (q, k, v)):
+            assert rel(a, t.grad) <= 2e-2
+    finally:
+        for k_ in ("xformers", "xformers.ops"):
+            sys.modules.pop(k_, None)
+        sys.modules.update(saved)
