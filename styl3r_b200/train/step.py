@@ -103,9 +103,15 @@ class _EncoderForDDP(nn.Module):
         super().__init__()
         self.encoder = encoder
 
-    def forward(self, context: dict, style: dict, global_step: int = 0):
-        g = self.encoder(context, style, global_step)
-        return g.means, g.covariances, g.harmonics, g.opacities
+    def forward(self, context: dict, styles, global_step: int = 0):
+        """`styles`: the style dicts of ALL encoder passes of one training step (stylised pass, identity pass) - like
+        Lightning's DDP wrapper around `training_step`, ONE wrapped forward covers every use of the parameters before
+        the single backward (the reducer's unused-parameter search runs once per wrapped forward)."""
+        out = []
+        for style in styles:
+            g = self.encoder(context, style, global_step)
+            out += [g.means, g.covariances, g.harmonics, g.opacities]
+        return tuple(out)
 
 
 class TrainStep:
@@ -126,24 +132,39 @@ class TrainStep:
         self.ddp = None
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
             dev = next(encoder.parameters()).device
+            # buffers are constants (SH mask, VGG statistics): no per-forward broadcast (which would also bump their
+            # version between the two encoder passes of a step)
             self.ddp = nn.parallel.DistributedDataParallel(
                 _EncoderForDDP(encoder), device_ids=[dev.index] if dev.type == "cuda" else None,
-                find_unused_parameters=True)
+                find_unused_parameters=True, broadcast_buffers=False)
 
     def backward_kind(self) -> str:
         """Which kernels run the encoder's backward (reported by bench.py next to the cfg5 number)."""
         from ..encoder import vit
         return getattr(vit, "TRAIN_BACKWARD_KIND", "torch autograd over the reference's fp32/TF32 ops (cuBLAS / cuDNN / SDPA)")
 
-    def _encode(self, context, style, global_step=0):
+    def _encoder_proxy(self, batch: dict):
+        """The `encoder` callable handed to training_step.  Single process: the encoder itself.  DDP: both passes of the
+        step (training_step's stylised and identity calls, in that order) are computed by ONE wrapped forward up front
+        and handed out in call order."""
+        stylized = getattr(self.encoder, "stylized", True)
         if self.ddp is None:
-            return self.encoder(context, style, global_step)
+            return type("Enc", (), {"stylized": stylized, "__call__": lambda s, c, st, gs=0: self.encoder(c, st, gs)})()
         from ..encoder.encoder import Gaussians
-        return Gaussians(*self.ddp(context, style, global_step))
+        b = self.data_shim(batch) if self.data_shim is not None else batch
+        ctx = b["context"]
+        if stylized:
+            st0 = dict(b["style"])
+            st0["image"] = (st0["image"].clone() - 0.5) / 0.5
+        else:
+            st0 = {"image": ctx["image"][:, 0]}
+        styles = [st0] + ([{"image": ctx["image"][:, 0]}] if self.identity_loss is not None else [])
+        flat = self.ddp(ctx, styles, self.global_step)
+        queue = [Gaussians(*flat[4 * i:4 * i + 4]) for i in range(len(styles))]
+        return type("Enc", (), {"stylized": stylized, "__call__": lambda s, c, st, gs=0: queue.pop(0)})()
 
     def __call__(self, batch: dict):
-        enc = type("Enc", (), {"stylized": getattr(self.encoder, "stylized", True),
-                               "__call__": lambda s, c, st, gs=0: self._encode(c, st, gs)})()
+        enc = self._encoder_proxy(batch)
         self.optimizer.zero_grad(set_to_none=True)
         loss, logs = training_step(enc, self.decoder, self.losses, batch, self.global_step, self.identity_loss,
                                    self.data_shim)
