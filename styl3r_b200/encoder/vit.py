@@ -248,6 +248,10 @@ class PatchEmbed(nn.Module):
         assert H % ph == 0, f"Input image height ({H}) is not a multiple of patch size ({ph})."
         assert W % pw == 0, f"Input image width ({W}) is not a multiple of patch size ({pw})."
         gh, gw = H // ph, W // pw
+        if max(gh + 1, gw) > _gemm.ROPE_MAX_POS:  # (+1: the intrinsics token sits at row gh)
+            # the fused-RoPE GEMM epilogue looks positions up in a (ROPE_MAX_POS + 1)-entry table and would clamp
+            raise ValueError(f"patch grid {gh}x{gw} exceeds the RoPE table ({_gemm.ROPE_MAX_POS} positions per axis): "
+                             f"images above {_gemm.ROPE_MAX_POS * ph} px per side are not supported")
         ys, xs = torch.meshgrid(torch.arange(gh, device=img.device), torch.arange(gw, device=img.device), indexing="ij")
         pos = torch.stack((ys.reshape(-1), xs.reshape(-1)), dim=-1)[None].expand(B, -1, -1).contiguous()
         w = self.proj.weight

@@ -42,7 +42,7 @@ class InferOutput:
 def infer(encoder, decoder: DecoderSplattingCUDA, context_images: Tensor, context_intrinsics: Tensor,
           context_extrinsics: Tensor, target_images: Tensor, target_intrinsics: Tensor, target_extrinsics: Tensor,
           style_image: Tensor, image_shape=(256, 256), near: float = 0.1, far: float = 100.0, pose_align_steps: int = 0,
-          num_video_frames: int = 60, output_dir: Optional[Path] = None) -> InferOutput:
+          num_video_frames: int = 60, output_dir: Optional[Path] = None, pose_align_losses=None) -> InferOutput:
     """context/target_images: raw [v,3,H0,W0] in [0,1]; *_intrinsics normalised [v,3,3]; *_extrinsics c2w [v,4,4]
     (already in the relative-pose frame of the first context camera); style_image [3,Hs,Ws] in [0,1]."""
     dev = context_images.device
@@ -69,8 +69,11 @@ def infer(encoder, decoder: DecoderSplattingCUDA, context_images: Tensor, contex
     tgt = batch["target"]
     extr = tgt["extrinsics"]
     if pose_align_steps > 0:  # test_step_align: poses refined against the non-stylised Gaussians
+        # `pose_align_losses`: the configured loss list of the reference (infer_model_re10k.py:121-124 sums every entry of
+        # `losses`; shipped config [mse, lpips]) as callables loss(color, target) -> scalar.  None = the MSE term only - a
+        # documented deviation: LPIPS weights are not shipped here (pose_align.py).
         extr, _ = pose_align(gaussians, extr, tgt["intrinsics"], tgt["near"], tgt["far"], image_shape, tgt["image"],
-                             steps=pose_align_steps)
+                             steps=pose_align_steps, losses=pose_align_losses)
     out = decoder.forward(gaussians, extr, tgt["intrinsics"], tgt["near"], tgt["far"], image_shape)
     sout = decoder.forward(stylized, extr, tgt["intrinsics"], tgt["near"], tgt["far"], image_shape)
     video = render_video_interpolation(stylized, decoder, batch, num_frames=num_video_frames) if num_video_frames else None

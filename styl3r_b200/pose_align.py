@@ -8,14 +8,20 @@ deltas (rho = cam_trans_delta, theta = cam_rot_delta), take an Adam step, fold t
 B200 version: the world->camera matrices stay on the device for the whole loop (no inverse / per-view Python loop /
 `.item()` per step), only dL/dtau is requested from the rasterizer backward (no Gaussian gradients are written), and
 one iteration = camera kernel + raster forward + loss gradient + raster backward + Adam + SE3 update is captured in
-ONE CUDA graph that is replayed `steps` times.  The image loss is the MSE part of the reference's loss list
-(`loss_mse`); a custom `loss_grad(color, target) -> dL/dcolor` may be supplied (LPIPS needs a VGG and is outside
-the hot path).
+ONE CUDA graph that is replayed `steps` times.
+
+Loss: the reference sums EVERY configured loss (`for loss_fn in losses: total_loss += loss_fn.forward(...)`,
+infer_model_re10k.py:121-124; the shipped config is `[mse, lpips]`).  Pass the same list as `losses` - callables
+`loss(color [B,3,h,w], target [B,3,h,w]) -> scalar` whose sum is differentiated with torch autograd inside the captured
+iteration - or an analytic `loss_grad(color, target) -> dL/dcolor`.  With neither, the MSE term alone is optimised
+(`loss_mse` with weight 1): that equals the reference only for an MSE-only loss list, and refined poses differ from the
+reference's whenever other terms (LPIPS needs the `lpips` package's VGG weights, which this repository does not ship)
+are configured.
 """
 from __future__ import annotations
 
 from math import isqrt
-from typing import Callable, Optional
+from typing import Callable, Optional, Sequence
 
 import torch
 from torch import Tensor
@@ -34,7 +40,7 @@ def pose_align(gaussians, extrinsics: Tensor, intrinsics: Tensor, near: Tensor, 
                target_image: Tensor, steps: int = 50, rot_lr: float = 0.005, trans_lr: float = 0.005,
                background: Optional[Tensor] = None, scale_invariant: bool = True,
                loss_grad: Optional[Callable[[Tensor, Tensor], Tensor]] = None, use_graph: bool = True,
-               betas=(0.9, 0.999), eps: float = 1e-8):
+               betas=(0.9, 0.999), eps: float = 1e-8, losses: Optional[Sequence[Callable[[Tensor, Tensor], Tensor]]] = None):
     """gaussians: object with means[b,G,3], covariances[b,G,3,3], harmonics[b,G,3,d_sh], opacities[b,G];
     extrinsics [b,v,4,4] camera-to-world; intrinsics [b,v,3,3]; near/far [b,v]; target_image [b,v,3,h,w].
     Returns (refined extrinsics [b,v,4,4] camera-to-world, loss history [steps] on device)."""
@@ -42,6 +48,16 @@ def pose_align(gaussians, extrinsics: Tensor, intrinsics: Tensor, near: Tensor, 
     B = b * v
     h, w = image_shape
     dev = extrinsics.device
+    if loss_grad is not None and losses:
+        raise ValueError("pass either `losses` or `loss_grad`")
+    if losses:
+        loss_fns = list(losses)
+
+        def loss_grad(color, tgt):  # autograd over the caller's loss list (the sum the reference back-propagates)
+            with torch.enable_grad():
+                c = color.detach().requires_grad_()
+                total = sum(fn(c, tgt) for fn in loss_fns)
+                return torch.autograd.grad(total, c)[0]
     loss_grad = loss_grad or _mse_grad
     K = intrinsics.reshape(B, 3, 3).float().contiguous()
     nr, fr = near.reshape(B).float().contiguous(), far.reshape(B).float().contiguous()
@@ -59,8 +75,9 @@ def pose_align(gaussians, extrinsics: Tensor, intrinsics: Tensor, near: Tensor, 
     vv = torch.zeros(B, 6, device=dev)
     t = torch.zeros((), device=dev)
     lr = torch.tensor([trans_lr] * 3 + [rot_lr] * 3, device=dev)  # tau = (rho, theta)
-    losses = torch.zeros(steps, device=dev)
+    loss_hist = torch.zeros(steps, device=dev)
     it = torch.zeros((), dtype=torch.long, device=dev)
+    overflowed = torch.zeros(1, dtype=torch.int64, device=dev)  # sticky across graph replays (any iteration, not the last)
 
     # capacity from one synchronous probe
     cam = camera_setup(w2c, K, nr, fr, scale_invariant, input_is_w2c=True)
@@ -75,8 +92,9 @@ def pose_align(gaussians, extrinsics: Tensor, intrinsics: Tensor, near: Tensor, 
         c = camera_setup(w2c, K, nr, fr, scale_invariant, input_is_w2c=True)
         plan = _rz.RasterPlan(tensors(c), S, P, B, w, h, M, degree, 9, cap)
         plan.launch()
+        overflowed.bitwise_or_(plan.ctx.view("status")[1:2])
         g_color = loss_grad(plan.color, target)
-        losses.index_put_((it,), ((plan.color - target) ** 2).mean())
+        loss_hist.index_put_((it,), ((plan.color - target) ** 2).mean())
         g = _rz.backward_raw(plan.ctx, g_color, None, need_pose=True, only_pose=True)["tau"]
         # Adam on parameters that are reset to zero every step (torch.optim.Adam semantics)
         t.add_(1.0)
@@ -101,10 +119,10 @@ def pose_align(gaussians, extrinsics: Tensor, intrinsics: Tensor, near: Tensor, 
             plan = iteration()
         for _ in range(steps - 1):  # capture records but does not execute
             graph.replay()
-        torch.cuda.synchronize(dev)
-        if plan.ctx.status()["overflow"]:
-            raise _rz._lib.S3RError("pose_align: instance capacity overflowed; re-run with use_graph=False")
     else:
         for _ in range(steps):
             iteration()
-    return w2c.inverse().reshape(b, v, 4, 4), losses
+    if int(overflowed.item()):  # an iteration that dropped instances corrupts every later Adam step
+        raise _rz._lib.S3RError("pose_align: the instance capacity overflowed during an iteration (poses moved the "
+                                "scene into more tiles than the probe saw); re-run - the capacity hint has grown")
+    return w2c.inverse().reshape(b, v, 4, 4), loss_hist

@@ -214,10 +214,11 @@ class RasterPlan:
         self.ctx = RasterContext(self.prm, lay, self.state, cap, tensors, V, S, P, W, H)
 
     def launch(self, stage_mask: int = STAGE_ALL):
-        stream = C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
-        _lib.check(_lib.lib().s3r_raster_forward_stages(self.prm, self.out, _ptr(self.state),
-                                                        self.ctx.layout.total_bytes, self.cap, stage_mask, stream),
-                   "s3r_raster_forward")
+        with torch.cuda.device(self.dev):  # the C entry points launch on the CURRENT device: make it the tensors' device
+            stream = C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
+            _lib.check(_lib.lib().s3r_raster_forward_stages(self.prm, self.out, _ptr(self.state),
+                                                            self.ctx.layout.total_bytes, self.cap, stage_mask, stream),
+                       "s3r_raster_forward")
 
 
 def backward_raw(ctx: RasterContext, dL_dcolor, dL_ddepth=None, *, need_pose: bool = True, only_pose: bool = False):
@@ -245,9 +246,10 @@ def backward_raw(ctx: RasterContext, dL_dcolor, dL_ddepth=None, *, need_pose: bo
         dL_dshs=_ptr(g["shs"]), dL_dcolors=_ptr(g["colors"]), dL_dopacities=_ptr(g["opacities"]),
         dL_dmeans2D=_ptr(g["means2D"]), dL_dtau=_ptr(g["tau"]) if need_pose else None, scratch=_ptr(scratch),
         scratch_bytes=nbytes)
-    stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-    _lib.check(L.s3r_raster_backward(prm, _ptr(ctx.state), ctx.layout.total_bytes, ctx.capacity, grads, stream),
-               "s3r_raster_backward")
+    with torch.cuda.device(dev):
+        stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        _lib.check(L.s3r_raster_backward(prm, _ptr(ctx.state), ctx.layout.total_bytes, ctx.capacity, grads, stream),
+                   "s3r_raster_backward")
     return g
 
 
@@ -266,18 +268,25 @@ class _Rasterize(torch.autograd.Function):
             want_n_touched=cfg.get("want_n_touched", False), capacity=cfg.get("capacity"),
             check=cfg.get("check", "sync"))
         ctx.rctx = rctx
+        # the kernels reach the inputs through raw pointers (RasterContext.keep), which bypasses autograd's version
+        # counters: remember the versions and refuse to differentiate through tensors that were modified in place since
+        ctx.versions = [(t, t._version) for t in (means, cov, opacities, shs, colors_precomp) if t is not None]
         ctx.cov_shape = cov.shape
         ctx.m2d_shape = None if means2D is None else means2D.shape
         ctx.has = (shs is not None, colors_precomp is not None, rho is not None, theta is not None)
         if n_touched is None:
             n_touched = torch.empty(0, dtype=torch.int32, device=means.device)
         ctx.mark_non_differentiable(opacity, radii, n_touched)
-        cfg["_ctx"] = rctx
         return color, depth, opacity, radii, n_touched
 
     @staticmethod
     def backward(ctx, g_color, g_depth, *_):
         rctx = ctx.rctx
+        for t, ver in ctx.versions:
+            if t._version != ver:
+                raise RuntimeError("one of the tensors given to the rasterizer (means / covariances / opacities / SH) was "
+                                   "modified in place between forward and backward; its gradient would be computed from "
+                                   "the new values")
         has_sh, has_col, has_rho, has_theta = ctx.has
         g = backward_raw(rctx, g_color, g_depth, need_pose=has_rho or has_theta)
         g_m2d = None if ctx.m2d_shape is None else g["means2D"].reshape(ctx.m2d_shape)

@@ -49,6 +49,12 @@ class _FrozenVGG(nn.Module):
     def vgg(self) -> VGGEncoder:
         return self._vgg
 
+    def load_vgg19_features(self, source) -> "_FrozenVGG":
+        """The VGG is deliberately outside state_dict() (like the reference's non-persistent buffers), so checkpoints do
+        not carry it: load torchvision VGG-19 weights explicitly (state dict or .pth path)."""
+        self._vgg.load_vgg19_features(source)
+        return self
+
     def _apply(self, fn, recurse=True):
         self._vgg._apply(fn)
         self._vgg._prep = None

@@ -1,8 +1,11 @@
 """VGG-19 feature encoder of the style / identity losses - mirror of `VGGEncoder` and
 `calc_mean_std` (src/test/vgg_model.py:19-28,79-98): features relu1_1, relu2_1, relu3_1, relu4_1 of ImageNet-normalised
 images.  The four slices keep torchvision's `vgg19().features` indices as sub-module names (`slice1.0`, `slice2.2`,
-`slice2.5`, `slice3.7`, `slice3.10`, `slice4.12/14/16/19`), i.e. the names under which the reference's checkpoints
-carry these (frozen) weights.  No download: weights are whatever the caller loads (random by default).
+`slice2.5`, `slice3.7`, `slice3.10`, `slice4.12/14/16/19`).  The reference builds them from
+`torchvision.models.vgg19(pretrained=True)` (a download) and registers them as NON-persistent buffers, so its
+checkpoints do NOT contain them; here they are loaded explicitly with `load_vgg19_features()` (a torchvision `vgg19`
+state dict / `.pth` file, keys `features.N.weight|bias` or `N.weight|bias`).  Running the encoder with weights that
+were never loaded raises a warning once: the losses would be computed on random features.
 
 B200 path (`fast=True`, CUDA): every 3x3 convolution (+ bias + ReLU) is ONE launch of the tcgen05 implicit-GEMM kernel
 (`conv.conv2d_nhwc`) in bf16 NHWC with fp32 accumulation, and so is its backward: the weights are frozen, so only the
@@ -82,6 +85,42 @@ class VGGEncoder(nn.Module):
         self.requires_grad_(False)
         self.fast = fast
         self._prep = None
+        self._loaded = False
+        self._warned = False
+        # any load_state_dict() (ours or a parent module's) invalidates the cached bf16 operands of the fast path
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module._invalidate(loaded=True))
+
+    def _invalidate(self, loaded: bool = False):
+        self._prep = None
+        if loaded:
+            self._loaded = True
+
+    def _param_versions(self):
+        return tuple(p._version for p in self.parameters())
+
+    def load_vgg19_features(self, source) -> "VGGEncoder":
+        """Load the 9 convolutions up to relu4_1 from a torchvision VGG-19 state dict (or a path to one):
+        keys `features.{0,2,5,7,10,12,14,16,19}.{weight,bias}` (full model) or `{0,...}.{weight,bias}` (`.features`)."""
+        sd = torch.load(source, map_location="cpu") if isinstance(source, (str, bytes)) or hasattr(source, "__fspath__") else source
+        sd = {k[len("features."):] if k.startswith("features.") else k: v for k, v in sd.items()}
+        mods = {}
+        for sl, (a, b) in zip((self.slice1, self.slice2, self.slice3, self.slice4), SLICES):
+            for idx, m in zip(range(a, b), sl):
+                if isinstance(m, nn.Conv2d):
+                    mods[idx] = m
+        missing = [f"{i}.{n}" for i in mods for n in ("weight", "bias") if f"{i}.{n}" not in sd]
+        if missing:
+            raise KeyError(f"VGG-19 state dict lacks {missing}")
+        with torch.no_grad():
+            for i, m in mods.items():
+                m.weight.copy_(sd[f"{i}.weight"])
+                m.bias.copy_(sd[f"{i}.bias"])
+        self._invalidate(loaded=True)
+        return self
+
+    def mark_weights_loaded(self) -> None:
+        """For callers that fill the parameters by other means (tests: name-derived weights)."""
+        self._invalidate(loaded=True)
 
     # ---- reference semantics (fp32 torch ops; also the numerics reference of the fast path)
     def forward_reference(self, images: Tensor, output_last_feature: bool = False):
@@ -106,11 +145,11 @@ class VGGEncoder(nn.Module):
             else:
                 w_bwd = w.flip(2, 3).transpose(0, 1).contiguous()  # dgrad filter: [Cin, Cout, kh, kw], flipped
                 prep.append((prep_conv_weight(w), prep_conv_weight(w_bwd), b))
-        self._prep = (device, prep)
+        self._prep = (device, prep, self._param_versions())
 
     def _forward_fast(self, images: Tensor):
         from ..gemm import linear
-        if self._prep is None or self._prep[0] != images.device:
+        if self._prep is None or self._prep[0] != images.device or self._prep[2] != self._param_versions():
             self._prepare(images.device)
         prep = self._prep[1]
         B, _, H, W = images.shape
@@ -131,6 +170,12 @@ class VGGEncoder(nn.Module):
 
     def forward(self, images: Tensor, output_last_feature: bool = False):
         """Returns NCHW feature maps like the reference (views of the NHWC buffers on the fast path, fp32)."""
+        if not self._loaded and not self._warned:
+            import warnings
+            warnings.warn("VGGEncoder is running with weights that were never loaded (random initialisation): style / "
+                          "identity losses are meaningless until load_vgg19_features() or load_state_dict() is called",
+                          RuntimeWarning, stacklevel=2)
+            self._warned = True
         if self.fast and images.is_cuda and _fast_supported(*images.shape[-2:]):
             feats = [f.permute(0, 3, 1, 2).float() for f in self._forward_fast(images)]
             return feats[-1] if output_last_feature else tuple(feats)

@@ -73,3 +73,21 @@ def test_pose_align_graph_equals_eager_iterations():
     b, lb = pose_align(g, pert, intr, near, far, (64, 64), target, steps=8, use_graph=False)
     np.testing.assert_allclose(la.cpu().numpy(), lb.cpu().numpy(), rtol=1e-3)
     np.testing.assert_allclose(a.cpu().numpy(), b.cpu().numpy(), atol=1e-4)
+
+
+def test_pose_align_takes_the_configured_loss_list():
+    """the reference sums every configured loss.  A list [mse] must equal the default; [mse, 0.5 * l1] must
+    run through autograd inside the captured iteration and still converge."""
+    import torch
+    from styl3r_b200.pose_align import pose_align
+    g, _, pert, intr, near, far, target, _ = _setup()
+    mse = lambda c, t: ((c - t) ** 2).mean()
+    l1 = lambda c, t: 0.5 * (c - t).abs().mean()
+    a, la = pose_align(g, pert, intr, near, far, (64, 64), target, steps=6)
+    b, lb = pose_align(g, pert, intr, near, far, (64, 64), target, steps=6, losses=[mse])
+    np.testing.assert_allclose(a.cpu().numpy(), b.cpu().numpy(), atol=1e-5)
+    c, lc = pose_align(g, pert, intr, near, far, (64, 64), target, steps=25, rot_lr=0.003, trans_lr=0.003, losses=[mse, l1])
+    lc = lc.cpu().numpy()
+    assert lc[-1] < 0.6 * lc[0]
+    with pytest.raises(ValueError):
+        pose_align(g, pert, intr, near, far, (64, 64), target, steps=2, losses=[mse], loss_grad=lambda c, t: c - t)

@@ -180,3 +180,44 @@ def test_compute_psnr_matches_reference_formula():
     a, b = torch.rand(3, 3, 8, 8, generator=g) * 1.2 - 0.1, torch.rand(3, 3, 8, 8, generator=g)
     ref = -10 * ((a.clip(0, 1) - b.clip(0, 1)) ** 2).mean(dim=(1, 2, 3)).log10()
     assert torch.allclose(compute_psnr(a, b), ref)
+
+
+def test_vgg_weights_loader_and_never_loaded_warning():
+    """the reference's VGG comes from torchvision (non-persistent buffers, absent from checkpoints) - the losses
+    need an explicit loader, must warn when they run on never-loaded weights, and cached operands must follow reloads."""
+    import warnings
+    import torch
+    from styl3r_b200.train import IdentityLoss, VGGEncoder
+    from styl3r_b200.train.vgg import VGG19_CFG
+    g = torch.Generator().manual_seed(0)
+    sd = {}
+    for item in VGG19_CFG:
+        if item != "M":
+            i, cin, cout = item
+            sd[f"features.{i}.weight"] = torch.randn(cout, cin, 3, 3, generator=g) * 0.05
+            sd[f"features.{i}.bias"] = torch.randn(cout, generator=g) * 0.01
+    sd["features.21.weight"] = torch.zeros(1)  # deeper layers of the full model are ignored
+    img = torch.rand(1, 3, 32, 32, generator=g)
+    vgg = VGGEncoder(fast=False)
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        vgg(img)
+        vgg(img)
+    assert sum(issubclass(x.category, RuntimeWarning) for x in w) == 1   # warned once
+    vgg.load_vgg19_features(sd)
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        f = vgg(img)
+    assert not w
+    ref = torch.relu(torch.nn.functional.conv2d(img, sd["features.0.weight"], sd["features.0.bias"], padding=1))
+    assert torch.allclose(f[0], ref, atol=1e-6)
+    with pytest.raises(KeyError):
+        VGGEncoder(fast=False).load_vgg19_features({"features.0.weight": sd["features.0.weight"]})
+    loss = IdentityLoss(fast=False)
+    assert "vgg" not in "".join(loss.state_dict().keys())        # like the reference: not part of checkpoints
+    loss.load_vgg19_features(sd)
+    assert torch.equal(loss.vgg.slice1[0].weight, sd["features.0.weight"])
+    # the fast path's cached operands are keyed on the parameter versions: an in-place reload invalidates them
+    v0 = loss.vgg._param_versions()
+    loss.vgg.load_vgg19_features(sd)
+    assert loss.vgg._param_versions() != v0 and loss.vgg._prep is None
