@@ -202,6 +202,7 @@ int s3r_rope2d(void* tokens, const int64_t* pos, int32_t B, int32_t N, int32_t H
 #define S3R_EPI_ROPE 16
 #define S3R_EPI_RELU 32
 #define S3R_EPI_DGELU 128 /* C = acc * gelu'(aux): backward of a fused GELU, aux = the saved pre-activation [M, N] bf16 */
+#define S3R_EPI_RES_F32 512 /* the residual operand is fp32 [M, N] (ldr in fp32 elements): fp32 residual stream of the ViT trunks */
 #define S3R_EPI_SAVE_PRE 256 /* internal: set when s3r_gemm_bf16_majors is given pre_out */
 #define S3R_EPI_PDL 64 /* internal: set by the launcher when programmatic dependent launch is enabled (S3R_TUNE_PDL) */
 int s3r_gemm_bf16(const void* A, const void* W, const void* bias, const void* residual, void* C, int32_t M,
@@ -287,6 +288,9 @@ int s3r_upsample2x_nhwc_bf16(const void* x, const void* add, void* y, int32_t n,
  * ------------------------------------------------------------------------ */
 int s3r_layernorm_bf16(const void* x, const void* weight, const void* bias, void* y, int32_t M, int32_t C, int64_t ldx,
                        float eps, void* stream);
+/* Same, x in fp32 (the residual stream of the inference layout is kept in fp32; y is the bf16 GEMM operand). */
+int s3r_layernorm_f32_bf16(const float* x, const void* weight, const void* bias, void* y, int32_t M, int32_t C, int64_t ldx,
+                           float eps, void* stream);
 /* Backward of the same LayerNorm (autograd of nn.LayerNorm in the reference): dx [M, C] bf16 from x (row pitch ldx),
  * weight and dy [M, C] (contiguous); dweight / dbias [C] fp32 are ACCUMULATED with atomicAdd (caller zero-fills; either
  * may be NULL).  Statistics are recomputed from x.  C % 256 == 0, C <= 1024. */

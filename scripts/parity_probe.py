@@ -71,8 +71,10 @@ def encoder():
         ref, scale = g[f"b1v2_{name}"], float(g[f"b1v2_{name}_stats"][2])
         e = np.abs(sample(tt) - ref)
         res[f"tf32_eager_{name}"] = dict(max_over_sigma=float(e.max() / scale), mean_over_sigma=float(e.mean() / scale))
-    for variant in ("tcgen05", "cudnn"):
-        fast = copy.deepcopy(enc).to_inference(torch.bfloat16, heads=variant)
+    from styl3r_b200.encoder import vit
+    for variant in ("tcgen05", "tcgen05_bf16stream", "cudnn"):
+        vit.STREAM_FP32 = variant != "tcgen05_bf16stream"
+        fast = copy.deepcopy(enc).to_inference(torch.bfloat16, heads="cudnn" if variant == "cudnn" else "tcgen05")
         dump = {}
         with torch.no_grad():
             ob = fast(context, style, visualization_dump=dump)
@@ -112,6 +114,7 @@ def encoder():
         res[f"{variant}_render"] = dict(max_abs=float(d.max()), mean_abs=float(d.mean()), p99=float(torch.quantile(d.flatten()[::7], 0.99)),
                                         psnr_db=float(10 * np.log10(peak * peak / max(mse, 1e-30))), peak=peak,
                                         coverage=float((ca.abs().sum(1) > 0).float().mean()))
+    vit.STREAM_FP32 = True
     print(json.dumps(res, indent=1))
 
 

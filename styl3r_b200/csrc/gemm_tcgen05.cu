@@ -440,7 +440,15 @@ s3r_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         }
       }
       if (row < M && col < N) {
-        if (has_res) {
+        if (has_res && (flags & S3R_EPI_RES_F32)) {  // fp32 residual stream (ldr in fp32 elements)
+          const float* rp = reinterpret_cast<const float*>(residual) + (size_t)row * ldr + col;
+          if (full4) {
+            const float4 r4 = *reinterpret_cast<const float4*>(rp);
+            f[0] += r4.x; f[1] += r4.y; f[2] += r4.z; f[3] += r4.w;
+          } else {
+            for (int j = 0; j < 4 && col + j < N; j++) f[j] += rp[j];
+          }
+        } else if (has_res) {
           const __nv_bfloat16* rp = residual + (size_t)row * ldr + col;
           if (full4) {
             const uint2 u = *reinterpret_cast<const uint2*>(rp);

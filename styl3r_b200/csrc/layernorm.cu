@@ -10,7 +10,8 @@
 #define LN_WARPS 4
 #define LN_MAX_VEC 8  // 8 x (32 lanes x 8 bf16) = 2048 channels
 
-__global__ void __launch_bounds__(32 * LN_WARPS) s3r_layernorm_kernel(const __nv_bfloat16* __restrict__ x,
+template <typename Tin>
+__global__ void __launch_bounds__(32 * LN_WARPS) s3r_layernorm_kernel(const Tin* __restrict__ x,
                                                                       const __nv_bfloat16* __restrict__ w,
                                                                       const __nv_bfloat16* __restrict__ b,
                                                                       __nv_bfloat16* __restrict__ y, int M, int C,
@@ -22,19 +23,32 @@ __global__ void __launch_bounds__(32 * LN_WARPS) s3r_layernorm_kernel(const __nv
   const int row = blockIdx.x * LN_WARPS + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= M) return;
   const int nvec = C / 256;  // full 32-lane x 8-element vectors per row (C % 256 == 0)
-  const uint4* xr = reinterpret_cast<const uint4*>(x + (long long)row * ldx);
   float v[LN_MAX_VEC][8];
   float sum = 0.f;
+  if (sizeof(Tin) == 4) {  // fp32 residual stream: two 16-byte loads per 8 elements
+    const float4* xr = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(x) + (long long)row * ldx);
 #pragma unroll
-  for (int i = 0; i < LN_MAX_VEC; i++) {
-    if (i < nvec) {
-      const uint4 u = xr[i * 32 + lane];
-      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+    for (int i = 0; i < LN_MAX_VEC; i++) {
+      if (i < nvec) {
+        const float4 a = xr[(i * 32 + lane) * 2], b2 = xr[(i * 32 + lane) * 2 + 1];
+        v[i][0] = a.x, v[i][1] = a.y, v[i][2] = a.z, v[i][3] = a.w;
+        v[i][4] = b2.x, v[i][5] = b2.y, v[i][6] = b2.z, v[i][7] = b2.w;
+        sum += (a.x + a.y) + (a.z + a.w) + (b2.x + b2.y) + (b2.z + b2.w);
+      }
+    }
+  } else {
+    const uint4* xr = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(x) + (long long)row * ldx);
 #pragma unroll
-      for (int t = 0; t < 4; t++) {
-        const float2 f = __bfloat1622float2(h[t]);
-        v[i][2 * t] = f.x, v[i][2 * t + 1] = f.y;
-        sum += f.x + f.y;
+    for (int i = 0; i < LN_MAX_VEC; i++) {
+      if (i < nvec) {
+        const uint4 u = xr[i * 32 + lane];
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+          const float2 f = __bfloat1622float2(h[t]);
+          v[i][2 * t] = f.x, v[i][2 * t + 1] = f.y;
+          sum += f.x + f.y;
+        }
       }
     }
   }
@@ -76,8 +90,9 @@ __global__ void __launch_bounds__(32 * LN_WARPS) s3r_layernorm_kernel(const __nv
   }
 }
 
-extern "C" int s3r_layernorm_bf16(const void* x, const void* weight, const void* bias, void* y, int32_t M, int32_t C,
-                                  int64_t ldx, float eps, void* stream) {
+template <typename Tin>
+static int launch_layernorm(const Tin* x, const void* weight, const void* bias, void* y, int32_t M, int32_t C, int64_t ldx,
+                            float eps, void* stream) {
   if (M < 0 || C <= 0 || ldx < C) return S3R_ERR_INVALID_ARG;
   if (M == 0) return S3R_OK;
   if (!x || !weight || !bias || !y) return S3R_ERR_INVALID_ARG;
@@ -95,9 +110,19 @@ extern "C" int s3r_layernorm_bf16(const void* x, const void* weight, const void*
     cfg.attrs = attr;
     cfg.numAttrs = 1;
   }
-  S3R_CUDA_CHECK(cudaLaunchKernelEx(&cfg, s3r_layernorm_kernel, (const __nv_bfloat16*)x, (const __nv_bfloat16*)weight,
+  S3R_CUDA_CHECK(cudaLaunchKernelEx(&cfg, s3r_layernorm_kernel<Tin>, x, (const __nv_bfloat16*)weight,
                                     (const __nv_bfloat16*)bias, (__nv_bfloat16*)y, (int)M, (int)C, (long long)ldx, eps, pdl));
   return S3R_OK;
+}
+
+extern "C" int s3r_layernorm_bf16(const void* x, const void* weight, const void* bias, void* y, int32_t M, int32_t C,
+                                  int64_t ldx, float eps, void* stream) {
+  return launch_layernorm((const __nv_bfloat16*)x, weight, bias, y, M, C, ldx, eps, stream);
+}
+
+extern "C" int s3r_layernorm_f32_bf16(const float* x, const void* weight, const void* bias, void* y, int32_t M, int32_t C,
+                                      int64_t ldx, float eps, void* stream) {
+  return launch_layernorm(x, weight, bias, y, M, C, ldx, eps, stream);
 }
 
 // ------------------------------------------------------------------------------------------------ backward

@@ -26,7 +26,7 @@ from torch import Tensor, nn
 
 from .. import _lib
 from ..streams import fork_join
-from .dpt import PixelwiseDPT
+from .dpt import HOOKS, PixelwiseDPT
 from .vit import CroCoTrunk, _lin, _ln
 
 
@@ -93,6 +93,12 @@ class EncoderNoPoSplatTokenStyleCfg:
     stylized: bool = False
 
 
+def _feature(t: Tensor, dtype: torch.dtype) -> Tensor:
+    """Feature maps handed to the DPT heads carry the trunk's operand dtype (the fp32 residual stream of the inference
+    layout is rounded once here)."""
+    return t if t.dtype == dtype else t.to(dtype)
+
+
 class AsymmetricCroCoMulti(CroCoTrunk):
     """Backbone: shared ViT-L encoder over all context views (+ intrinsics token) and two cross-view decoders —
     `dec_blocks` for view 0, `dec_blocks2` for views 1..v-1 (backbone_croco_multiview.py:51-227)."""
@@ -136,7 +142,7 @@ class AsymmetricCroCoMulti(CroCoTrunk):
         are independent given the previous layer's output and run as concurrent branches (streams.fork_join)."""
         b, v = feat.shape[:2]
         outs = [feat]
-        cur = _lin(self.decoder_embed, feat)
+        cur = _lin(self.decoder_embed, feat, stream=True)
         pos_ctx = self._others(pos)
         blocks2 = self.dec_blocks2 if self.asymmetric else self.dec_blocks
         for blk1, blk2 in zip(self.dec_blocks, blocks2):
@@ -154,7 +160,8 @@ class AsymmetricCroCoMulti(CroCoTrunk):
             cur = torch.cat(parts, dim=1)
             outs.append(cur)
         outs[-1] = _ln(self.dec_norm, outs[-1])
-        return [o[:, :, :-1] for o in outs]  # drop the intrinsics token
+        # drop the intrinsics token; only the layers the DPT heads hook are converted
+        return [_feature(o[:, :, :-1], feat.dtype) if i in HOOKS else o[:, :, :-1] for i, o in enumerate(outs)]
 
     def forward(self, context: dict):
         img = context["image"]
@@ -182,13 +189,13 @@ class TokenStylizer(CroCoTrunk):
                parallel: bool = False) -> List[Tensor]:
         b, v, l, _ = content_feat.shape
         outs = [content_feat]
-        x = _lin(self.decoder_embed, content_feat.reshape(b, v * l, -1))
+        x = _lin(self.decoder_embed, content_feat.reshape(b, v * l, -1), stream=True)
         xpos = content_pos.reshape(b, v * l, 2)
         for blk in self.dec_blocks:
             x = blk(x, y, xpos, spos, parallel=parallel)
             outs.append(x.reshape(b, v, l, -1))
         outs[-1] = _ln(self.dec_norm, x).reshape(b, v, l, -1)
-        return [o[:, :, :-1] for o in outs]
+        return [_feature(o[:, :, :-1], content_feat.dtype) if i in HOOKS else o[:, :, :-1] for i, o in enumerate(outs)]
 
 
 class UnifiedGaussianAdapter(nn.Module):

@@ -50,11 +50,21 @@ def _fast(layer: nn.Linear, x: Tensor) -> bool:
             and not _ops.FORCE_LIBRARY)
 
 
-def _lin(layer: nn.Linear, x: Tensor, residual: Tensor | None = None, gelu: bool = False) -> Tensor:
+# Inference layout: the residual stream of the trunks (patch embedding -> blocks -> decoder blocks) is kept in fp32 -
+# the proj / fc2 GEMMs add an fp32 residual and write fp32, LayerNorm reads fp32 and emits the bf16 GEMM operand - so
+# that only GEMM / attention OPERANDS are rounded to bf16 (fresh rounding per layer) instead of the stream itself
+# (rounding that accumulates over 36 layers).  Costs 2 extra bytes per stream element; measured effect in DESIGN.md §4.
+STREAM_FP32 = True
+
+
+def _lin(layer: nn.Linear, x: Tensor, residual: Tensor | None = None, gelu: bool = False, stream: bool = False) -> Tensor:
     """y = act(layer(x)) + residual.  bf16 inference layout (to_inference): one tcgen05 GEMM with the bias, exact
-    GELU and residual add fused in its epilogue; otherwise (fp32 / training) the torch ops of the reference."""
+    GELU and residual add fused in its epilogue; otherwise (fp32 / training) the torch ops of the reference.
+    `stream`: the result starts a residual stream (fp32 in the inference layout when STREAM_FP32)."""
     if _fast(layer, x):
-        return _gemm.linear(x, layer.weight, layer.bias, residual=residual, gelu=gelu)
+        f32 = STREAM_FP32 and ((residual is not None and residual.dtype == torch.float32) or stream)
+        return _gemm.linear(x, layer.weight, layer.bias, residual=residual, gelu=gelu,
+                            out_dtype=torch.float32 if f32 else torch.bfloat16)
     if _train(x) and not gelu and layer.in_features % 8 == 0 and layer.out_features % 8 == 0:
         return _tops.linear(_bf16(x), layer, residual=None if residual is None else _bf16(residual))
     y = layer(x)
@@ -69,7 +79,7 @@ def _ln(norm: nn.LayerNorm, x: Tensor) -> Tensor:
     C_ = x.shape[-1]
     if _train(x) and C_ % 256 == 0 and C_ <= 1024:
         return _tops.layer_norm(_bf16(x), norm)
-    if (not _ops.FORCE_LIBRARY and x.dtype == torch.bfloat16 and norm.weight.dtype == torch.bfloat16
+    if (not _ops.FORCE_LIBRARY and x.dtype in (torch.bfloat16, torch.float32) and norm.weight.dtype == torch.bfloat16
             and not torch.is_grad_enabled() and x.is_cuda
             and C_ % 256 == 0 and C_ <= 2048):
         import ctypes as C
@@ -78,7 +88,8 @@ def _ln(norm: nn.LayerNorm, x: Tensor) -> Tensor:
         if x2.stride(1) != 1 or x2.stride(0) % 8:
             x2 = x2.contiguous()
         y = torch.empty((x2.shape[0], C_), dtype=torch.bfloat16, device=x.device)
-        _lib.check(_lib.lib().s3r_layernorm_bf16(C.c_void_p(x2.data_ptr()), C.c_void_p(norm.weight.data_ptr()),
+        fn = _lib.lib().s3r_layernorm_f32_bf16 if x.dtype == torch.float32 else _lib.lib().s3r_layernorm_bf16
+        _lib.check(fn(C.c_void_p(x2.data_ptr()), C.c_void_p(norm.weight.data_ptr()),
                                                  C.c_void_p(norm.bias.data_ptr()), C.c_void_p(y.data_ptr()), x2.shape[0], C_,
                                                  x2.stride(0), float(norm.eps),
                                                  C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)),
@@ -259,7 +270,8 @@ class PatchEmbed(nn.Module):
             # kernel == stride: the convolution is a GEMM over non-overlapping patches, columns ordered (c, kh, kw)
             # like weight.flatten(1) - one gather copy + the tcgen05 GEMM instead of a cuDNN conv with layout transposes
             cols = img.reshape(B, -1, gh, ph, gw, pw).permute(0, 2, 4, 1, 3, 5).reshape(B * gh * gw, -1)
-            return _gemm.linear(cols, w.flatten(1), self.proj.bias).view(B, gh * gw, -1), pos
+            return _gemm.linear(cols, w.flatten(1), self.proj.bias,
+                                out_dtype=torch.float32 if STREAM_FP32 else torch.bfloat16).view(B, gh * gw, -1), pos
         if _train(img):
             cols = _bf16(img).reshape(B, -1, gh, ph, gw, pw).permute(0, 2, 4, 1, 3, 5).reshape(B * gh * gw, -1)
             y = _tops.LinearFn.apply(cols, w.flatten(1), self.proj.bias, None, None, 0, 100.0)
@@ -308,7 +320,7 @@ class CroCoTrunk(nn.Module):
     def encode(self, img: Tensor, extra_token: Tensor | None = None):
         x, pos = self.patch_embed(img)
         if extra_token is not None:  # intrinsics token appended at position (grid_h, 0)  (…multiview.py:131-135)
-            x = torch.cat((x, extra_token), dim=1)
+            x = torch.cat((x, extra_token.to(x.dtype)), dim=1)
             tok_pos = pos[:, :1].clone()
             tok_pos[:, :, 0] += pos[:, -1:, 0] + 1
             pos = torch.cat((pos, tok_pos), dim=1)

@@ -15,6 +15,7 @@ import torch
 from . import _lib
 
 EPI_BIAS, EPI_GELU, EPI_RESIDUAL, EPI_OUT_F32, EPI_ROPE, EPI_RELU = 1, 2, 4, 8, 16, 32
+EPI_RES_F32 = 512
 ROPE_MAX_POS = 255  # positions are patch-grid coordinates (16 for 256 px, 64 for 1024 px)
 _rope_tables: dict = {}
 _workspaces: dict = {}
@@ -78,7 +79,11 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] =
     if residual is not None:
         flags |= EPI_RESIDUAL
         r2 = residual.reshape(-1, N)
-        if r2.stride(1) != 1 or r2.dtype != torch.bfloat16:
+        if r2.dtype == torch.float32:  # fp32 residual stream (inference layout of the ViT trunks)
+            if r2.stride(1) != 1 or r2.stride(0) % 4:
+                r2 = r2.contiguous()
+            flags |= EPI_RES_F32
+        elif r2.stride(1) != 1 or r2.dtype != torch.bfloat16:
             r2 = r2.to(torch.bfloat16).contiguous()
         rp, ldr = C.c_void_p(r2.data_ptr()), r2.stride(0)
     pp = tp = None
