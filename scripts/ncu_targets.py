@@ -45,5 +45,28 @@ for M in (514, 4112):
 q = torch.randn(2, 257, 3, 16, 64, device=dev).to(torch.bfloat16)
 for _ in range(2):
     memory_efficient_attention(q[:, :, 0], q[:, :, 1], q[:, :, 2], scale=0.125)
+q4 = torch.randn(4, 1028, 3, 12, 64, device=dev).to(torch.bfloat16)
+for _ in range(2):
+    memory_efficient_attention(q4[:, :, 0], q4[:, :, 1], q4[:, :, 2], scale=0.125)
+# LayerNorm forward / backward, backward GEMMs (MN-major operands) and the attention backward (training layout)
+import ctypes as C
+from styl3r_b200 import _lib
+from styl3r_b200.attention_bwd import attention_backward
+from styl3r_b200.encoder import train_ops as T
+from styl3r_b200.gemm import linear_dgrad, linear_wgrad
+ln = torch.nn.LayerNorm(1024, eps=1e-6).to(dev)
+xl = torch.randn(5140, 1024, device=dev).to(torch.bfloat16).requires_grad_()
+for _ in range(2):
+    yl = T.layer_norm(xl, ln)
+    yl.backward(torch.ones_like(yl))
+dy = torch.randn(5140, 3072, device=dev).to(torch.bfloat16)
+w3 = torch.randn(3072, 1024, device=dev).to(torch.bfloat16)
+x3 = torch.randn(5140, 1024, device=dev).to(torch.bfloat16)
+for _ in range(2):
+    linear_dgrad(dy, w3)
+    linear_wgrad(dy, x3)
+o = memory_efficient_attention(q[:, :, 0], q[:, :, 1], q[:, :, 2], scale=0.125)
+for _ in range(2):
+    attention_backward(q[:, :, 0], q[:, :, 1], q[:, :, 2], o, torch.ones_like(o), 0.125)
 torch.cuda.synchronize()
 print("done")
