@@ -1,4 +1,6 @@
-"""Launches each hot kernel a few times so that one `ncu --set full` pass captures them (development aid):
+"""Launches each hot kernel so that one `ncu --set full` pass captures them.  Run it as
+  ncu --set full --import-source on --clock-control none --profile-from-start off -k regex:s3r_ -o OUT python scripts/ncu_targets.py
+(the first pass below is an unprofiled warm-up; the second runs inside cudaProfilerStart/Stop):
 raster forward chain on the bench scene (cfg2), the implicit-GEMM convolution at the gs-head shape, GEMMs at the
 cfg2 / cfg3 qkv shapes, attention at 257 tokens."""
 import sys
@@ -26,47 +28,56 @@ full = (view_t @ proj_t).contiguous()
 tensors = (g["means"], g["cov"], g["opac"], g["sh"].reshape(1, -1, 1, 3), None, view_t, full, proj_t, extr[:, :3, 3].contiguous(),
            (0.5 * fov).tan().contiguous(), scale.contiguous(), torch.zeros(1, 3, device=dev), torch.zeros(1, dtype=torch.int32, device=dev))
 P = g["means"].shape[1]
-plan = rz.RasterPlan(tensors, 1, P, 1, 256, 256, 1, 0, 9, 3 * P)
-for _ in range(3):
-    plan.launch()
+def work(reps):
+    plan = rz.RasterPlan(tensors, 1, P, 1, 256, 256, 1, 0, 9, 3 * P)
+    for _ in range(reps):
+        plan.launch()
+    torch.cuda.synchronize()
+    x = torch.randn(1, 256, 256, 256, device=dev).to(torch.bfloat16)
+    w = prep_conv_weight((torch.randn(256, 256, 3, 3, device=dev) / 48).to(torch.bfloat16))
+    for _ in range(reps):
+        conv2d_nhwc(x, w, (3, 3), relu=True)
+    x64 = torch.randn(1, 64, 64, 256, device=dev).to(torch.bfloat16)
+    for _ in range(reps):
+        conv2d_nhwc(x64, w, (3, 3), relu=True)
+    for M in (514, 4112):
+        a = torch.randn(M, 1024, device=dev).to(torch.bfloat16); wt = torch.randn(3072, 1024, device=dev).to(torch.bfloat16)
+        b = torch.randn(3072, device=dev).to(torch.bfloat16)
+        for _ in range(reps):
+            linear(a, wt, b)
+    q = torch.randn(2, 257, 3, 16, 64, device=dev).to(torch.bfloat16)
+    for _ in range(reps):
+        memory_efficient_attention(q[:, :, 0], q[:, :, 1], q[:, :, 2], scale=0.125)
+    q4 = torch.randn(4, 1028, 3, 12, 64, device=dev).to(torch.bfloat16)
+    for _ in range(reps):
+        memory_efficient_attention(q4[:, :, 0], q4[:, :, 1], q4[:, :, 2], scale=0.125)
+    # LayerNorm forward / backward, backward GEMMs (MN-major operands) and the attention backward (training layout)
+    import ctypes as C
+    from styl3r_b200 import _lib
+    from styl3r_b200.attention_bwd import attention_backward
+    from styl3r_b200.encoder import train_ops as T
+    from styl3r_b200.gemm import linear_dgrad, linear_wgrad
+    ln = torch.nn.LayerNorm(1024, eps=1e-6).to(dev)
+    xl = torch.randn(5140, 1024, device=dev).to(torch.bfloat16).requires_grad_()
+    for _ in range(reps):
+        yl = T.layer_norm(xl, ln)
+        yl.backward(torch.ones_like(yl))
+    dy = torch.randn(5140, 3072, device=dev).to(torch.bfloat16)
+    w3 = torch.randn(3072, 1024, device=dev).to(torch.bfloat16)
+    x3 = torch.randn(5140, 1024, device=dev).to(torch.bfloat16)
+    for _ in range(reps):
+        linear_dgrad(dy, w3)
+        linear_wgrad(dy, x3)
+    o = memory_efficient_attention(q[:, :, 0], q[:, :, 1], q[:, :, 2], scale=0.125)
+    for _ in range(reps):
+        attention_backward(q[:, :, 0], q[:, :, 1], q[:, :, 2], o, torch.ones_like(o), 0.125)
+    torch.cuda.synchronize()
+
+
+work(2)
 torch.cuda.synchronize()
-x = torch.randn(1, 256, 256, 256, device=dev).to(torch.bfloat16)
-w = prep_conv_weight((torch.randn(256, 256, 3, 3, device=dev) / 48).to(torch.bfloat16))
-for _ in range(2):
-    conv2d_nhwc(x, w, (3, 3), relu=True)
-x64 = torch.randn(1, 64, 64, 256, device=dev).to(torch.bfloat16)
-for _ in range(2):
-    conv2d_nhwc(x64, w, (3, 3), relu=True)
-for M in (514, 4112):
-    a = torch.randn(M, 1024, device=dev).to(torch.bfloat16); wt = torch.randn(3072, 1024, device=dev).to(torch.bfloat16)
-    b = torch.randn(3072, device=dev).to(torch.bfloat16)
-    for _ in range(2):
-        linear(a, wt, b)
-q = torch.randn(2, 257, 3, 16, 64, device=dev).to(torch.bfloat16)
-for _ in range(2):
-    memory_efficient_attention(q[:, :, 0], q[:, :, 1], q[:, :, 2], scale=0.125)
-q4 = torch.randn(4, 1028, 3, 12, 64, device=dev).to(torch.bfloat16)
-for _ in range(2):
-    memory_efficient_attention(q4[:, :, 0], q4[:, :, 1], q4[:, :, 2], scale=0.125)
-# LayerNorm forward / backward, backward GEMMs (MN-major operands) and the attention backward (training layout)
-import ctypes as C
-from styl3r_b200 import _lib
-from styl3r_b200.attention_bwd import attention_backward
-from styl3r_b200.encoder import train_ops as T
-from styl3r_b200.gemm import linear_dgrad, linear_wgrad
-ln = torch.nn.LayerNorm(1024, eps=1e-6).to(dev)
-xl = torch.randn(5140, 1024, device=dev).to(torch.bfloat16).requires_grad_()
-for _ in range(2):
-    yl = T.layer_norm(xl, ln)
-    yl.backward(torch.ones_like(yl))
-dy = torch.randn(5140, 3072, device=dev).to(torch.bfloat16)
-w3 = torch.randn(3072, 1024, device=dev).to(torch.bfloat16)
-x3 = torch.randn(5140, 1024, device=dev).to(torch.bfloat16)
-for _ in range(2):
-    linear_dgrad(dy, w3)
-    linear_wgrad(dy, x3)
-o = memory_efficient_attention(q[:, :, 0], q[:, :, 1], q[:, :, 2], scale=0.125)
-for _ in range(2):
-    attention_backward(q[:, :, 0], q[:, :, 1], q[:, :, 2], o, torch.ones_like(o), 0.125)
+torch.cuda.profiler.start()
+work(1)
 torch.cuda.synchronize()
+torch.cuda.profiler.stop()
 print("done")
