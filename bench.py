@@ -360,10 +360,11 @@ def run_ours(args):
     for s in slots:
         sc = s["sc"]
         pin = lambda a: torch.as_tensor(np.ascontiguousarray(a)).pin_memory()
-        host.append(dict(means=pin(sc["means"][None]), cov=pin(sc["covariances"][None]), sh=pin(sc["harmonics"][None]),
+        triu = sc["covariances"][:, [0, 0, 0, 1, 1, 2], [0, 1, 2, 1, 2, 2]]  # packed cov3D_precomp layout (cuda_splatting.py:118)
+        host.append(dict(means=pin(sc["means"][None]), cov=pin(sc["covariances"][None]), cov6=pin(triu[None]), sh=pin(sc["harmonics"][None]),
                          opac=pin(sc["opacities"][None]), extr=pin(sc["extrinsics"]), intr=pin(sc["intrinsics"]),
                          near=pin(sc["near"]), far=pin(sc["far"]), bg=torch.zeros(V_TGT, 3).pin_memory()))
-    h2d_bytes = sum(v.numel() * v.element_size() for v in host[0].values())
+    h2d_bytes = sum(v.numel() * v.element_size() for k_, v in host[0].items() if k_ != "cov")  # the session uploads cov6
     d2h_bytes = V_TGT * 3 * HW * HW * 4
 
     # public serving API: one RenderSession per resident request buffer = CUDA graph of
@@ -373,7 +374,7 @@ def run_ours(args):
     n_e2e_streams = max(1, min(args.e2e_streams, n_slots))
     e2e_streams = [torch.cuda.Stream() for _ in range(n_e2e_streams)]
     sessions = [RenderSession(dict(extrinsics=h["extr"], intrinsics=h["intr"], near=h["near"], far=h["far"],
-                                   background=h["bg"], means=h["means"], covariances=h["cov"], harmonics=h["sh"],
+                                   background=h["bg"], means=h["means"], covariances=h["cov6"], harmonics=h["sh"],
                                    opacities=h["opac"]), (HW, HW), scale_invariant=True) for h in host]
 
     def e2e_loop(count):
@@ -552,7 +553,7 @@ def run_ours(args):
                        "parallelism": f"scene-sharded x{world}, no collective"},
             "clocks": clk.summary(),
             "e2e": {"value": e2e_val, "unit": "views/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
-                    "steps": Ke, "api": "styl3r_b200.decoder.RenderSession.run(): pinned host Gaussians+cameras -> H2D -> camera kernel -> "
+                    "steps": Ke, "api": "styl3r_b200.decoder.RenderSession.run(): pinned host Gaussians (covariances as the packed cov3D_precomp triangle the reference hands to its rasterizer) + cameras -> H2D -> camera kernel -> "
                            f"raster chain -> D2H pinned image (one CUDA graph per request buffer, {n_e2e_streams} streams)"},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": "s3r_blend_fwd_kernel", "achieved": achieved, "peak": peak,

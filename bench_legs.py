@@ -137,7 +137,7 @@ def e2e_render_cuda(dev, slots_host, iters=100):
     def step(i=[0]):
         h = slots_host[i[0] % n]
         i[0] += 1
-        d = {k: v.to(dev, non_blocking=True) for k, v in h.items()}
+        d = {k: v.to(dev, non_blocking=True) for k, v in h.items() if k != "cov6"}
         color, depth = render_cuda(d["extr"], d["intr"], d["near"], d["far"], (HW, HW), d["bg"], d["means"], d["cov"], d["sh"],
                                    d["opac"], scale_invariant=True)
         return color.cpu()

@@ -7,6 +7,10 @@ request, more than the GPU work of a 256x256 view).  Same math as `render_cuda` 
 src/model/decoder/cuda_splatting.py:46-61); the inputs are *bound* pinned host tensors which the caller refills
 between launches (zero staging copies).
 
+`host["covariances"]` may be the reference's [S,G,3,3] matrices or the packed upper triangle [S,G,6]
+(xx, xy, xz, yy, yz, zz) - the layout the reference itself hands to the rasterizer (`cov3D_precomp`,
+cuda_splatting.py:118,126): 24 instead of 36 bytes per Gaussian over PCIe.
+
     sess = RenderSession(host)            # host: dict of pinned tensors, see `KEYS`
     sess.run()                            # enqueue on the current stream; sess.color_host holds the image afterwards
     torch.cuda.current_stream().synchronize(); sess.check()
@@ -73,7 +77,8 @@ class RenderSession:
         shs = _sh_layout(d["harmonics"])
         tensors = (d["means"], d["covariances"], d["opacities"], shs, None, view_t, full, proj_t, campos, tan_fov,
                    scale if self.scale_invariant else None, d["background"], self.view_set)
-        return _rz.RasterPlan(tensors, S, P, V, self.w, self.h, shs.shape[2], self.degree, 9, cap)
+        cov_stride = 6 if d["covariances"].dim() == 3 else 9
+        return _rz.RasterPlan(tensors, S, P, V, self.w, self.h, shs.shape[2], self.degree, cov_stride, cap)
 
     def _capture(self):
         side = torch.cuda.Stream(device=self.device)

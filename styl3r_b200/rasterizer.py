@@ -221,10 +221,14 @@ class RasterPlan:
                        "s3r_raster_forward")
 
 
-def backward_raw(ctx: RasterContext, dL_dcolor, dL_ddepth=None, *, need_pose: bool = True, only_pose: bool = False):
+def backward_raw(ctx: RasterContext, dL_dcolor, dL_ddepth=None, *, need_pose: bool = True, only_pose: bool = False,
+                 needs: Optional[dict] = None):
     """Gradients w.r.t. the tensors given to forward_raw. Returns a dict of tensors shaped like the inputs
     (`cov` in the packing it was given), plus dL_dmeans2D [V,P,3] and dL_dtau [V,6] = (rho, theta).
-    only_pose: the pose-align loop needs dL/dtau only — no Gaussian gradient buffers are allocated or written."""
+    only_pose: the pose-align loop needs dL/dtau only — no Gaussian gradient buffers are allocated or written.
+    needs: {"means", "cov", "opacities", "shs", "colors", "means2D"} -> bool (default all True): gradients that are not
+    needed are neither allocated, zero-filled nor accumulated (stage-2 training needs dL/dSH only: the structure heads
+    are frozen, model_wrapper_style.py:854-868)."""
     L = _lib.lib()
     prm = ctx.params
     dev = ctx.state.device
@@ -232,12 +236,14 @@ def backward_raw(ctx: RasterContext, dL_dcolor, dL_ddepth=None, *, need_pose: bo
     M, cs = prm.sh_coeffs, prm.cov_stride
     dL_dcolor = _f32c(dL_dcolor)
     dL_ddepth = _f32c(dL_ddepth) if dL_ddepth is not None else None
-    z = (lambda *shape: None) if only_pose else (lambda *shape: torch.zeros(*shape, device=dev))
+    needs = needs or {}
+    want = lambda k: not only_pose and needs.get(k, True)
+    z = lambda k, *shape: torch.zeros(*shape, device=dev) if want(k) else None
     g = dict(
-        means=z(S, P, 3), cov=z(S, P, cs), opacities=z(S, P), means2D=z(V, P, 3),
+        means=z("means", S, P, 3), cov=z("cov", S, P, cs), opacities=z("opacities", S, P), means2D=z("means2D", V, P, 3),
         tau=torch.zeros(V, 6, device=dev),
-        shs=z(S, P, M, 3) if prm.shs else None,
-        colors=z(S, P, 3) if prm.colors_precomp else None,
+        shs=z("shs", S, P, M, 3) if prm.shs else None,
+        colors=z("colors", S, P, 3) if prm.colors_precomp else None,
     )
     nbytes = L.s3r_raster_backward_scratch_bytes(V, P)
     scratch = torch.empty(nbytes, dtype=torch.uint8, device=dev)
@@ -288,9 +294,12 @@ class _Rasterize(torch.autograd.Function):
                                    "modified in place between forward and backward; its gradient would be computed from "
                                    "the new values")
         has_sh, has_col, has_rho, has_theta = ctx.has
-        g = backward_raw(rctx, g_color, g_depth, need_pose=has_rho or has_theta)
-        g_m2d = None if ctx.m2d_shape is None else g["means2D"].reshape(ctx.m2d_shape)
-        return (g["means"], g["cov"].reshape(ctx.cov_shape), g["opacities"], g["shs"] if has_sh else None,
+        ni = ctx.needs_input_grad  # (means, cov, opacities, shs, colors_precomp, rho, theta, means2D, cfg)
+        needs = dict(means=ni[0], cov=ni[1], opacities=ni[2], shs=ni[3], colors=ni[4],
+                     means2D=ctx.m2d_shape is not None and ni[7])
+        g = backward_raw(rctx, g_color, g_depth, need_pose=(has_rho and ni[5]) or (has_theta and ni[6]), needs=needs)
+        g_m2d = None if g["means2D"] is None else g["means2D"].reshape(ctx.m2d_shape)
+        return (g["means"], None if g["cov"] is None else g["cov"].reshape(ctx.cov_shape), g["opacities"], g["shs"] if has_sh else None,
                 g["colors"] if has_col else None, g["tau"][:, :3] if has_rho else None,
                 g["tau"][:, 3:] if has_theta else None, g_m2d, None)
 

@@ -122,3 +122,27 @@ def test_autograd_through_render_cuda():
 def test_backward_full_size_cfg2():
     """BASELINE cfg2 size: 131 072 Gaussians, one 256x256 view - every gradient (incl. dL/dtau) against the oracle."""
     run(syn.make_scene(seed=1234, v=2, V=1, hw=256), bg=(0.0, 0.0, 0.0), seed=3)
+
+
+def test_only_requested_gradients_are_computed():
+    """needs_input_grad is honoured: with only the SH coefficients requiring a gradient (stage-2
+    training: frozen structure heads) the other gradient buffers are neither allocated nor accumulated, and dL/dSH
+    equals the one of the full backward."""
+    import torch
+    from styl3r_b200.decoder import render_cuda
+    sc = syn.make_scene(seed=9, v=2, V=2, hw=64)
+    t = lambda a: torch.as_tensor(a).cuda()
+    vs = torch.zeros(2, dtype=torch.int32, device="cuda")
+    target = torch.rand(2, 3, 64, 64, device="cuda", generator=torch.Generator(device="cuda").manual_seed(0))
+
+    def run(req):
+        means, cov, sh, op = (t(sc[k])[None].requires_grad_(k in req) for k in ("means", "covariances", "harmonics", "opacities"))
+        color, _ = render_cuda(t(sc["extrinsics"]), t(sc["intrinsics"]), t(sc["near"]), t(sc["far"]), (64, 64),
+                               torch.zeros(2, 3, device="cuda"), means, cov, sh, op, view_set=vs)
+        ((color - target) ** 2).mean().backward()
+        return means.grad, cov.grad, sh.grad, op.grad
+
+    full = run({"means", "covariances", "harmonics", "opacities"})
+    only = run({"harmonics"})
+    assert only[0] is None and only[1] is None and only[3] is None
+    assert torch.allclose(only[2], full[2], rtol=1e-4, atol=1e-9) and only[2].abs().max() > 0
