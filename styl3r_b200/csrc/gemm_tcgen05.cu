@@ -151,6 +151,21 @@ __device__ __forceinline__ void g_tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// erf for the exact-GELU epilogues: Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, far below the bf16 output rounding)
+// - 5 FMAs + MUFU.RCP + MUFU.EX2 instead of the ~25-instruction branchy erff
+__device__ __forceinline__ float g_fast_erf(float x) {
+  const float ax = fabsf(x);
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));  // MUFU.RCP
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * ax * ax));  // MUFU.EX2
+  const float y = 1.0f - p * t * e;
+  return copysignf(y, x);
+}
+
 template <int BN, int STAGES_>
 struct GemmSmem {
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
@@ -192,7 +207,12 @@ struct ConvArgs {
 // multicasts into (its cluster row and column, CM + CN - 1 CTAs).
 // MAJ: bit 0 = A is MN-major (given as [K, M] row-major), bit 1 = B is MN-major (given as [K, N] row-major) - the
 // dgrad (B = W as stored) and wgrad (A = dY, B = X as stored) GEMMs of the encoder's backward, no transposed copies.
-template <int BN, int STAGES_, bool kConv, int CM = 1, int CN = 1, int MAJ = 0>
+// EPI: compile-time superset of the epilogue features this instantiation can execute (S3R_EPI_* bits; the runtime
+// `flags` select inside it).  The epilogue is issue-bound and every compiled-in feature costs registers and branches even
+// when its flag is off (measured: the three training-only features slowed the inference GEMMs by 15-25 %), so the hot
+// inference shapes are instantiated per feature set and everything else uses the all-features instance.
+#define S3R_EPI_ALL 0xfff
+template <int BN, int STAGES_, bool kConv, int CM = 1, int CN = 1, int MAJ = 0, int EPI = S3R_EPI_ALL>
 __global__ void __launch_bounds__(GEMM_THREADS, (STAGES_ * (GEMM_BM + BN) * GEMM_BK * 2 <= 100 * 1024) ? 2 : 1)
 s3r_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const __nv_bfloat16* __restrict__ bias, const __nv_bfloat16* __restrict__ residual, void* __restrict__ Cout,
@@ -201,6 +221,7 @@ s3r_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);  // SWIZZLE_128B atoms need 1024-B alignment
   using S = GemmSmem<BN, STAGES_>;
+#define EF(X) (((EPI) & (X)) && (flags & (X)))
   constexpr int GEMM_STAGES = S::STAGES;
   uint64_t* full = (uint64_t*)(smem + GEMM_STAGES * S::STAGE_BYTES);
   uint64_t* empty = full + GEMM_STAGES;
@@ -348,7 +369,7 @@ s3r_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     int* spos = reinterpret_cast<int*>(smem + GEMM_STAGES * S::STAGE_BYTES - 2048);  // [128][2] row positions (RoPE)
     g_mbar_wait(tmem_full, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    if (flags & S3R_EPI_ROPE) {
+    if (EF(S3R_EPI_ROPE)) {
       {  // one coalesced read of this tile's 128 (y, x) positions, clamped to the table
         const int prow = m0 + q * 32 + lane;
         long long py = 0, px = 0;
@@ -379,9 +400,9 @@ s3r_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     constexpr int RPI = 128 / LPR;     // rows per iteration of the 128 epilogue threads
     const int cl = (et % LPR) * 4;     // this lane's first column inside the tile
     const int col = n0 + cg * CG + cl;
-    const bool has_bias = flags & S3R_EPI_BIAS, gelu = flags & S3R_EPI_GELU, has_res = flags & S3R_EPI_RESIDUAL,
-               relu = flags & S3R_EPI_RELU,
-               out_f32 = flags & S3R_EPI_OUT_F32, do_rope = (flags & S3R_EPI_ROPE) && col < rope.cols;
+    const bool has_bias = EF(S3R_EPI_BIAS), gelu = EF(S3R_EPI_GELU), has_res = EF(S3R_EPI_RESIDUAL),
+               relu = EF(S3R_EPI_RELU),
+               out_f32 = EF(S3R_EPI_OUT_F32), do_rope = EF(S3R_EPI_ROPE) && col < rope.cols;
     const bool full4 = col + 4 <= N;
     float bias4[4] = {0.f, 0.f, 0.f, 0.f};
     if (has_bias) {
@@ -392,7 +413,7 @@ s3r_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     auto finish = [&](float (&f)[4], int row) {  // f = accumulators of columns col..col+3 of `row`
 #pragma unroll
       for (int j = 0; j < 4; j++) f[j] += bias4[j];
-      if (flags & S3R_EPI_ROPE) {
+      if (EF(S3R_EPI_ROPE)) {
         // pairs (d, d+16) inside each 32-column half head sit 4 lanes apart: exchange with lane ^ 4 (all lanes shuffle)
         float o[4];
 #pragma unroll
@@ -408,7 +429,7 @@ s3r_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           }
         }
       }
-      if ((flags & S3R_EPI_SAVE_PRE) && row < M && col < N) {  // training forward: keep the pre-activation for gelu'
+      if (EF(S3R_EPI_SAVE_PRE) && row < M && col < N) {  // training forward: keep the pre-activation for gelu'
         __nv_bfloat16* pp = reinterpret_cast<__nv_bfloat16*>(ws) + (size_t)row * ldc + col;
         if (full4) {
           uint2 u;
@@ -421,26 +442,26 @@ s3r_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       }
       if (gelu) {
 #pragma unroll
-        for (int j = 0; j < 4; j++) f[j] = 0.5f * f[j] * (1.0f + erff(f[j] * 0.70710678118654752f));
+        for (int j = 0; j < 4; j++) f[j] = 0.5f * f[j] * (1.0f + g_fast_erf(f[j] * 0.70710678118654752f));
       }
       if (relu) {
 #pragma unroll
         for (int j = 0; j < 4; j++) f[j] = fmaxf(f[j], 0.0f);
       }
-      if ((flags & S3R_EPI_DGELU) && row < M && col < N) {
+      if (EF(S3R_EPI_DGELU) && row < M && col < N) {
         // backward of y = gelu(h): f = dL/dy (accumulator) -> dL/dh = f * gelu'(h), h = pre-activation in `residual`
         const __nv_bfloat16* hp = residual + (size_t)row * ldr + col;
 #pragma unroll
         for (int j = 0; j < 4; j++) {
           if (col + j < N) {
             const float h = __bfloat162float(hp[j]);
-            const float cdf = 0.5f * (1.0f + erff(h * 0.70710678118654752f));
+            const float cdf = 0.5f * (1.0f + g_fast_erf(h * 0.70710678118654752f));
             f[j] *= cdf + h * 0.39894228040143268f * __expf(-0.5f * h * h);
           }
         }
       }
       if (row < M && col < N) {
-        if (has_res && (flags & S3R_EPI_RES_F32)) {  // fp32 residual stream (ldr in fp32 elements)
+        if (has_res && EF(S3R_EPI_RES_F32)) {  // fp32 residual stream (ldr in fp32 elements)
           const float* rp = reinterpret_cast<const float*>(residual) + (size_t)row * ldr + col;
           if (full4) {
             const float4 r4 = *reinterpret_cast<const float4*>(rp);
@@ -597,13 +618,13 @@ static int make_map(CUtensorMap* map, const void* ptr, int rows, int cols, int l
   return r == CUDA_SUCCESS ? S3R_OK : S3R_ERR_CUDA;
 }
 
-template <int BN, int STAGES_, bool kConv = false, int CM = 1, int CN = 1, int MAJ = 0>
+template <int BN, int STAGES_, bool kConv = false, int CM = 1, int CN = 1, int MAJ = 0, int EPI = S3R_EPI_ALL>
 static int launch_gemm(const CUtensorMap& a, const CUtensorMap& b, const void* bias, const void* residual, void* C, int M,
                        int N, int K, int ldc, int ldr, int flags, const RopeArgs& rope, int splits, float* ws, unsigned* counters,
                        cudaStream_t st, const ConvArgs& conv = ConvArgs{}, int batch = 0, long long batch_stride_c = 0) {
   static size_t configured[64] = {};  // per device: cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute
   const int smem = GemmSmem<BN, STAGES_>::TOTAL;
-  auto kern = s3r_gemm_bf16_kernel<BN, STAGES_, kConv, CM, CN, MAJ>;
+  auto kern = s3r_gemm_bf16_kernel<BN, STAGES_, kConv, CM, CN, MAJ, EPI>;
   {
     const int rc_ = s3r_ensure_dynamic_smem(kern, (size_t)smem, configured);
     if (rc_ != S3R_OK) return rc_;
@@ -737,6 +758,22 @@ extern "C" int s3r_gemm_bf16_rope(const void* A, const void* W, const void* bias
 #define S3R_GEMM_GO(BN_, ST_, CM_, CN_)                                                                             \
   return launch_gemm<BN_, ST_, false, CM_, CN_>(ta, tb, bias, residual, C, M, N, K, ldc, ldr, flags, rope, splits, ws, \
                                                  counters, st)
+  // the inference feature sets of the ViT trunks get their own instances (no cluster, no split-K)
+  constexpr int E_BASE = S3R_EPI_BIAS | S3R_EPI_OUT_F32 | S3R_EPI_PDL;
+  const int extra = flags & ~E_BASE;
+#define S3R_GEMM_EPI(BN_, ST_)                                                                                          \
+  do {                                                                                                                  \
+    if (cm == 1 && cn == 1 && splits == 1) {                                                                            \
+      if (extra == 0)                                                                                                   \
+        return launch_gemm<BN_, ST_, false, 1, 1, 0, E_BASE>(ta, tb, bias, residual, C, M, N, K, ldc, ldr, flags, rope, 1, ws, counters, st); \
+      if (extra == S3R_EPI_GELU)                                                                                        \
+        return launch_gemm<BN_, ST_, false, 1, 1, 0, E_BASE | S3R_EPI_GELU>(ta, tb, bias, residual, C, M, N, K, ldc, ldr, flags, rope, 1, ws, counters, st); \
+      if (extra == S3R_EPI_RESIDUAL)                                                                                    \
+        return launch_gemm<BN_, ST_, false, 1, 1, 0, E_BASE | S3R_EPI_RESIDUAL>(ta, tb, bias, residual, C, M, N, K, ldc, ldr, flags, rope, 1, ws, counters, st); \
+      if (extra == S3R_EPI_ROPE)                                                                                        \
+        return launch_gemm<BN_, ST_, false, 1, 1, 0, E_BASE | S3R_EPI_ROPE>(ta, tb, bias, residual, C, M, N, K, ldc, ldr, flags, rope, 1, ws, counters, st); \
+    }                                                                                                                   \
+  } while (0)
 #define S3R_GEMM_CLUSTERS(BN_, ST_)                  \
   do {                                               \
     if (cm == 1 && cn == 2) S3R_GEMM_GO(BN_, ST_, 1, 2); \
@@ -747,13 +784,22 @@ extern "C" int s3r_gemm_bf16_rope(const void* A, const void* W, const void* bias
     S3R_GEMM_GO(BN_, ST_, 1, 1);                     \
   } while (0)
   if (BN == 64) {
-    if (tiles64 * splits < 148 && !g_gemm_shallow) S3R_GEMM_CLUSTERS(64, 8);
+    if (tiles64 * splits < 148 && !g_gemm_shallow) {
+      S3R_GEMM_EPI(64, 8);
+      S3R_GEMM_CLUSTERS(64, 8);
+    }
+    S3R_GEMM_EPI(64, 4);
     S3R_GEMM_CLUSTERS(64, 4);
   }
   splits = 1, counters = nullptr;
   if (!t_pre_out) ws = nullptr;
-  if (BN == 256) S3R_GEMM_CLUSTERS(256, 2);
+  if (BN == 256) {
+    S3R_GEMM_EPI(256, 2);
+    S3R_GEMM_CLUSTERS(256, 2);
+  }
+  S3R_GEMM_EPI(128, 3);
   S3R_GEMM_CLUSTERS(128, 3);
+#undef S3R_GEMM_EPI
 #undef S3R_GEMM_CLUSTERS
 #undef S3R_GEMM_GO
 }
