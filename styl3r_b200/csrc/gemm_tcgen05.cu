@@ -13,8 +13,10 @@
 //   warp 1   allocates BN TMEM columns; one elected lane issues 4 x tcgen05.mma (M=128, N=BN, K=16) per k-block from
 //            shared-memory matrix descriptors, releases ring slots with tcgen05.commit -> `empty` mbarriers and signals
 //            the epilogue with a final commit
-//   warps 2-5 epilogue: tcgen05.ld (32 lanes x 32 columns per instruction) TMEM -> registers, + bias, exact GELU,
-//            + residual, -> bf16 (or fp32), 16-byte global stores
+//   warps 2-5 epilogue phase 1: tcgen05.ld (32 lanes x 32 columns per instruction) TMEM -> registers -> fp32 staging tile
+//   all 8 warps (the TMA / MMA warps have finished by then, warps 6-7 exist for this) epilogue phase 2: + bias, exact
+//            GELU, + residual, RoPE -> bf16 (or fp32), 16-byte global stores.  The epilogue math is latency-bound per
+//            warp (one warp per SM sub-partition issues ~0.25 IPC), so phase 2 is spread over twice the warps
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <stdlib.h>
@@ -23,7 +25,7 @@
 
 #define GEMM_BM 128
 #define GEMM_BK 64
-#define GEMM_THREADS 192
+#define GEMM_THREADS 256
 
 __device__ __forceinline__ uint32_t g_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -356,20 +358,29 @@ s3r_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       }
       g_umma_commit(tmem_full);  // accumulator complete
     }
-  } else {
-    // ===== epilogue warps (TMEM lane quarter = warp % 4)
-    // phase 1: TMEM -> registers -> fp32 staging tile in shared memory (the TMA ring is idle once tmem_full fires);
-    // phase 2: the 128 threads walk the tile row-wise, 4 consecutive columns per lane, so that every global access
-    //          (partials, bias, residual, output) is a fully coalesced 256/512-byte row segment.
+  }
+  __syncwarp();  // reconverge the single-lane producer / MMA warps before they join the epilogue's second phase
+  // ===== epilogue
+  // phase 1 (warps 2-5, TMEM lane quarter = warp % 4): TMEM -> registers -> fp32 staging tile in shared memory (the TMA
+  //          ring is idle once tmem_full fires);
+  // phase 2 (all 256 threads; only the 128 epilogue threads when split-K is on): the tile is walked row-wise, 4
+  //          consecutive columns per lane, so that every global access (partials, bias, residual, output) is a fully
+  //          coalesced 256/512-byte row segment.
+  const bool is_p1 = warp >= 2 && warp < 6;
+  const int NT2 = splits == 1 ? GEMM_THREADS : 128;   // threads of phase 2
+  // phase-2 thread index: epilogue warps 0..127, then the TMA / MMA warps, then warps 6-7
+  const int et = is_p1 ? (int)threadIdx.x - 64 : (warp < 2 ? 128 + (int)threadIdx.x : (int)threadIdx.x);
+  if (et < NT2) {
     const int q = warp & 3;
-    const int et = threadIdx.x - 64;  // 0..127
     constexpr int CG = BN > 128 ? 128 : BN;  // columns staged per pass (BN = 256: two passes over one 68 KB staging tile)
     constexpr int LDS_ = CG + 4;      // padded row pitch (floats): conflict-free for both phases
     float* stage = reinterpret_cast<float*>(smem);
     int* spos = reinterpret_cast<int*>(smem + GEMM_STAGES * S::STAGE_BYTES - 2048);  // [128][2] row positions (RoPE)
-    g_mbar_wait(tmem_full, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    if (EF(S3R_EPI_ROPE)) {
+    if (is_p1) {
+      g_mbar_wait(tmem_full, 0);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
+    if (is_p1 && EF(S3R_EPI_ROPE)) {
       {  // one coalesced read of this tile's 128 (y, x) positions, clamped to the table
         const int prow = m0 + q * 32 + lane;
         long long py = 0, px = 0;
@@ -383,7 +394,7 @@ s3r_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     }
 #pragma unroll 1
     for (int cg = 0; cg < BN / CG; cg++) {
-    {
+    if (is_p1) {
       float* srow = stage + (size_t)(q * 32 + lane) * LDS_;
 #pragma unroll 1
       for (int c = 0; c < CG / 32; c++) {
@@ -395,9 +406,9 @@ s3r_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
               make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
       }
     }
-    asm volatile("bar.sync 1, 128;" ::: "memory");
+    asm volatile("bar.sync 1, %0;" ::"r"(NT2) : "memory");
     constexpr int LPR = CG / 4;        // lanes per row
-    constexpr int RPI = 128 / LPR;     // rows per iteration of the 128 epilogue threads
+    const int RPI = NT2 / LPR;         // rows per iteration of the phase-2 threads
     const int cl = (et % LPR) * 4;     // this lane's first column inside the tile
     const int col = n0 + cg * CG + cl;
     const bool has_bias = EF(S3R_EPI_BIAS), gelu = EF(S3R_EPI_GELU), has_res = EF(S3R_EPI_RESIDUAL),
@@ -563,11 +574,11 @@ s3r_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         }
       }
     }
-    if (BN > CG) asm volatile("bar.sync 1, 128;" ::: "memory");  // staging tile is reused by the next column group
+    if (BN > CG) asm volatile("bar.sync 1, %0;" ::"r"(NT2) : "memory");  // staging tile is reused by the next column group
     }  // cg
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncwarp();                    // reconverge the single-lane producer / MMA warps: barrier.cluster is .aligned
+  __syncwarp();
   if (kCluster) g_cluster_sync();  // no CTA may retire while a peer can still multicast into it / signal its barriers
   else __syncthreads();
   if (warp == 1) {
