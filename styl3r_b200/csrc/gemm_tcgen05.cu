@@ -214,7 +214,13 @@ struct ConvArgs {
 // when its flag is off (measured: the three training-only features slowed the inference GEMMs by 15-25 %), so the hot
 // inference shapes are instantiated per feature set and everything else uses the all-features instance.
 #define S3R_EPI_ALL 0xfff
-template <int BN, int STAGES_, bool kConv, int CM = 1, int CN = 1, int MAJ = 0, int EPI = S3R_EPI_ALL>
+// KS > 1: cluster split-K - a cluster of KS CTAs (cluster dims (1, 1, KS), rank = blockIdx.z) shares one output tile,
+// each runs 1/KS of the k-blocks into its own TMEM accumulator and parks it in its own shared-memory staging tile; rank 0
+// then sums the KS tiles through distributed shared memory (ld.shared::cluster) inside its fused epilogue.  For the
+// narrow-N / long-K GEMMs of the batch-1 encoder (fc2, proj: 18-80 tiles for 148 SMs, every SM bound by its ~50 B/cycle
+// TMA ingress) this spreads the K stream over KS times as many SMs without the L2 workspace + ticket round trips of the
+// global split-K.
+template <int BN, int STAGES_, bool kConv, int CM = 1, int CN = 1, int MAJ = 0, int EPI = S3R_EPI_ALL, int KS = 1>
 __global__ void __launch_bounds__(GEMM_THREADS, (STAGES_ * (GEMM_BM + BN) * GEMM_BK * 2 <= 100 * 1024) ? 2 : 1)
 s3r_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const __nv_bfloat16* __restrict__ bias, const __nv_bfloat16* __restrict__ residual, void* __restrict__ Cout,
@@ -257,6 +263,7 @@ s3r_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   constexpr bool kCluster = CM * CN > 1;
+  static_assert(KS == 1 || (CM * CN == 1 && BN <= 128 && !kConv), "cluster split-K: plain GEMM tiles, single epilogue pass");
   uint32_t xr = 0, yr = 0;       // this CTA's position inside its cluster (x = M direction, fastest)
   uint16_t mask_a = 1, mask_b = 1, mask_rel = 1;
   if (kCluster) {
@@ -367,7 +374,7 @@ s3r_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   //          consecutive columns per lane, so that every global access (partials, bias, residual, output) is a fully
   //          coalesced 256/512-byte row segment.
   const bool is_p1 = warp >= 2 && warp < 6;
-  const int NT2 = splits == 1 ? GEMM_THREADS : 128;   // threads of phase 2
+  const int NT2 = (splits == 1 || KS > 1) ? GEMM_THREADS : 128;   // threads of phase 2
   // phase-2 thread index: epilogue warps 0..127, then the TMA / MMA warps, then warps 6-7
   const int et = is_p1 ? (int)threadIdx.x - 64 : (warp < 2 ? 128 + (int)threadIdx.x : (int)threadIdx.x);
   if (et < NT2) {
@@ -406,7 +413,8 @@ s3r_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
               make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
       }
     }
-    asm volatile("bar.sync 1, %0;" ::"r"(NT2) : "memory");
+    if (KS > 1) g_cluster_sync();  // every rank's partial tile is parked in its staging buffer (all 256 threads take part)
+    else asm volatile("bar.sync 1, %0;" ::"r"(NT2) : "memory");
     constexpr int LPR = CG / 4;        // lanes per row
     const int RPI = NT2 / LPR;         // rows per iteration of the phase-2 threads
     const int cl = (et % LPR) * 4;     // this lane's first column inside the tile
@@ -508,7 +516,29 @@ s3r_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         }
       }
     };
-    if (splits == 1) {
+    if (KS > 1) {
+      if (blockIdx.z == 0) {  // rank 0: sum the KS partial tiles through distributed shared memory, then the fused epilogue
+#pragma unroll 2
+        for (int r = et / LPR; r < GEMM_BM; r += RPI) {
+          const float* sp = stage + (size_t)r * LDS_ + cl;
+          const float4 t = *reinterpret_cast<const float4*>(sp);
+          float f[4] = {t.x, t.y, t.z, t.w};
+          const uint32_t local = g_smem_u32(sp);
+#pragma unroll
+          for (int k = 1; k < KS; k++) {
+            uint32_t remote;
+            asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(k));
+            float4 p;
+            asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(p.x), "=f"(p.y), "=f"(p.z), "=f"(p.w)
+                         : "r"(remote)
+                         : "memory");
+            f[0] += p.x; f[1] += p.y; f[2] += p.z; f[3] += p.w;
+          }
+          finish(f, m0 + r);
+        }
+      }
+    } else if (splits == 1) {
 #pragma unroll 2
       for (int r = et / LPR; r < GEMM_BM; r += RPI) {
         const float4 t = *reinterpret_cast<const float4*>(stage + (size_t)r * LDS_ + cl);
@@ -579,7 +609,7 @@ s3r_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncwarp();
-  if (kCluster) g_cluster_sync();  // no CTA may retire while a peer can still multicast into it / signal its barriers
+  if (kCluster || KS > 1) g_cluster_sync();  // no CTA may retire while a peer can still multicast into it / read its tile
   else __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -599,6 +629,7 @@ static int g_gemm_big_tile = 0;  // S3R_TUNE_GEMM_BIG_TILE: 0 = auto (wide many-
 // at 514x1024x1024, neutral for grids whose shared memory fills the SMs; results identical.  On by default.
 static int g_pdl = 1;
 int s3r_pdl_enabled() { return g_pdl; }
+static int g_gemm_ksplit = 0;    // S3R_TUNE_GEMM_KSPLIT: 0 = auto, 1 = never, 2 / 4 = force that cluster split-K factor on 64-wide tiles
 static int g_gemm_shallow = 0;   // S3R_TUNE_GEMM_SHALLOW: small grids use the 4-stage (96 KB, 2 CTAs/SM) ring too
 static int g_conv_cluster = 0;   // S3R_TUNE_CONV_CLUSTER: pairs of pixel tiles multicast the weight tile
 
@@ -629,13 +660,14 @@ static int make_map(CUtensorMap* map, const void* ptr, int rows, int cols, int l
   return r == CUDA_SUCCESS ? S3R_OK : S3R_ERR_CUDA;
 }
 
-template <int BN, int STAGES_, bool kConv = false, int CM = 1, int CN = 1, int MAJ = 0, int EPI = S3R_EPI_ALL>
+template <int BN, int STAGES_, bool kConv = false, int CM = 1, int CN = 1, int MAJ = 0, int EPI = S3R_EPI_ALL, int KS = 1>
 static int launch_gemm(const CUtensorMap& a, const CUtensorMap& b, const void* bias, const void* residual, void* C, int M,
                        int N, int K, int ldc, int ldr, int flags, const RopeArgs& rope, int splits, float* ws, unsigned* counters,
                        cudaStream_t st, const ConvArgs& conv = ConvArgs{}, int batch = 0, long long batch_stride_c = 0) {
   static size_t configured[64] = {};  // per device: cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute
   const int smem = GemmSmem<BN, STAGES_>::TOTAL;
-  auto kern = s3r_gemm_bf16_kernel<BN, STAGES_, kConv, CM, CN, MAJ, EPI>;
+  auto kern = s3r_gemm_bf16_kernel<BN, STAGES_, kConv, CM, CN, MAJ, EPI, KS>;
+  if (KS > 1) splits = KS, ws = nullptr, counters = nullptr;
   {
     const int rc_ = s3r_ensure_dynamic_smem(kern, (size_t)smem, configured);
     if (rc_ != S3R_OK) return rc_;
@@ -650,11 +682,11 @@ static int launch_gemm(const CUtensorMap& a, const CUtensorMap& b, const void* b
   cfg.stream = st;
   cudaLaunchAttribute attr[2];
   int na = 0;
-  if (CM * CN > 1) {
+  if (CM * CN > 1 || KS > 1) {
     attr[na].id = cudaLaunchAttributeClusterDimension;
     attr[na].val.clusterDim.x = CM;
     attr[na].val.clusterDim.y = CN;
-    attr[na].val.clusterDim.z = 1;
+    attr[na].val.clusterDim.z = KS;
     na++;
   }
   if (g_pdl) {  // PDL: this launch may begin while the previous kernel of the stream drains (kernel waits before its loads)
@@ -794,6 +826,26 @@ extern "C" int s3r_gemm_bf16_rope(const void* A, const void* W, const void* bias
     if (cm == 2 && cn == 4) S3R_GEMM_GO(BN_, ST_, 2, 4); \
     S3R_GEMM_GO(BN_, ST_, 1, 1);                     \
   } while (0)
+  if (BN == 64 && cm == 1 && cn == 1 && splits == 1 && !t_pre_out && g_gemm_ksplit != 1 && !(flags & S3R_EPI_ROPE)) {
+    // cluster split-K for the narrow-N / long-K GEMMs of the batch-1 encoder (fc2, proj): KS CTAs per tile
+    const int total_kb = (K + GEMM_BK - 1) / GEMM_BK;
+    int ks = 1;
+    if (g_gemm_ksplit > 1) ks = g_gemm_ksplit;
+    // measured on B200 (scripts/bench_splitk.py, +residual epilogue): 257x768x3072 18.2 -> 11.9 us (KS 4), 257x1024x4096
+    // 22.9 -> 13.2 (KS 4), 514x1024x4096 23.9 -> 16.5 (KS 2), 1028x768x3072 19.4 -> 14.5 (KS 2); neutral below K = 1536
+    else if (tiles64 * 4 <= 200 && total_kb >= 32) ks = 4;
+    else if (tiles64 * 2 <= 300 && total_kb >= 24) ks = 2;
+    if (ks == 4 || ks == 2) {
+      const bool res_only = extra == S3R_EPI_RESIDUAL || extra == 0;
+#define S3R_GEMM_KS(KS_, EPI_) \
+  return launch_gemm<64, 4, false, 1, 1, 0, EPI_, KS_>(ta, tb, bias, residual, C, M, N, K, ldc, ldr, flags, rope, 1, nullptr, nullptr, st)
+      if (ks == 4 && res_only) S3R_GEMM_KS(4, E_BASE | S3R_EPI_RESIDUAL);
+      if (ks == 4) S3R_GEMM_KS(4, S3R_EPI_ALL);
+      if (res_only) S3R_GEMM_KS(2, E_BASE | S3R_EPI_RESIDUAL);
+      S3R_GEMM_KS(2, S3R_EPI_ALL);
+#undef S3R_GEMM_KS
+    }
+  }
   if (BN == 64) {
     if (tiles64 * splits < 148 && !g_gemm_shallow) {
       S3R_GEMM_EPI(64, 8);
@@ -915,6 +967,11 @@ extern "C" int s3r_set_tunable(int32_t key, int32_t value) {
     const int cm = value / 10, cn = value % 10;
     if (value != 0 && !((cm == 1 || cm == 2) && (cn == 1 || cn == 2 || cn == 4))) return S3R_ERR_INVALID_ARG;
     g_gemm_cluster = value;
+    return S3R_OK;
+  }
+  if (key == S3R_TUNE_GEMM_KSPLIT) {
+    if (value != 0 && value != 1 && value != 2 && value != 4) return S3R_ERR_INVALID_ARG;
+    g_gemm_ksplit = value;
     return S3R_OK;
   }
   if (key == S3R_TUNE_GEMM_SHALLOW) {
