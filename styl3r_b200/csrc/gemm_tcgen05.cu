@@ -85,6 +85,46 @@ __device__ __forceinline__ void g_umma_commit_mc(uint64_t* bar, uint16_t mask) {
                "h"(mask)
                : "memory");
 }
+// ---- CTA pairs (cta_group::2): two CTAs of a (2,1,1) cluster on the two SMs of a TPC run ONE tcgen05.mma of M = 256:
+// each CTA holds its own 128 rows of A, HALF of the B tile (the tensor core reads the other half from the peer's shared
+// memory) and 128 lanes of the accumulator in its own TMEM.  Both CTAs' TMA loads complete on the LEADER's (rank 0) full
+// barrier; the leader's elected thread issues the MMAs and releases ring slots in both CTAs with a multicast commit.
+__device__ __forceinline__ uint32_t g_mapa(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void g_tma_load_2d_pair(void* dst, const CUtensorMap* map, int c0, int c1, uint32_t leader_bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+          g_smem_u32(dst)),
+      "l"(map), "r"(c0), "r"(c1), "r"(leader_bar)
+      : "memory");
+}
+__device__ __forceinline__ void g_tma_load_4d_pair(void* dst, const CUtensorMap* map, int c0, int c1, int c2, int c3,
+                                                   uint32_t leader_bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(
+          g_smem_u32(dst)),
+      "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(leader_bar)
+      : "memory");
+}
+__device__ __forceinline__ void g_umma_pair(uint32_t tmem_c, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_c),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void g_umma_commit_pair(uint64_t* bar) {  // arrives on the barrier at this offset in BOTH CTAs
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   g_smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
 __device__ __forceinline__ void g_cluster_sync() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -168,10 +208,10 @@ __device__ __forceinline__ float g_fast_erf(float x) {
   return copysignf(y, x);
 }
 
-template <int BN, int STAGES_>
+template <int BN, int STAGES_, int PAIR = 0>
 struct GemmSmem {
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
-  static constexpr int B_BYTES = BN * GEMM_BK * 2;
+  static constexpr int B_BYTES = (PAIR ? BN / 2 : BN) * GEMM_BK * 2;  // a CTA of a pair holds half of the B tile
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   // ring depth: large grids use ~100 KB per CTA so that TWO CTAs are resident per SM — the epilogue of one tile (TMEM
   // -> registers, bias / erf-GELU / residual, stores) then overlaps the TMA + MMA main loop of the other (measured:
@@ -220,15 +260,15 @@ struct ConvArgs {
 // narrow-N / long-K GEMMs of the batch-1 encoder (fc2, proj: 18-80 tiles for 148 SMs, every SM bound by its ~50 B/cycle
 // TMA ingress) this spreads the K stream over KS times as many SMs without the L2 workspace + ticket round trips of the
 // global split-K.
-template <int BN, int STAGES_, bool kConv, int CM = 1, int CN = 1, int MAJ = 0, int EPI = S3R_EPI_ALL, int KS = 1>
-__global__ void __launch_bounds__(GEMM_THREADS, (STAGES_ * (GEMM_BM + BN) * GEMM_BK * 2 <= 100 * 1024) ? 2 : 1)
+template <int BN, int STAGES_, bool kConv, int CM = 1, int CN = 1, int MAJ = 0, int EPI = S3R_EPI_ALL, int KS = 1, int PAIR = 0>
+__global__ void __launch_bounds__(GEMM_THREADS, (GemmSmem<BN, STAGES_, PAIR>::STAGES * GemmSmem<BN, STAGES_, PAIR>::STAGE_BYTES <= 100 * 1024) ? 2 : 1)
 s3r_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const __nv_bfloat16* __restrict__ bias, const __nv_bfloat16* __restrict__ residual, void* __restrict__ Cout,
                      int M, int N, int K, int ldc, int ldr, int flags, RopeArgs rope, int splits, float* __restrict__ ws,
                      unsigned* __restrict__ counters, ConvArgs conv, long long batch_stride_c) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);  // SWIZZLE_128B atoms need 1024-B alignment
-  using S = GemmSmem<BN, STAGES_>;
+  using S = GemmSmem<BN, STAGES_, PAIR>;
 #define EF(X) (((EPI) & (X)) && (flags & (X)))
   constexpr int GEMM_STAGES = S::STAGES;
   uint64_t* full = (uint64_t*)(smem + GEMM_STAGES * S::STAGE_BYTES);
@@ -262,11 +302,13 @@ s3r_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     g_mbar_init(tmem_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  constexpr bool kCluster = CM * CN > 1;
+  constexpr bool kCluster = CM * CN > 1 || PAIR;
+  static_assert(!PAIR || (CM * CN == 1 && KS == 1 && MAJ == 0), "CTA pairs: K-major operands, no multicast / split-K");
+  const uint32_t prank = PAIR ? g_cluster_ctarank() : 0u;  // rank inside the CTA pair (0 = leader: issues the MMAs)
   static_assert(KS == 1 || (CM * CN == 1 && BN <= 128 && !kConv), "cluster split-K: plain GEMM tiles, single epilogue pass");
   uint32_t xr = 0, yr = 0;       // this CTA's position inside its cluster (x = M direction, fastest)
   uint16_t mask_a = 1, mask_b = 1, mask_rel = 1;
-  if (kCluster) {
+  if (CM * CN > 1) {
     const uint32_t crank = g_cluster_ctarank();
     xr = crank % CM, yr = crank / CM;
     mask_a = mask_b = 0;
@@ -277,9 +319,15 @@ s3r_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     mask_rel = mask_a | mask_b;
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(g_smem_u32(tmem_slot)), "r"(BN)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (PAIR) {  // one warp of EACH CTA of the pair: the same columns are allocated in both CTAs' TMEM
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(g_smem_u32(tmem_slot)), "r"(BN)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(g_smem_u32(tmem_slot)), "r"(BN)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncwarp();
@@ -308,6 +356,20 @@ s3r_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         g_mbar_wait(&empty[s], ((kb / GEMM_STAGES) & 1) ^ 1);
         uint8_t* a_dst = smem + s * S::STAGE_BYTES;
         uint8_t* b_dst = a_dst + S::A_BYTES;
+        if (PAIR) {
+          // both CTAs' bytes land on the leader's barrier; only the leader posts the expectation (for both)
+          const uint32_t lbar = g_mapa(g_smem_u32(&full[s]), 0);
+          if (prank == 0) g_mbar_expect_tx(&full[s], 2 * S::STAGE_BYTES);
+          if (kConv) {
+            const int tap = (kb0 + kb) / conv.cblocks, cb = (kb0 + kb) - tap * conv.cblocks;
+            const int kh = tap / conv.KW, kw = tap - kh * conv.KW;
+            g_tma_load_4d_pair(a_dst, &tmA, cb * GEMM_BK, cw0 + kw - conv.pad, ch0 + kh - conv.pad, cn0, lbar);
+          } else {
+            g_tma_load_2d_pair(a_dst, &tmA, (kb0 + kb) * GEMM_BK, m0, lbar);
+          }
+          g_tma_load_2d_pair(b_dst, &tmB, (kb0 + kb) * GEMM_BK, n0 + (int)prank * (BN / 2), lbar);
+          continue;
+        }
         g_mbar_expect_tx(&full[s], S::STAGE_BYTES);
         if (kConv) {
           const int tap = (kb0 + kb) / conv.cblocks, cb = (kb0 + kb) - tap * conv.cblocks;
@@ -344,8 +406,8 @@ s3r_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = g_make_idesc(GEMM_BM, BN, MAJ & 1, (MAJ >> 1) & 1);
+    if (lane == 0 && prank == 0) {
+      const uint32_t idesc = g_make_idesc(PAIR ? 2 * GEMM_BM : GEMM_BM, BN, MAJ & 1, (MAJ >> 1) & 1);
       for (int kb = 0; kb < num_kb; kb++) {
         const int s = kb % GEMM_STAGES;
         g_mbar_wait(&full[s], (kb / GEMM_STAGES) & 1);
@@ -357,13 +419,17 @@ s3r_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         // MN-major +16 rows of 128 B (+128)
         constexpr int AK = (MAJ & 1) ? 128 : 2, BK_ = (MAJ & 2) ? 128 : 2;
 #pragma unroll
-        for (int k = 0; k < GEMM_BK / 16; k++)
-          g_umma(tmem_base, adesc + (uint64_t)(AK * k), bdesc + (uint64_t)(BK_ * k), idesc, (kb | k) ? 1u : 0u);
-        // frees the ring slot once these MMAs have read it (in every CTA that multicasts into it)
-        if (kCluster) g_umma_commit_mc(&empty[s], mask_rel);
+        for (int k = 0; k < GEMM_BK / 16; k++) {
+          if (PAIR) g_umma_pair(tmem_base, adesc + (uint64_t)(AK * k), bdesc + (uint64_t)(BK_ * k), idesc, (kb | k) ? 1u : 0u);
+          else g_umma(tmem_base, adesc + (uint64_t)(AK * k), bdesc + (uint64_t)(BK_ * k), idesc, (kb | k) ? 1u : 0u);
+        }
+        // frees the ring slot once these MMAs have read it (in every CTA that multicasts into it / in both CTAs of a pair)
+        if (PAIR) g_umma_commit_pair(&empty[s]);
+        else if (kCluster) g_umma_commit_mc(&empty[s], mask_rel);
         else g_umma_commit(&empty[s]);
       }
-      g_umma_commit(tmem_full);  // accumulator complete
+      if (PAIR) g_umma_commit_pair(tmem_full);  // accumulator complete (both halves)
+      else g_umma_commit(tmem_full);
     }
   }
   __syncwarp();  // reconverge the single-lane producer / MMA warps before they join the epilogue's second phase
@@ -613,7 +679,8 @@ s3r_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   else __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(BN) : "memory");
+    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(BN) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(BN) : "memory");
   }
 }
 
@@ -632,6 +699,7 @@ int s3r_pdl_enabled() { return g_pdl; }
 static int g_gemm_ksplit = 0;    // S3R_TUNE_GEMM_KSPLIT: 0 = auto, 1 = never, 2 / 4 = force that cluster split-K factor on 64-wide tiles
 static int g_gemm_shallow = 0;   // S3R_TUNE_GEMM_SHALLOW: small grids use the 4-stage (96 KB, 2 CTAs/SM) ring too
 static int g_conv_cluster = 0;   // S3R_TUNE_CONV_CLUSTER: pairs of pixel tiles multicast the weight tile
+static int g_gemm_pair = 0;      // S3R_TUNE_GEMM_PAIR: CTA pairs (cta_group::2, M = 256 per MMA): 0 = auto, 1 = 256x128 pair tiles whenever possible, 2 = never, 3 = 256x256 pair tiles whenever possible
 
 static PFN_encodeTiled get_encode() {
   static PFN_encodeTiled fn = nullptr;
@@ -660,13 +728,14 @@ static int make_map(CUtensorMap* map, const void* ptr, int rows, int cols, int l
   return r == CUDA_SUCCESS ? S3R_OK : S3R_ERR_CUDA;
 }
 
-template <int BN, int STAGES_, bool kConv = false, int CM = 1, int CN = 1, int MAJ = 0, int EPI = S3R_EPI_ALL, int KS = 1>
+template <int BN, int STAGES_, bool kConv = false, int CM = 1, int CN = 1, int MAJ = 0, int EPI = S3R_EPI_ALL, int KS = 1, int PAIR = 0>
 static int launch_gemm(const CUtensorMap& a, const CUtensorMap& b, const void* bias, const void* residual, void* C, int M,
                        int N, int K, int ldc, int ldr, int flags, const RopeArgs& rope, int splits, float* ws, unsigned* counters,
                        cudaStream_t st, const ConvArgs& conv = ConvArgs{}, int batch = 0, long long batch_stride_c = 0) {
   static size_t configured[64] = {};  // per device: cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute
-  const int smem = GemmSmem<BN, STAGES_>::TOTAL;
-  auto kern = s3r_gemm_bf16_kernel<BN, STAGES_, kConv, CM, CN, MAJ, EPI, KS>;
+  const int smem = GemmSmem<BN, STAGES_, PAIR>::TOTAL;
+  auto kern = s3r_gemm_bf16_kernel<BN, STAGES_, kConv, CM, CN, MAJ, EPI, KS, PAIR>;
+  constexpr int CMX = PAIR ? 2 : CM;  // cluster extent along M
   if (KS > 1) splits = KS, ws = nullptr, counters = nullptr;
   {
     const int rc_ = s3r_ensure_dynamic_smem(kern, (size_t)smem, configured);
@@ -674,7 +743,7 @@ static int launch_gemm(const CUtensorMap& a, const CUtensorMap& b, const void* b
   }
   // grid padded to whole clusters: CTAs past the last tile still take part in the multicast (their own loads are fully
   // out of bounds = zero fill, their epilogue is masked)
-  const unsigned gx = ((M + GEMM_BM - 1) / GEMM_BM + CM - 1) / CM * CM, gy = ((N + BN - 1) / BN + CN - 1) / CN * CN;
+  const unsigned gx = ((M + GEMM_BM - 1) / GEMM_BM + CMX - 1) / CMX * CMX, gy = ((N + BN - 1) / BN + CN - 1) / CN * CN;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(gx, gy, batch > 0 ? batch : splits);
   cfg.blockDim = dim3(GEMM_THREADS, 1, 1);
@@ -682,9 +751,9 @@ static int launch_gemm(const CUtensorMap& a, const CUtensorMap& b, const void* b
   cfg.stream = st;
   cudaLaunchAttribute attr[2];
   int na = 0;
-  if (CM * CN > 1 || KS > 1) {
+  if (CMX * CN > 1 || KS > 1) {
     attr[na].id = cudaLaunchAttributeClusterDimension;
-    attr[na].val.clusterDim.x = CM;
+    attr[na].val.clusterDim.x = CMX;
     attr[na].val.clusterDim.y = CN;
     attr[na].val.clusterDim.z = KS;
     na++;
@@ -767,6 +836,42 @@ extern "C" int s3r_gemm_bf16_rope(const void* A, const void* W, const void* bias
   if (BN == 128 && N % 256 == 0 && g_gemm_big_tile != 2 &&
       ((g_gemm_big_tile == 1 && mt * (N / 256) >= 120) || (N >= 4096 && mt * (N / 256) >= 444)))
     BN = 256;
+  // CTA pairs (cta_group::2): 256-row MMAs, every CTA ingests its own A rows and only HALF of the B tile
+  {
+    int pair_bn = 0;
+    if (g_gemm_pair == 1 && mt >= 2 && N % 128 == 0) pair_bn = 128;
+    if (g_gemm_pair == 3 && mt >= 2 && N % 256 == 0) pair_bn = 256;
+    if (g_gemm_pair == 0) {
+      // measured on B200 (scripts/bench_pair.py): 256x256 pair tiles win once the grid is many waves deep (8192^3: 1375 ->
+      // 1547 TFLOP/s; cuBLAS 1643) and lose to wave quantisation on the 1.4-wave grids of M = 4112; 256x128 pair tiles
+      // (half the B ingress per CTA, same CTA count) win on the long-K / narrow-N shapes (4112x1024x4096: 30.7 -> 27.6 us,
+      // 4112x768x3072: 24.1 -> 21.6)
+      if (N % 256 == 0 && mt * (N / 256) >= 4 * 296) pair_bn = 256;
+      else if (N % 128 == 0 && N <= 1024 && K >= 3072 && mt >= 16) pair_bn = 128;
+    }
+    if (pair_bn && !t_pre_out) {
+      if ((rc = make_map(&ta, A, M, K, lda, GEMM_BM)) != S3R_OK) return rc;
+      if ((rc = make_map(&tb, W, N, K, ldw, pair_bn / 2)) != S3R_OK) return rc;
+      cudaStream_t st = (cudaStream_t)stream;
+      constexpr int E_BASE = S3R_EPI_BIAS | S3R_EPI_OUT_F32 | S3R_EPI_PDL;
+      const int extra = flags & ~E_BASE;
+#define S3R_GEMM_PAIR(BN_, ST_)                                                                                          \
+  do {                                                                                                                  \
+    if (extra == 0)                                                                                                     \
+      return launch_gemm<BN_, ST_, false, 1, 1, 0, E_BASE, 1, 1>(ta, tb, bias, residual, C, M, N, K, ldc, ldr, flags, rope, 1, nullptr, nullptr, st); \
+    if (extra == S3R_EPI_GELU)                                                                                          \
+      return launch_gemm<BN_, ST_, false, 1, 1, 0, E_BASE | S3R_EPI_GELU, 1, 1>(ta, tb, bias, residual, C, M, N, K, ldc, ldr, flags, rope, 1, nullptr, nullptr, st); \
+    if (extra == S3R_EPI_RESIDUAL)                                                                                      \
+      return launch_gemm<BN_, ST_, false, 1, 1, 0, E_BASE | S3R_EPI_RESIDUAL, 1, 1>(ta, tb, bias, residual, C, M, N, K, ldc, ldr, flags, rope, 1, nullptr, nullptr, st); \
+    if (extra == S3R_EPI_ROPE)                                                                                          \
+      return launch_gemm<BN_, ST_, false, 1, 1, 0, E_BASE | S3R_EPI_ROPE, 1, 1>(ta, tb, bias, residual, C, M, N, K, ldc, ldr, flags, rope, 1, nullptr, nullptr, st); \
+    return launch_gemm<BN_, ST_, false, 1, 1, 0, S3R_EPI_ALL, 1, 1>(ta, tb, bias, residual, C, M, N, K, ldc, ldr, flags, rope, 1, nullptr, nullptr, st); \
+  } while (0)
+      if (pair_bn == 128) S3R_GEMM_PAIR(128, 4);   // 4 x 24 KB ring, 2 CTAs / SM
+      S3R_GEMM_PAIR(256, 3);                        // 3 x 32 KB ring, 2 CTAs / SM (2 x 256 TMEM columns)
+#undef S3R_GEMM_PAIR
+    }
+  }
   int cm = 1, cn = 1;  // cluster shape (multicast): tunable, else the measured default per tile class
   if (g_gemm_cluster > 0) cm = g_gemm_cluster / 10, cn = g_gemm_cluster % 10;
   if ((N + BN - 1) / BN < cn) cn = 1;
@@ -974,6 +1079,11 @@ extern "C" int s3r_set_tunable(int32_t key, int32_t value) {
     g_gemm_ksplit = value;
     return S3R_OK;
   }
+  if (key == S3R_TUNE_GEMM_PAIR) {
+    if (value < 0 || value > 3) return S3R_ERR_INVALID_ARG;
+    g_gemm_pair = value;
+    return S3R_OK;
+  }
   if (key == S3R_TUNE_GEMM_SHALLOW) {
     g_gemm_shallow = value != 0;
     return S3R_OK;
@@ -1057,6 +1167,22 @@ extern "C" int s3r_conv2d_bf16(const void* x, const void* w, const void* bias, c
   if ((rc = make_map(&tb, w, cout, K, K, BN / cm)) != S3R_OK) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   RopeArgs rope{nullptr, nullptr, 0, 0};
+  {  // CTA pairs (cta_group::2): two adjacent pixel tiles run one 256-row MMA, each CTA stages half of the weight tile
+    int pair_bn = 0;
+    const bool cm_forced = g_conv_cluster != 0;
+    const long mtiles = (M + GEMM_BM - 1) / GEMM_BM;
+    if (g_gemm_pair == 1 && mtiles >= 2 && cout % 128 == 0) pair_bn = 128;
+    if (g_gemm_pair == 3 && mtiles >= 2 && cout % 256 == 0) pair_bn = 256;
+    // measured: 3x3 256->256 at 16 x 128^2 / 4 x 256^2: 1189 -> 1231 TFLOP/s, at 2 x 128^2 1005 -> 1026; below that the grid is
+    // smaller than the machine and the 128-wide single-CTA tile (twice the CTAs) wins
+    if (g_gemm_pair == 0 && cout % 256 == 0 && mtiles >= 256 && g_conv_variant < 0 && !cm_forced) pair_bn = 256;
+    if (pair_bn) {
+      if ((rc = make_map(&tb, w, cout, K, K, pair_bn / 2)) != S3R_OK) return rc;
+      if (pair_bn == 128)
+        return launch_gemm<128, 4, true, 1, 1, 0, S3R_EPI_ALL, 1, 1>(ta, tb, bias, residual, y, (int)M, cout, K, cout, cout, flags, rope, 1, nullptr, nullptr, st, conv);
+      return launch_gemm<256, 3, true, 1, 1, 0, S3R_EPI_ALL, 1, 1>(ta, tb, bias, residual, y, (int)M, cout, K, cout, cout, flags, rope, 1, nullptr, nullptr, st, conv);
+    }
+  }
   if (cm == 2) {
     if (BN == 256 && variant == 1)
       return launch_gemm<256, 4, true, 2, 1>(ta, tb, bias, residual, y, (int)M, cout, K, cout, cout, flags, rope, 1, nullptr, nullptr, st, conv);

@@ -122,6 +122,56 @@ def test_gemm_cluster_multicast_variants_match_reference(code, M, N, K, big):
     assert torch.equal(y, base) or (y.float() - base.float()).abs().max().item() <= 2 ** -6
 
 
+@pytest.mark.parametrize("mode", [1, 3])
+@pytest.mark.parametrize("M,N,K", [(514, 3072, 1024), (257, 768, 768), (4112, 1024, 4096), (1300, 512, 200), (129, 256, 64)])
+@pytest.mark.parametrize("epi", ["bias", "bias_gelu", "bias_res", "none_f32"])
+def test_gemm_cta_pair_variants_match_reference(mode, M, N, K, epi):
+    """CTA pairs (tcgen05 cta_group::2, S3R_TUNE_GEMM_PAIR = 1: 256x128 pair tiles, 3: 256x256): one 256-row MMA over the
+    two SMs of a TPC, each CTA stages its own A rows and half of the B tile; includes ragged M (odd number of 128-row
+    tiles: the padding CTA of the last pair loads zeros and stores nothing) and a K tail."""
+    import torch
+    from styl3r_b200 import _lib
+    from styl3r_b200.gemm import linear
+    L = _lib.lib()
+    g = torch.Generator(device="cuda").manual_seed(M + N + K + mode)
+    x = torch.randn(M, K, device="cuda", generator=g).to(torch.bfloat16)
+    w = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5).to(torch.bfloat16)
+    b = torch.randn(N, device="cuda", generator=g).to(torch.bfloat16) if "bias" in epi else None
+    r = torch.randn(M, N, device="cuda", generator=g).to(torch.bfloat16) if "res" in epi else None
+    out_dtype = torch.float32 if "f32" in epi else torch.bfloat16
+    try:
+        _lib.check(L.s3r_set_tunable(11, mode))
+        y = linear(x, w, b, r, gelu="gelu" in epi, out_dtype=out_dtype)
+        torch.cuda.synchronize()
+    finally:
+        L.s3r_set_tunable(11, 0)
+    expect = ref(x, w, b, r, "gelu" in epi)
+    tol = (2e-3 if out_dtype == torch.float32 else 1e-2) * expect.abs().max().item()
+    assert (y.float() - expect).abs().max().item() <= tol
+
+
+def test_conv_cta_pair_matches_plain():
+    import torch
+    from styl3r_b200 import _lib
+    from styl3r_b200.conv import conv2d_nhwc, prep_conv_weight
+    L = _lib.lib()
+    g = torch.Generator(device="cuda").manual_seed(5)
+    for (n, h, w, ci, co) in [(1, 128, 128, 256, 256), (3, 8, 8, 128, 128), (1, 256, 256, 64, 256), (2, 32, 32, 256, 256)]:
+        x = torch.randn(n, h, w, ci, device="cuda", generator=g).to(torch.bfloat16)
+        wp = prep_conv_weight((torch.randn(co, ci, 3, 3, device="cuda", generator=g) / (9 * ci) ** 0.5).to(torch.bfloat16))
+        bias = torch.randn(co, device="cuda", generator=g).to(torch.bfloat16)
+        try:
+            _lib.check(L.s3r_set_tunable(11, 2))
+            base = conv2d_nhwc(x, wp, (3, 3), bias=bias, relu=True)
+            for mode in (1, 3):
+                _lib.check(L.s3r_set_tunable(11, mode))
+                y = conv2d_nhwc(x, wp, (3, 3), bias=bias, relu=True)
+                torch.cuda.synchronize()
+                assert torch.equal(y, base) or (y.float() - base.float()).abs().max().item() <= 2 ** -6
+        finally:
+            L.s3r_set_tunable(11, 0)
+
+
 def test_conv_cluster_multicast_matches_plain():
     import torch
     from styl3r_b200 import _lib
