@@ -11,6 +11,7 @@ from styl3r_b200.gemm import linear
 L = _lib.lib()
 PAIR = 11
 what = sys.argv[1] if len(sys.argv) > 1 else "all"
+MODES = ((2, "single"), (1, "pair128"), (3, "pair256"), (4, "persist128"), (5, "persist256"))
 
 
 def gtime(fn, reps=20):
@@ -37,7 +38,7 @@ if what in ("gemm", "all"):
         ref = x.float() @ w.float().t() + b.float()
         reps = 5 if M >= 8192 else 20
         row = f"M={M:5d} N={N:5d} K={K:5d} |"
-        for mode, name in ((2, "single"), (1, "pair128"), (3, "pair256")):
+        for mode, name in MODES:
             L.s3r_set_tunable(PAIR, mode)
             y = linear(x, w, b)
             err = (y.float() - ref).abs().max().item()
@@ -61,7 +62,7 @@ if what in ("conv", "all"):
         ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.to(torch.bfloat16).float(), b.float(), padding=1).permute(0, 2, 3, 1)
         row = f"conv n={n:2d} {hw:3d}^2 {cin}->{cout} |"
         fl = 2.0 * n * hw * hw * cin * cout * 9
-        for mode, name in ((2, "single"), (1, "pair128"), (3, "pair256")):
+        for mode, name in MODES:
             L.s3r_set_tunable(PAIR, mode)
             y = conv2d_nhwc(x, wp, (3, 3), bias=b)
             err = (y.float() - ref).abs().max().item()

@@ -684,6 +684,279 @@ s3r_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   }
 }
 
+
+// ------------------------------------------------------------------------------------------ persistent CTA pairs
+// The many-wave shapes (M = 4112 of cfg3, the large convolutions): ONE resident CTA pair per TPC walks the list of
+// 256 x BN output tiles (static round-robin over the pairs), so that
+//   * there is no wave quantisation (204 pair tiles over 74 pairs cost 3 tile times, not 2 waves of half-empty SMs),
+//   * the accumulator is DOUBLE-BUFFERED in TMEM (2 x BN columns): the MMAs of tile i+1 start while the epilogue warps
+//     still drain tile i, and the TMA ring (the whole shared memory: no staging tile) never stops across tile boundaries,
+//   * barrier set-up, TMEM allocation and the tensor-map fetch are paid once per SM instead of once per tile.
+// Roles: warp 0 = TMA producer (both CTAs), warp 1 = MMA issuer (leader CTA only, cta_group::2), warps 2-9 = epilogue:
+// two warps per TMEM lane quarter (column halves), each thread owns ONE output row and walks it in 32-column blocks
+// straight from TMEM registers: bias / GELU / ReLU / residual / RoPE (the rotation pairs (d, d+16) sit in the same
+// thread) -> 64 contiguous bytes per thread and block to global memory.  No staging tile, no CTA barrier in the loop
+// (the staged two-phase epilogue of the one-tile kernel cost 11.6 k warp instructions per tile here and made the
+// K = 1024 shapes epilogue-bound: ncu tensor pipe 42 %).
+// tmem_full[b]: multicast commit of the leader -> both CTAs; tmem_empty[b]: lives in the leader, one arrival per
+// epilogue warp of BOTH CTAs (16), remote arrivals through mapa + mbarrier.arrive.shared::cluster.
+__device__ __forceinline__ void g_mbar_arrive_cluster(uint32_t bar_cluster_addr) {
+  // .relaxed: the arrival only hands back TMEM columns (ordered by tcgen05.fence::before_thread_sync); the default
+  // .release at cluster scope compiles to MEMBAR.ALL.GPU, which stalls the warp until all of its earlier global stores
+  // have been acknowledged - measured: the accumulator hand-back was delayed by ~2 us per tile
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+}
+
+template <int BN, int STAGES_>
+struct PersistSmem {
+  static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
+  static constexpr int B_BYTES = (BN / 2) * GEMM_BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = STAGES_;
+  static constexpr int BIAS_BYTES = 8 * (BN / 2) * 4;  // per epilogue warp: its column half of the tile's bias, fp32
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + BIAS_BYTES + 256 /* barriers */ + 1024 /* alignment */;
+};
+
+#define GEMM_P_EPI_WARPS 8
+#define GEMM_P_THREADS (64 + 32 * GEMM_P_EPI_WARPS)
+template <int BN, int STAGES_, bool kConv, int EPI>
+__global__ void __launch_bounds__(GEMM_P_THREADS, 1)
+s3r_gemm_pair_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                                const __nv_bfloat16* __restrict__ bias, const __nv_bfloat16* __restrict__ residual,
+                                void* __restrict__ Cout, int M, int N, int K, int ldc, int ldr, int flags, RopeArgs rope,
+                                ConvArgs conv, int mt_pairs, int total_tiles) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  using S = PersistSmem<BN, STAGES_>;
+#define EFP(X) (((EPI) & (X)) && (flags & (X)))
+  constexpr int ST = S::STAGES;
+  float* sbias_all = reinterpret_cast<float*>(smem + ST * S::STAGE_BYTES);
+  uint64_t* full = (uint64_t*)(smem + ST * S::STAGE_BYTES + S::BIAS_BYTES);
+  uint64_t* empty = full + ST;
+  uint64_t* tmem_full = empty + ST;    // [2]
+  uint64_t* tmem_empty = tmem_full + 2;  // [2] (used in the leader CTA)
+  uint32_t* tmem_slot = (uint32_t*)(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t prank = g_cluster_ctarank();
+  const int cid = blockIdx.x >> 1, ncl = gridDim.x >> 1;
+  const int num_kb = (K + GEMM_BK - 1) / GEMM_BK;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    for (int s = 0; s < ST; s++) {
+      g_mbar_init(&full[s], 1);
+      g_mbar_init(&empty[s], 1);
+    }
+    for (int b = 0; b < 2; b++) {
+      g_mbar_init(&tmem_full[b], 1);
+      g_mbar_init(&tmem_empty[b], 2 * GEMM_P_EPI_WARPS);  // every epilogue warp of both CTAs
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(g_smem_u32(tmem_slot)), "r"(2 * BN)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncwarp();
+  g_cluster_sync();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+  if (flags & S3R_EPI_PDL) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+  }
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int t = cid; t < total_tiles; t += ncl) {
+        const int m0 = ((t % mt_pairs) * 2 + (int)prank) * GEMM_BM, n0 = (t / mt_pairs) * BN;
+        int cw0 = 0, ch0 = 0, cn0 = 0;
+        if (kConv) {
+          cw0 = conv.W >= GEMM_BM ? m0 % conv.W : 0;
+          ch0 = (m0 / conv.W) % conv.H;
+          cn0 = m0 / (conv.W * conv.H);
+        }
+        for (int kb = 0; kb < num_kb; kb++, it++) {
+          const int s = it % ST;
+          g_mbar_wait(&empty[s], ((it / ST) & 1) ^ 1);
+          uint8_t* a_dst = smem + s * S::STAGE_BYTES;
+          uint8_t* b_dst = a_dst + S::A_BYTES;
+          const uint32_t lbar = g_mapa(g_smem_u32(&full[s]), 0);
+          if (prank == 0) g_mbar_expect_tx(&full[s], 2 * S::STAGE_BYTES);
+          if (kConv) {
+            const int tap = kb / conv.cblocks, cb = kb - tap * conv.cblocks;
+            const int kh = tap / conv.KW, kw = tap - kh * conv.KW;
+            g_tma_load_4d_pair(a_dst, &tmA, cb * GEMM_BK, cw0 + kw - conv.pad, ch0 + kh - conv.pad, cn0, lbar);
+          } else {
+            g_tma_load_2d_pair(a_dst, &tmA, kb * GEMM_BK, m0, lbar);
+          }
+          g_tma_load_2d_pair(b_dst, &tmB, kb * GEMM_BK, n0 + (int)prank * (BN / 2), lbar);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && prank == 0) {
+      const uint32_t idesc = g_make_idesc(2 * GEMM_BM, BN);
+      uint32_t it = 0, i = 0;
+      for (int t = cid; t < total_tiles; t += ncl, i++) {
+        const uint32_t b = i & 1;
+        g_mbar_wait(&tmem_empty[b], ((i >> 1) & 1) ^ 1);  // both CTAs have drained this accumulator buffer
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t tacc = tmem_base + b * BN;
+        for (int kb = 0; kb < num_kb; kb++, it++) {
+          const int s = it % ST;
+          g_mbar_wait(&full[s], (it / ST) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint64_t adesc = g_make_desc(smem + s * S::STAGE_BYTES);
+          const uint64_t bdesc = g_make_desc(smem + s * S::STAGE_BYTES + S::A_BYTES);
+#pragma unroll
+          for (int k = 0; k < GEMM_BK / 16; k++)
+            g_umma_pair(tacc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+          g_umma_commit_pair(&empty[s]);
+        }
+        g_umma_commit_pair(&tmem_full[b]);
+      }
+    }
+  } else {
+    // ===== epilogue warps 2..9: TMEM lane quarter q = warp % 4 (hardware rule), column half = (warp - 2) / 4
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    constexpr int NB = BN / 64;  // 32-column blocks per warp and tile
+    const uint32_t empty_bar0 = g_mapa(g_smem_u32(&tmem_empty[0]), 0), empty_bar1 = g_mapa(g_smem_u32(&tmem_empty[1]), 0);
+    const bool has_bias = EFP(S3R_EPI_BIAS), gelu = EFP(S3R_EPI_GELU), has_res = EFP(S3R_EPI_RESIDUAL), relu = EFP(S3R_EPI_RELU),
+               out_f32 = EFP(S3R_EPI_OUT_F32);
+    uint32_t i = 0;
+    for (int t = cid; t < total_tiles; t += ncl, i++) {
+      const int m0 = ((t % mt_pairs) * 2 + (int)prank) * GEMM_BM, n0 = (t / mt_pairs) * BN;
+      const uint32_t b = i & 1;
+      const int row = m0 + q * 32 + lane;
+      const bool row_ok = row < M;
+      int py = 0, px = 0;
+      if (EFP(S3R_EPI_ROPE) && row_ok) {  // requested before the accumulator wait: the latency hides behind the main loop
+        const long long y = rope.pos[(size_t)row * 2], x = rope.pos[(size_t)row * 2 + 1];
+        py = (int)(y < 0 ? 0 : (y > rope.max_pos ? rope.max_pos : y));
+        px = (int)(x < 0 ? 0 : (x > rope.max_pos ? rope.max_pos : x));
+      }
+      // everything that does not depend on the accumulator is fetched BEFORE the accumulator wait, so that its global
+      // latency hides behind the main loop of this tile: the warp's column half of the bias goes to its private
+      // shared-memory row (fp32, read back as broadcasts), the first block's residual segment to registers
+      float* sb = sbias_all + (warp - 2) * (BN / 2);
+      if (has_bias) {
+        const int cb0 = n0 + half * (BN / 2);
+#pragma unroll
+        for (int c = lane; c < BN / 2; c += 32) sb[c] = (cb0 + c < N) ? __bfloat162float(bias[cb0 + c]) : 0.0f;
+        __syncwarp();
+      }
+      uint4 rq[4];
+      auto load_res = [&](int blk_) {
+        const int col_ = n0 + half * (BN / 2) + blk_ * 32;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          rq[j] = make_uint4(0u, 0u, 0u, 0u);
+          if (row_ok && col_ + 8 * j + 8 <= N) rq[j] = *reinterpret_cast<const uint4*>(residual + (size_t)row * ldr + col_ + 8 * j);
+        }
+      };
+      if (has_res) load_res(0);
+      g_mbar_wait(&tmem_full[b], (i >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+      for (int blk = 0; blk < NB; blk++) {
+        const int c0 = half * (BN / 2) + blk * 32;
+        const int col = n0 + c0;
+        uint32_t v[32];
+        g_tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * BN + c0), v);
+        if (blk == NB - 1) {  // this warp's share of the accumulator buffer is in registers: hand the buffer back
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) g_mbar_arrive_cluster(b ? empty_bar1 : empty_bar0);
+        }
+        float f[32];
+        if (has_bias) {
+#pragma unroll
+          for (int j = 0; j < 8; j++) {
+            const float4 b4 = *reinterpret_cast<const float4*>(sb + blk * 32 + 4 * j);  // broadcast read
+            f[4 * j] = __uint_as_float(v[4 * j]) + b4.x;
+            f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b4.y;
+            f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b4.z;
+            f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b4.w;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; j++) f[j] = __uint_as_float(v[j]);
+        }
+        if (EFP(S3R_EPI_ROPE) && col < rope.cols) {
+          // 32 columns = one half head: (u, v) = (f[d], f[d + 16]), position y for the first half of a head, x for the second
+          const float2* tb = rope.table + (((col >> 5) & 1) ? px : py) * 16;
+#pragma unroll
+          for (int d = 0; d < 16; d++) {
+            const float2 cs = __ldg(tb + d);
+            const float u = f[d], w2 = f[d + 16];
+            f[d] = u * cs.x - w2 * cs.y;
+            f[d + 16] = w2 * cs.x + u * cs.y;
+          }
+        }
+        if (gelu) {
+#pragma unroll
+          for (int j = 0; j < 32; j++) f[j] = 0.5f * f[j] * (1.0f + g_fast_erf(f[j] * 0.70710678118654752f));
+        }
+        if (relu) {
+#pragma unroll
+          for (int j = 0; j < 32; j++) f[j] = fmaxf(f[j], 0.0f);
+        }
+        if (has_res) {
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            const uint32_t rw[4] = {rq[j].x, rq[j].y, rq[j].z, rq[j].w};
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+              const float2 rr = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rw[k]));
+              f[8 * j + 2 * k] += rr.x;
+              f[8 * j + 2 * k + 1] += rr.y;
+            }
+          }
+          // next block's residual segment: in flight during this block's stores and the next TMEM read.  C may alias
+          // the residual (x += f(x)): the segment a thread loads here is only ever written by that same thread, later.
+          if (blk + 1 < NB) load_res(blk + 1);
+        }
+        if (row_ok) {
+          if (out_f32) {
+            float* op = (float*)Cout + (size_t)row * ldc + col;
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+              if (col + 4 * j + 4 <= N)
+                *reinterpret_cast<float4*>(op + 4 * j) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+          } else {
+            __nv_bfloat16* op = (__nv_bfloat16*)Cout + (size_t)row * ldc + col;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+              if (col + 8 * j + 8 <= N) {
+                uint4 u;
+                *reinterpret_cast<__nv_bfloat162*>(&u.x) = __floats2bfloat162_rn(f[8 * j], f[8 * j + 1]);
+                *reinterpret_cast<__nv_bfloat162*>(&u.y) = __floats2bfloat162_rn(f[8 * j + 2], f[8 * j + 3]);
+                *reinterpret_cast<__nv_bfloat162*>(&u.z) = __floats2bfloat162_rn(f[8 * j + 4], f[8 * j + 5]);
+                *reinterpret_cast<__nv_bfloat162*>(&u.w) = __floats2bfloat162_rn(f[8 * j + 6], f[8 * j + 7]);
+                *reinterpret_cast<uint4*>(op + 8 * j) = u;
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+#undef EFP
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncwarp();
+  g_cluster_sync();  // no CTA of the pair retires (or frees TMEM) while the other still computes
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * BN) : "memory");
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------- host
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -699,7 +972,7 @@ int s3r_pdl_enabled() { return g_pdl; }
 static int g_gemm_ksplit = 0;    // S3R_TUNE_GEMM_KSPLIT: 0 = auto, 1 = never, 2 / 4 = force that cluster split-K factor on 64-wide tiles
 static int g_gemm_shallow = 0;   // S3R_TUNE_GEMM_SHALLOW: small grids use the 4-stage (96 KB, 2 CTAs/SM) ring too
 static int g_conv_cluster = 0;   // S3R_TUNE_CONV_CLUSTER: pairs of pixel tiles multicast the weight tile
-static int g_gemm_pair = 0;      // S3R_TUNE_GEMM_PAIR: CTA pairs (cta_group::2, M = 256 per MMA): 0 = auto, 1 = 256x128 pair tiles whenever possible, 2 = never, 3 = 256x256 pair tiles whenever possible
+static int g_gemm_pair = 0;      // S3R_TUNE_GEMM_PAIR: CTA pairs (cta_group::2, M = 256 per MMA): 0 = auto, 1 = 256x128 pair tiles whenever possible, 2 = never, 3 = 256x256 pair tiles whenever possible, 4 / 5 = PERSISTENT 256x128 / 256x256 pair tiles whenever possible
 
 static PFN_encodeTiled get_encode() {
   static PFN_encodeTiled fn = nullptr;
@@ -768,6 +1041,54 @@ static int launch_gemm(const CUtensorMap& a, const CUtensorMap& b, const void* b
   cfg.numAttrs = na;
   S3R_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, a, b, (const __nv_bfloat16*)bias, (const __nv_bfloat16*)residual, C, M, N, K,
                                     ldc, ldr, flags, rope, splits, ws, counters, conv, batch > 0 ? batch_stride_c : 0LL));
+  return S3R_OK;
+}
+
+// persistent CTA pairs: grid = 2 x min(#pair tiles, TPCs)
+template <int BN, int STAGES_, bool kConv, int EPI>
+static int launch_gemm_persist(const CUtensorMap& a, const CUtensorMap& b, const void* bias, const void* residual, void* C,
+                               int M, int N, int K, int ldc, int ldr, int flags, const RopeArgs& rope, cudaStream_t st,
+                               const ConvArgs& conv = ConvArgs{}) {
+  static size_t configured[64] = {};
+  static int pairs[64] = {};
+  const int smem = PersistSmem<BN, STAGES_>::TOTAL;
+  auto kern = s3r_gemm_pair_persistent_kernel<BN, STAGES_, kConv, EPI>;
+  {
+    const int rc_ = s3r_ensure_dynamic_smem(kern, (size_t)smem, configured);
+    if (rc_ != S3R_OK) return rc_;
+  }
+  int dev = 0;
+  S3R_CUDA_CHECK(cudaGetDevice(&dev));
+  dev &= 63;
+  if (pairs[dev] == 0) {
+    int sms = 0;
+    S3R_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    pairs[dev] = sms / 2 > 0 ? sms / 2 : 1;
+  }
+  const int mt_pairs = ((M + GEMM_BM - 1) / GEMM_BM + 1) / 2, nt = (N + BN - 1) / BN;
+  const int total = mt_pairs * nt;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * (unsigned)(total < pairs[dev] ? total : pairs[dev]), 1, 1);
+  cfg.blockDim = dim3(GEMM_P_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  attr[na].id = cudaLaunchAttributeClusterDimension;
+  attr[na].val.clusterDim.x = 2;
+  attr[na].val.clusterDim.y = 1;
+  attr[na].val.clusterDim.z = 1;
+  na++;
+  if (g_pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    na++;
+    flags |= S3R_EPI_PDL;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  S3R_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, a, b, (const __nv_bfloat16*)bias, (const __nv_bfloat16*)residual, C, M, N, K,
+                                    ldc, ldr, flags, rope, conv, mt_pairs, total));
   return S3R_OK;
 }
 
@@ -846,8 +1167,38 @@ extern "C" int s3r_gemm_bf16_rope(const void* A, const void* W, const void* bias
       // 1547 TFLOP/s; cuBLAS 1643) and lose to wave quantisation on the 1.4-wave grids of M = 4112; 256x128 pair tiles
       // (half the B ingress per CTA, same CTA count) win on the long-K / narrow-N shapes (4112x1024x4096: 30.7 -> 27.6 us,
       // 4112x768x3072: 24.1 -> 21.6)
-      if (N % 256 == 0 && mt * (N / 256) >= 4 * 296) pair_bn = 256;
-      else if (N % 128 == 0 && N <= 1024 && K >= 3072 && mt >= 16) pair_bn = 128;
+      if (N % 128 == 0 && N <= 1024 && K >= 3072 && mt >= 16) pair_bn = 128;  // (N % 256 != 0 cases the persistent kernel did not take)
+    }
+    int persist_bn = 0;
+    constexpr int E_PERSIST = S3R_EPI_BIAS | S3R_EPI_OUT_F32 | S3R_EPI_PDL | S3R_EPI_GELU | S3R_EPI_RESIDUAL | S3R_EPI_ROPE | S3R_EPI_RELU;
+    if (g_gemm_pair == 4 && mt >= 2 && N % 128 == 0) persist_bn = 128;
+    if (g_gemm_pair == 5 && mt >= 2 && N % 256 == 0) persist_bn = 256;
+    // auto: the many-row shapes (M = 4112 of cfg3).  Measured on B200 (scripts/bench_pair.py; bias / +gelu / +residual, us):
+    //   4112x3072x1024  30.0/39.6/42.1 -> 24.5/29.8/31.1     4112x4096x1024  33.2/45.7/65.1 -> 28.8/36.8/37.5
+    //   4112x1024x4096  30.3/33.3/36.6 -> 26.2/27.9/28.3     4112x768x3072   23.4/26.9/27.1 -> 22.1/23.9/24.1
+    // and slower below ~2000 rows (1028x3072x1024: 10.7 -> 12.6: a 256-row pair tile pads 1028 rows to 1280)
+    if (g_gemm_pair == 0 && M >= 2048 && N % 256 == 0 && ((mt + 1) / 2) * (long)(N / 256) >= 48) persist_bn = 256;
+    if (persist_bn && !t_pre_out && !(flags & ~E_PERSIST) && N % 8 == 0 && !(((uintptr_t)bias | (uintptr_t)residual) & 15)) {
+      if ((rc = make_map(&ta, A, M, K, lda, GEMM_BM)) != S3R_OK) return rc;
+      if ((rc = make_map(&tb, W, N, K, ldw, persist_bn / 2)) != S3R_OK) return rc;
+      cudaStream_t st = (cudaStream_t)stream;
+      constexpr int E_BASE = S3R_EPI_BIAS | S3R_EPI_OUT_F32 | S3R_EPI_PDL;
+      const int extra = flags & ~E_BASE;
+#define S3R_GEMM_PERSIST(BN_, ST_)                                                                                       \
+  do {                                                                                                                  \
+    if (extra == 0)                                                                                                     \
+      return launch_gemm_persist<BN_, ST_, false, E_BASE>(ta, tb, bias, residual, C, M, N, K, ldc, ldr, flags, rope, st); \
+    if (extra == S3R_EPI_GELU)                                                                                          \
+      return launch_gemm_persist<BN_, ST_, false, E_BASE | S3R_EPI_GELU>(ta, tb, bias, residual, C, M, N, K, ldc, ldr, flags, rope, st); \
+    if (extra == S3R_EPI_RESIDUAL)                                                                                      \
+      return launch_gemm_persist<BN_, ST_, false, E_BASE | S3R_EPI_RESIDUAL>(ta, tb, bias, residual, C, M, N, K, ldc, ldr, flags, rope, st); \
+    if (extra == S3R_EPI_ROPE)                                                                                          \
+      return launch_gemm_persist<BN_, ST_, false, E_BASE | S3R_EPI_ROPE>(ta, tb, bias, residual, C, M, N, K, ldc, ldr, flags, rope, st); \
+    return launch_gemm_persist<BN_, ST_, false, E_PERSIST>(ta, tb, bias, residual, C, M, N, K, ldc, ldr, flags, rope, st); \
+  } while (0)
+      if (persist_bn == 128) S3R_GEMM_PERSIST(128, 8);
+      S3R_GEMM_PERSIST(256, 6);
+#undef S3R_GEMM_PERSIST
     }
     if (pair_bn && !t_pre_out) {
       if ((rc = make_map(&ta, A, M, K, lda, GEMM_BM)) != S3R_OK) return rc;
@@ -1080,7 +1431,7 @@ extern "C" int s3r_set_tunable(int32_t key, int32_t value) {
     return S3R_OK;
   }
   if (key == S3R_TUNE_GEMM_PAIR) {
-    if (value < 0 || value > 3) return S3R_ERR_INVALID_ARG;
+    if (value < 0 || value > 5) return S3R_ERR_INVALID_ARG;
     g_gemm_pair = value;
     return S3R_OK;
   }
@@ -1175,7 +1526,21 @@ extern "C" int s3r_conv2d_bf16(const void* x, const void* w, const void* bias, c
     if (g_gemm_pair == 3 && mtiles >= 2 && cout % 256 == 0) pair_bn = 256;
     // measured: 3x3 256->256 at 16 x 128^2 / 4 x 256^2: 1189 -> 1231 TFLOP/s, at 2 x 128^2 1005 -> 1026; below that the grid is
     // smaller than the machine and the 128-wide single-CTA tile (twice the CTAs) wins
-    if (g_gemm_pair == 0 && cout % 256 == 0 && mtiles >= 256 && g_conv_variant < 0 && !cm_forced) pair_bn = 256;
+
+    constexpr int E_CONVP = S3R_EPI_BIAS | S3R_EPI_OUT_F32 | S3R_EPI_PDL | S3R_EPI_RESIDUAL | S3R_EPI_RELU;
+    // auto (measured, 3x3 convolutions): 256->256 at 16 x 128^2 1173 -> 1446 TFLOP/s (cuDNN bf16 NHWC 1185-1289), 16 x 64^2
+    // 1100 -> 1388, 2 x 128^2 1068 -> 1262, 2 x 64^2 499 -> 535; 128->128 at 2 x 256^2 693 -> 824, 16 x 256^2 794 -> 910
+    const bool auto_p = g_gemm_pair == 0 && g_conv_variant < 0 && !cm_forced &&
+                        ((cout % 256 == 0 && mtiles >= 64) || (cout % 128 == 0 && mtiles >= 256));
+    if ((g_gemm_pair == 4 || g_gemm_pair == 5 || auto_p) && mtiles >= 2 && !(flags & ~E_CONVP) && !(((uintptr_t)bias | (uintptr_t)residual) & 15)) {
+      const int pbn = ((g_gemm_pair == 5 || auto_p) && cout % 256 == 0) ? 256 : (cout % 128 == 0 ? 128 : 0);
+      if (pbn) {
+        if ((rc = make_map(&tb, w, cout, K, K, pbn / 2)) != S3R_OK) return rc;
+        if (pbn == 128)
+          return launch_gemm_persist<128, 8, true, E_CONVP>(ta, tb, bias, residual, y, (int)M, cout, K, cout, cout, flags, rope, st, conv);
+        return launch_gemm_persist<256, 6, true, E_CONVP>(ta, tb, bias, residual, y, (int)M, cout, K, cout, cout, flags, rope, st, conv);
+      }
+    }
     if (pair_bn) {
       if ((rc = make_map(&tb, w, cout, K, K, pair_bn / 2)) != S3R_OK) return rc;
       if (pair_bn == 128)

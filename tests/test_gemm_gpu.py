@@ -50,22 +50,28 @@ def test_gemm_batched_leading_dims_and_strided_rows():
     assert (y.float() - expect).abs().max() <= 1e-2 * expect.abs().max()
 
 
-@pytest.mark.parametrize("M,H", [(514, 16), (257, 12), (771, 12)])
-def test_gemm_with_fused_rope_epilogue_matches_gemm_then_rope_oracle(M, H):
+@pytest.mark.parametrize("M,H,pair", [(514, 16, 0), (257, 12, 0), (771, 12, 0), (514, 16, 5), (771, 12, 5), (2570, 16, 0)])
+def test_gemm_with_fused_rope_epilogue_matches_gemm_then_rope_oracle(M, H, pair):
     """qkv projection with RoPE-2D on the q and k thirds fused in the epilogue == fp32 GEMM followed by the RoPE
-    oracle (oracle/rope_oracle.c restating curope.cpp:11-47)."""
+    oracle (oracle/rope_oracle.c restating curope.cpp:11-47).  pair = 5: the persistent CTA-pair kernel's register
+    epilogue (rotation pairs inside one thread); M = 2570 takes that kernel through the automatic dispatch."""
     import numpy as np
     import torch
     from oracle import raster_oracle as ro
+    from styl3r_b200 import _lib
     from styl3r_b200.gemm import linear
+    _lib.check(_lib.lib().s3r_set_tunable(11, pair))
     torch.manual_seed(M)
     C_ = H * 64
     x = (torch.randn(M, C_, device="cuda") * 0.5).to(torch.bfloat16)
     w = (torch.randn(3 * C_, C_, device="cuda") * C_ ** -0.5).to(torch.bfloat16)
     b = (torch.randn(3 * C_, device="cuda") * 0.1).to(torch.bfloat16)
     pos = torch.randint(0, 17, (M, 2), device="cuda")
-    y = linear(x, w, b, rope_pos=pos, rope_cols=2 * C_, rope_base=100.0)
-    torch.cuda.synchronize()
+    try:
+        y = linear(x, w, b, rope_pos=pos, rope_cols=2 * C_, rope_base=100.0)
+        torch.cuda.synchronize()
+    finally:
+        _lib.lib().s3r_set_tunable(11, 0)
     ref = (x.float() @ w.float().t() + b.float()).cpu().numpy().reshape(1, M, 3, H, 64)
     expect = ref.copy()
     for part in (0, 1):  # q and k thirds
@@ -122,13 +128,14 @@ def test_gemm_cluster_multicast_variants_match_reference(code, M, N, K, big):
     assert torch.equal(y, base) or (y.float() - base.float()).abs().max().item() <= 2 ** -6
 
 
-@pytest.mark.parametrize("mode", [1, 3])
-@pytest.mark.parametrize("M,N,K", [(514, 3072, 1024), (257, 768, 768), (4112, 1024, 4096), (1300, 512, 200), (129, 256, 64)])
+@pytest.mark.parametrize("mode", [1, 3, 4, 5])
+@pytest.mark.parametrize("M,N,K", [(514, 3072, 1024), (257, 768, 768), (4112, 1024, 4096), (1300, 512, 200), (129, 256, 64), (300, 264, 72)])
 @pytest.mark.parametrize("epi", ["bias", "bias_gelu", "bias_res", "none_f32"])
 def test_gemm_cta_pair_variants_match_reference(mode, M, N, K, epi):
-    """CTA pairs (tcgen05 cta_group::2, S3R_TUNE_GEMM_PAIR = 1: 256x128 pair tiles, 3: 256x256): one 256-row MMA over the
-    two SMs of a TPC, each CTA stages its own A rows and half of the B tile; includes ragged M (odd number of 128-row
-    tiles: the padding CTA of the last pair loads zeros and stores nothing) and a K tail."""
+    """CTA pairs (tcgen05 cta_group::2, S3R_TUNE_GEMM_PAIR = 1: 256x128 pair tiles, 3: 256x256; 4 / 5: the PERSISTENT pair
+    kernel with the double-buffered TMEM accumulator and the register epilogue): one 256-row MMA over the two SMs of a
+    TPC, each CTA stages its own A rows and half of the B tile; includes ragged M (odd number of 128-row tiles: the
+    padding CTA of the last pair loads zeros and stores nothing), a K tail and an N that is not a multiple of the tile."""
     import torch
     from styl3r_b200 import _lib
     from styl3r_b200.gemm import linear
@@ -163,7 +170,7 @@ def test_conv_cta_pair_matches_plain():
         try:
             _lib.check(L.s3r_set_tunable(11, 2))
             base = conv2d_nhwc(x, wp, (3, 3), bias=bias, relu=True)
-            for mode in (1, 3):
+            for mode in (1, 3, 4, 5):
                 _lib.check(L.s3r_set_tunable(11, mode))
                 y = conv2d_nhwc(x, wp, (3, 3), bias=bias, relu=True)
                 torch.cuda.synchronize()
