@@ -420,6 +420,72 @@ def run_ours(args):
         e2e_ms = float(tms.item())
     e2e_val = world * V_TGT * Ke / (e2e_ms / 1e3)
 
+    # ---- what bounds e2e: the same bytes per request moved by plain pinned copies (no kernels) on the same streams -
+    # the host<->device ceiling of this box at this rank count (all ranks copy at once, max over ranks)
+    def copy_loop(count):  # the sessions' own pinned buffers and device tensors: exactly the copies a request makes
+        for i in range(count):
+            sl = i % n_slots
+            with torch.cuda.stream(e2e_streams[sl % n_e2e_streams]):
+                se = sessions[sl]
+                se._copy_in()
+                se.color_host.copy_(se._plan.color, non_blocking=True)
+        torch.cuda.synchronize()
+
+    copy_loop(8)
+    barrier()
+    t0 = time.perf_counter()
+    copy_loop(200)
+    copy_ms = (time.perf_counter() - t0) * 1e3
+    if dist is not None:
+        tms = torch.tensor([copy_ms], device=dev)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        copy_ms = float(tms.item())
+    pcie_ceiling = world * V_TGT * 200 / (copy_ms / 1e3)
+
+    # ---- the same serving path when one upload feeds several target views (the shape of cfg3 / cfg4: 6 views per scene):
+    # the Gaussians cross PCIe once per scene, cameras in / images out per view
+    e2e_multi = None
+    try:
+        V6 = 6
+        from styl3r_b200 import synthetic as syn
+        sess6 = []
+        for i6 in range(min(4, n_slots)):
+            sc6 = syn.make_scene(seed=4321 + i6, v=V_CTX, V=V6, hw=HW)
+            pin6 = lambda a: torch.as_tensor(np.ascontiguousarray(a)).pin_memory()
+            tri6 = sc6["covariances"][:, [0, 0, 0, 1, 1, 2], [0, 1, 2, 1, 2, 2]]
+            h6 = dict(extrinsics=pin6(sc6["extrinsics"]), intrinsics=pin6(sc6["intrinsics"]), near=pin6(sc6["near"]),
+                      far=pin6(sc6["far"]), background=torch.zeros(V6, 3).pin_memory(), means=pin6(sc6["means"][None]),
+                      covariances=pin6(tri6[None]), harmonics=pin6(sc6["harmonics"][None]), opacities=pin6(sc6["opacities"][None]))
+            sess6.append(RenderSession(h6, (HW, HW), scale_invariant=True))
+        h2d6 = sum(v.numel() * v.element_size() for v in sess6[0].host.values())
+
+        def loop6(count):
+            for i in range(count):
+                with torch.cuda.stream(e2e_streams[i % n_e2e_streams]):
+                    sess6[i % len(sess6)].run()
+            torch.cuda.synchronize()
+            for s_ in sess6:
+                s_.check()
+
+        n6 = max(40, min(Ke // V6, 200))
+        with torch.no_grad():
+            loop6(2 * len(sess6))
+            barrier()
+            t0 = time.perf_counter()
+            loop6(n6)
+            ms6 = (time.perf_counter() - t0) * 1e3
+        if dist is not None:
+            tms = torch.tensor([ms6], device=dev)
+            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+            ms6 = float(tms.item())
+        e2e_multi = {"value": world * V6 * n6 / (ms6 / 1e3), "unit": "views/s", "views_per_upload": V6,
+                     "h2d_bytes_per_view": h2d6 / V6, "d2h_bytes_per_view": 3 * HW * HW * 4, "requests": n6,
+                     "what": "RenderSession.run() with 6 target views per uploaded scene (cfg3 / cfg4 shape): the Gaussians cross "
+                             "PCIe once per scene; host wall clock, max over ranks"}
+        del sess6
+    except Exception as e:  # supplementary
+        e2e_multi = {"error": repr(e)[:200]}
+
     cb = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cb = cpu_baseline()
@@ -554,7 +620,12 @@ def run_ours(args):
             "clocks": clk.summary(),
             "e2e": {"value": e2e_val, "unit": "views/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                     "steps": Ke, "api": "styl3r_b200.decoder.RenderSession.run(): pinned host Gaussians (covariances as the packed cov3D_precomp triangle the reference hands to its rasterizer) + cameras -> H2D -> camera kernel -> "
-                           f"raster chain -> D2H pinned image (one CUDA graph per request buffer, {n_e2e_streams} streams)"},
+                           f"raster chain -> D2H pinned image (one CUDA graph per request buffer, {n_e2e_streams} streams)",
+                    "pcie_ceiling_views_per_s": pcie_ceiling,
+                    "pcie_ceiling_what": "the same H2D + D2H bytes per request as plain pinned copies on the same streams, no kernels, all ranks at "
+                                         "once (max over ranks): e2e / ceiling = " + f"{e2e_val / pcie_ceiling:.2f}",
+                    "h2d_gbs": e2e_val * h2d_bytes / 1e9},
+            "e2e_multi_view": e2e_multi,
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": "s3r_blend_fwd_kernel", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,

@@ -381,11 +381,8 @@ extern "C" int s3r_attention_bf16(const void* q, const void* k, const void* v, v
   if ((rc = att_make_map(&tq, q, B, Nq, H, q_strides[0], q_strides[1], q_strides[2], ATT_BM)) != S3R_OK) return rc;
   if ((rc = att_make_map(&tk, k, B, Nk, H, k_strides[0], k_strides[1], k_strides[2], ATT_BN)) != S3R_OK) return rc;
   if ((rc = att_make_map(&tv, v, B, Nk, H, v_strides[0], v_strides[1], v_strides[2], ATT_BN)) != S3R_OK) return rc;
-  static bool configured = false;
-  if (!configured) {
-    S3R_CUDA_CHECK(cudaFuncSetAttribute(s3r_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AttSmem::TOTAL));
-    configured = true;
-  }
+  static size_t configured[64] = {};  // per device (cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute)
+  if ((rc = s3r_ensure_dynamic_smem(s3r_attention_kernel, (size_t)AttSmem::TOTAL, configured)) != S3R_OK) return rc;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((Nq + ATT_BM - 1) / ATT_BM, H, B);
   cfg.blockDim = dim3(ATT_THREADS, 1, 1);

@@ -10,7 +10,10 @@
 #define LN_WARPS 4
 #define LN_MAX_VEC 8  // 8 x (32 lanes x 8 bf16) = 2048 channels
 
-template <typename Tin>
+// NV: compile-time number of 256-channel vectors per row (3 = 768, 4 = 1024 channels: the two trunk widths) so that only
+// the registers the row needs are allocated (95 -> ~60: 8 instead of 5 CTAs per SM), 0 = generic (C <= 2048).  The affine
+// parameters are requested together with the row, not after the two reductions (one dependent memory round trip less).
+template <typename Tin, int NV>
 __global__ void __launch_bounds__(32 * LN_WARPS) s3r_layernorm_kernel(const Tin* __restrict__ x,
                                                                       const __nv_bfloat16* __restrict__ w,
                                                                       const __nv_bfloat16* __restrict__ b,
@@ -22,13 +25,22 @@ __global__ void __launch_bounds__(32 * LN_WARPS) s3r_layernorm_kernel(const Tin*
   }
   const int row = blockIdx.x * LN_WARPS + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= M) return;
-  const int nvec = C / 256;  // full 32-lane x 8-element vectors per row (C % 256 == 0)
-  float v[LN_MAX_VEC][8];
+  constexpr int NMAX = NV ? NV : LN_MAX_VEC;
+  const int nvec = NV ? NV : C / 256;  // full 32-lane x 8-element vectors per row (C % 256 == 0)
+  float v[NMAX][8];
   float sum = 0.f;
+  uint4 uwv[NMAX], ubv[NMAX];
+  if (NV) {
+#pragma unroll
+    for (int i = 0; i < NMAX; i++) {
+      uwv[i] = __ldg(reinterpret_cast<const uint4*>(w) + i * 32 + lane);
+      ubv[i] = __ldg(reinterpret_cast<const uint4*>(b) + i * 32 + lane);
+    }
+  }
   if (sizeof(Tin) == 4) {  // fp32 residual stream: two 16-byte loads per 8 elements
     const float4* xr = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(x) + (long long)row * ldx);
 #pragma unroll
-    for (int i = 0; i < LN_MAX_VEC; i++) {
+    for (int i = 0; i < NMAX; i++) {
       if (i < nvec) {
         const float4 a = xr[(i * 32 + lane) * 2], b2 = xr[(i * 32 + lane) * 2 + 1];
         v[i][0] = a.x, v[i][1] = a.y, v[i][2] = a.z, v[i][3] = a.w;
@@ -39,7 +51,7 @@ __global__ void __launch_bounds__(32 * LN_WARPS) s3r_layernorm_kernel(const Tin*
   } else {
     const uint4* xr = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(x) + (long long)row * ldx);
 #pragma unroll
-    for (int i = 0; i < LN_MAX_VEC; i++) {
+    for (int i = 0; i < NMAX; i++) {
       if (i < nvec) {
         const uint4 u = xr[i * 32 + lane];
         const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
@@ -57,7 +69,7 @@ __global__ void __launch_bounds__(32 * LN_WARPS) s3r_layernorm_kernel(const Tin*
   const float mean = sum / (float)C;
   float sq = 0.f;
 #pragma unroll
-  for (int i = 0; i < LN_MAX_VEC; i++) {
+  for (int i = 0; i < NMAX; i++) {
     if (i < nvec) {
 #pragma unroll
       for (int t = 0; t < 8; t++) {
@@ -73,9 +85,9 @@ __global__ void __launch_bounds__(32 * LN_WARPS) s3r_layernorm_kernel(const Tin*
   const uint4* wr = reinterpret_cast<const uint4*>(w);
   const uint4* br = reinterpret_cast<const uint4*>(b);
 #pragma unroll
-  for (int i = 0; i < LN_MAX_VEC; i++) {
+  for (int i = 0; i < NMAX; i++) {
     if (i < nvec) {
-      const uint4 uw = wr[i * 32 + lane], ub = br[i * 32 + lane];
+      const uint4 uw = NV ? uwv[i] : wr[i * 32 + lane], ub = NV ? ubv[i] : br[i * 32 + lane];
       const __nv_bfloat162* hw = reinterpret_cast<const __nv_bfloat162*>(&uw);
       const __nv_bfloat162* hb = reinterpret_cast<const __nv_bfloat162*>(&ub);
       uint4 o;
@@ -110,7 +122,8 @@ static int launch_layernorm(const Tin* x, const void* weight, const void* bias, 
     cfg.attrs = attr;
     cfg.numAttrs = 1;
   }
-  S3R_CUDA_CHECK(cudaLaunchKernelEx(&cfg, s3r_layernorm_kernel<Tin>, x, (const __nv_bfloat16*)weight,
+  auto kern = C == 1024 ? s3r_layernorm_kernel<Tin, 4> : (C == 768 ? s3r_layernorm_kernel<Tin, 3> : s3r_layernorm_kernel<Tin, 0>);
+  S3R_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, x, (const __nv_bfloat16*)weight,
                                     (const __nv_bfloat16*)bias, (__nv_bfloat16*)y, (int)M, (int)C, (long long)ldx, eps, pdl));
   return S3R_OK;
 }

@@ -174,8 +174,10 @@ def _fusion(f, x: Tensor, skip: Tensor | None = None) -> Tensor:
         w1, b1, w2, b2 = f["resConfUnit1"]
         t = conv2d_nhwc(torch.relu(skip), w1, (3, 3), bias=b1, relu=True)
         x = conv2d_nhwc(t, w2, (3, 3), bias=b2, residual=skip + x)
-    up = upsample2x_nhwc(_rcu(x, f["resConfUnit2"]))
-    return linear(up, f["out_w"], f["out_b"])
+    # out_conv (1x1) BEFORE the bilinear x2: a per-pixel channel mix commutes with an interpolation whose weights sum to
+    # one (bias included), so the GEMM runs on a quarter of the pixels (reference order: heads/dpt_block.py:189-218)
+    t = _rcu(x, f["resConfUnit2"])
+    return upsample2x_nhwc(linear(t, f["out_w"], f["out_b"]))
 
 
 def dpt_forward_nhwc(m: "DPTAdapter", tokens: List[Tensor], image_size, img: Tensor | None = None) -> Tensor:

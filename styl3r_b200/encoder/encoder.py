@@ -145,14 +145,17 @@ class AsymmetricCroCoMulti(CroCoTrunk):
         cur = _lin(self.decoder_embed, feat, stream=True)
         pos_ctx = self._others(pos)
         blocks2 = self.dec_blocks2 if self.asymmetric else self.dec_blocks
+        # loop-invariant position slices (a [b, v-1, ...] slice of a batched tensor is a copy: once, not once per layer)
+        pos0, pctx0 = pos[:, 0], pos_ctx[:, 0]
+        pos1 = pos[:, 1:].reshape(b * (v - 1), *pos.shape[2:]) if v > 1 else None
+        pctx1 = pos_ctx[:, 1:].reshape(b * (v - 1), *pos_ctx.shape[2:]) if v > 1 else None
         for blk1, blk2 in zip(self.dec_blocks, blocks2):
             ctx = self._others(cur)
-            branches = [lambda: blk1(cur[:, 0], ctx[:, 0], pos[:, 0], pos_ctx[:, 0], parallel=parallel)]
+            branches = [lambda: blk1(cur[:, 0], ctx[:, 0], pos0, pctx0, parallel=parallel)]
             if v > 1:
                 branches.append(lambda: blk2(
                     cur[:, 1:].reshape(b * (v - 1), *cur.shape[2:]), ctx[:, 1:].reshape(b * (v - 1), *ctx.shape[2:]),
-                    pos[:, 1:].reshape(b * (v - 1), *pos.shape[2:]), pos_ctx[:, 1:].reshape(b * (v - 1), *pos_ctx.shape[2:]),
-                    parallel=parallel))
+                    pos1, pctx1, parallel=parallel))
             res = fork_join(branches, feat.device, parallel=parallel)
             parts = [res[0][:, None]]
             if v > 1:
