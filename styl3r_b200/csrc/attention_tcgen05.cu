@@ -2,8 +2,9 @@
 // contraction the reference delegates to xformers.ops.memory_efficient_attention
 // (src/model/encoder/backbone/croco/blocks.py:126-130,192-196) on [B, N, H, 64] tensors.
 //
-// Shapes in Styl3R are short (Nq, Nk in {256, 257, 514, 771, 1028}) so the kernel favours simplicity over an online
-// softmax: TWO passes over the keys per 128-query tile — pass 1 finds the exact row maxima (S = Q K^T only), pass 2
+// Two kernels (S3R_TUNE_ATTN_ONEPASS): the default ONE-PASS kernel further down (s3r_attention1_kernel) and the original
+// two-pass kernel described here.  Shapes in Styl3R are short (Nq, Nk in {256, 257, 514, 771, 1028}); the two-pass kernel
+// favours simplicity over an online softmax: TWO passes over the keys per 128-query tile — pass 1 finds the exact row maxima (S = Q K^T only), pass 2
 // recomputes S tile by tile, forms P = exp2((S - max) * scale * log2e) and accumulates O += P V.  No running-max
 // correction of O is ever needed; the extra Q K^T costs one third more tensor work, which is negligible here.
 //
@@ -107,6 +108,19 @@ __device__ __forceinline__ void a_tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void a_tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, "
+      "%25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]),
+      "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]),
+      "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
 __device__ __forceinline__ float a_ex2(float x) {  // MUFU.EX2 (flush-to-zero)
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -119,8 +133,8 @@ struct AttSmem {  // offsets from a 1024-B aligned base
   static constexpr int V = K + ATT_KV_STAGES * 8192; // ATT_KV_STAGES x 8 KB
   static constexpr int P = V + ATT_KV_STAGES * 8192; // 128 x 64 bf16 = 16 KB
   static constexpr int BARS = P + 16384;
-  static constexpr int RED = BARS + 256;             // [2][128] floats: row max / row sum partials of the column halves
-  static constexpr int TOTAL = RED + 1024 + 1024;
+  static constexpr int RED = BARS + 256;             // [2][2][128] floats: row max / row sum partials of the column halves
+  static constexpr int TOTAL = RED + 2048 + 1024;
 };
 
 __global__ void __launch_bounds__(ATT_THREADS, 2)
@@ -335,6 +349,246 @@ s3r_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// ONE-PASS variant (longer key sequences: the 771 / 1028-key cross-view and stylizer attentions of v >= 3): every K tile is
+// loaded and contracted once.  Instead of an online softmax with a per-tile exchange between the two threads that share a
+// query row (column halves of the 64-key tile), EACH HALF IS ITS OWN SOFTMAX STREAM: it keeps its own reference maximum and
+// row sum and accumulates into its own O accumulator in TMEM (O_a: keys 0-31 of every tile = k-steps 0,1 of the P V MMA;
+// O_b: keys 32-63 = k-steps 2,3), so no cross-warp traffic exists inside the loop; the two streams are merged once in
+// the epilogue: O = (O_a 2^(m_a-m) + O_b 2^(m_b-m)) / (l_a 2^(m_a-m) + l_b 2^(m_b-m)).
+// The reference maximum is LAZY: P = exp2(S c - m_ref) may exceed 1 (bf16 / fp32 share the exponent range); only when a
+// tile's maximum exceeds m_ref by more than 2^6 does the thread rescale its O row in TMEM (tcgen05.ld / st) - between
+// the p_empty wait (P V of the previous tile has completed) and its p_full arrival (the next P V cannot start), i.e. with
+// exclusive access and no extra synchronisation.  The result is the exact softmax up to rounding.
+__global__ void __launch_bounds__(ATT_THREADS, 2)
+s3r_attention1_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                      const __grid_constant__ CUtensorMap tmV, __nv_bfloat16* __restrict__ O, int H, int Nq, int Nk,
+                      long long so_b, long long so_n, long long so_h, float scale_log2e, int pdl) {
+  extern __shared__ uint8_t att_smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)att_smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = (uint64_t*)(smem + AttSmem::BARS);
+  uint64_t* q_full = bars + 0;
+  uint64_t* k_full = bars + 1;
+  uint64_t* k_empty = k_full + ATT_KV_STAGES;
+  uint64_t* v_full = k_empty + ATT_KV_STAGES;
+  uint64_t* v_empty = v_full + ATT_KV_STAGES;
+  uint64_t* s_full = v_empty + ATT_KV_STAGES;  // [2]
+  uint64_t* s_empty = s_full + 2;              // [2]
+  uint64_t* p_full = s_empty + 2;
+  uint64_t* p_empty = p_full + 1;
+  uint64_t* o_full = p_empty + 1;
+  uint32_t* tmem_slot = (uint32_t*)(o_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * ATT_BM, h = blockIdx.y, b = blockIdx.z;
+  const int nkv = (Nk + ATT_BN - 1) / ATT_BN;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmQ) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmK) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmV) : "memory");
+    a_mbar_init(q_full, 1);
+    for (int s = 0; s < ATT_KV_STAGES; s++) {
+      a_mbar_init(&k_full[s], 1);
+      a_mbar_init(&k_empty[s], 1);
+      a_mbar_init(&v_full[s], 1);
+      a_mbar_init(&v_empty[s], 1);
+    }
+    for (int s = 0; s < 2; s++) {
+      a_mbar_init(&s_full[s], 1);
+      a_mbar_init(&s_empty[s], ATT_SM_WARPS);
+    }
+    a_mbar_init(p_full, ATT_SM_WARPS);
+    a_mbar_init(p_empty, 1);
+    a_mbar_init(o_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(a_smem_u32(tmem_slot)), "r"(256)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_S = tmem_base, tmem_Oa = tmem_base + 128, tmem_Ob = tmem_base + 192;  // S0, S1, O_a, O_b: 64 columns each
+  if (pdl) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+  }
+
+  if (warp == 0) {
+    if (lane == 0) {
+      a_mbar_expect_tx(q_full, 16384);
+      a_tma_load_4d(smem + AttSmem::Q, &tmQ, 0, h, q0, b, q_full);
+      for (int it = 0; it < nkv; it++) {
+        const int s = it % ATT_KV_STAGES;
+        a_mbar_wait(&k_empty[s], ((it / ATT_KV_STAGES) & 1) ^ 1);
+        a_mbar_expect_tx(&k_full[s], 8192);
+        a_tma_load_4d(smem + AttSmem::K + s * 8192, &tmK, 0, h, it * ATT_BN, b, &k_full[s]);
+        a_mbar_wait(&v_empty[s], ((it / ATT_KV_STAGES) & 1) ^ 1);
+        a_mbar_expect_tx(&v_full[s], 8192);
+        a_tma_load_4d(smem + AttSmem::V + s * 8192, &tmV, 0, h, it * ATT_BN, b, &v_full[s]);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc_s = a_make_idesc(ATT_BM, ATT_BN, 0);
+      const uint32_t idesc_o = a_make_idesc(ATT_BM, ATT_D, 1);
+      const uint64_t qdesc = a_make_desc(smem + AttSmem::Q);
+      const uint64_t pdesc = a_make_desc(smem + AttSmem::P);
+      a_mbar_wait(q_full, 0);
+      auto issue_pv = [&](int jj) {  // O_a += P(jj)[:, 0:32] V_jj[0:32], O_b += P(jj)[:, 32:64] V_jj[32:64]
+        const int sv = jj % ATT_KV_STAGES;
+        a_mbar_wait(&v_full[sv], (jj / ATT_KV_STAGES) & 1);
+        a_mbar_wait(p_full, jj & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint64_t vdesc = a_make_desc(smem + AttSmem::V + sv * 8192);
+#pragma unroll
+        for (int k = 0; k < ATT_BN / 16; k++)
+          a_umma(k < 2 ? tmem_Oa : tmem_Ob, pdesc + (uint64_t)(2 * k), vdesc + (uint64_t)(128 * k), idesc_o,
+                 (jj | (k & 1)) ? 1u : 0u);
+        a_umma_commit(&v_empty[sv]);
+        a_umma_commit(p_empty);
+      };
+      for (int it = 0; it < nkv; it++) {
+        const int s = it & 1, ks = it % ATT_KV_STAGES;
+        a_mbar_wait(&k_full[ks], (it / ATT_KV_STAGES) & 1);
+        a_mbar_wait(&s_empty[s], ((it >> 1) & 1) ^ 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint64_t kdesc = a_make_desc(smem + AttSmem::K + ks * 8192);
+#pragma unroll
+        for (int k = 0; k < ATT_D / 16; k++)
+          a_umma(tmem_S + (uint32_t)(s * 64), qdesc + (uint64_t)(2 * k), kdesc + (uint64_t)(2 * k), idesc_s, k ? 1u : 0u);
+        a_umma_commit(&k_empty[ks]);
+        a_umma_commit(&s_full[s]);
+        if (it >= 1) issue_pv(it - 1);  // one tile behind: S(it) runs while the softmax warps make P(it-1)
+      }
+      issue_pv(nkv - 1);
+      a_umma_commit(o_full);
+    }
+  } else {
+    const int qd = warp & 3;
+    const int ch = (warp - 2) >> 2;
+    const int row = qd * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(qd * 32) << 16;
+    const uint32_t tmem_Omine = ch ? tmem_Ob : tmem_Oa;
+    float* red = reinterpret_cast<float*>(smem + AttSmem::RED);   // [2][2][128]: (m_ref, l) of the two halves
+    float mref = -INFINITY;  // reference maximum in the scaled log2 domain (S * scale * log2e)
+    float l = 0.f;
+    uint8_t* prow = smem + AttSmem::P + row * 128;
+    for (int it = 0; it < nkv; it++) {
+      a_mbar_wait(&s_full[it & 1], (it >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      uint32_t v0[32];
+      a_tmem_ld32(tmem_S + (uint32_t)((it & 1) * 64) + lane_base + (uint32_t)(ch * 32), v0);
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) a_mbar_arrive(&s_empty[it & 1]);
+      const int valid = Nk - it * ATT_BN - ch * 32;  // my columns >= valid are the zero-filled key tail (warp-uniform)
+      float p[32];
+      float factor = 1.0f;     // what the accumulated l / O row must be multiplied by (!= 1: the reference moved)
+      bool rescale = false;
+      if (valid > 0) {
+        float tm = -INFINITY;
+        if (valid >= 32) {
+#pragma unroll
+          for (int c = 0; c < 32; c++) tm = fmaxf(tm, __uint_as_float(v0[c]));
+        } else {
+#pragma unroll
+          for (int c = 0; c < 32; c++)
+            if (c < valid) tm = fmaxf(tm, __uint_as_float(v0[c]));
+        }
+        const float ts = tm * scale_log2e;
+        if (ts > mref + 6.0f) {  // (always true for the first valid tile: mref = -inf)
+          factor = a_ex2(mref - ts);  // exp2(-inf) = 0 for the first tile
+          rescale = l > 0.f;          // nothing accumulated yet -> the O row needs no correction
+          mref = ts;
+        }
+        if (valid >= 32) {
+#pragma unroll
+          for (int c = 0; c < 32; c++) p[c] = a_ex2(fmaf(__uint_as_float(v0[c]), scale_log2e, -mref));
+        } else {
+#pragma unroll
+          for (int c = 0; c < 32; c++) p[c] = c < valid ? a_ex2(fmaf(__uint_as_float(v0[c]), scale_log2e, -mref)) : 0.f;
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 32; c++) p[c] = 0.f;
+      }
+      float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+#pragma unroll
+      for (int c = 0; c < 32; c += 4) l0 += p[c], l1 += p[c + 1], l2 += p[c + 2], l3 += p[c + 3];
+      l = l * factor + ((l0 + l1) + (l2 + l3));
+      a_mbar_wait(p_empty, (it & 1) ^ 1);  // P V of the previous tile has completed: P buffer free, O rows stable
+      if (__any_sync(0xffffffffu, rescale)) {
+        // rare (the running maximum settles within the first tiles): scale this thread's row of its own accumulator
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const float f = rescale ? factor : 1.0f;
+#pragma unroll 1
+        for (int hcol = 0; hcol < 2; hcol++) {
+          uint32_t o[32];
+          a_tmem_ld32(tmem_Omine + lane_base + (uint32_t)(hcol * 32), o);
+#pragma unroll
+          for (int c = 0; c < 32; c++) o[c] = __float_as_uint(__uint_as_float(o[c]) * f);
+          a_tmem_st32(tmem_Omine + lane_base + (uint32_t)(hcol * 32), o);
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      }
+#pragma unroll
+      for (int c16 = 0; c16 < 4; c16++) {
+        uint4 u;
+        __nv_bfloat162* hh = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+        for (int t = 0; t < 4; t++) hh[t] = __floats2bfloat162_rn(p[c16 * 8 + 2 * t], p[c16 * 8 + 2 * t + 1]);
+        *reinterpret_cast<uint4*>(prow + (((ch * 4 + c16) ^ (row & 7)) << 4)) = u;
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) a_mbar_arrive(p_full);
+    }
+    // merge the two softmax streams of a row
+    red[(ch * 2 + 0) * 128 + row] = mref;
+    red[(ch * 2 + 1) * 128 + row] = l;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    const float mo = red[((ch ^ 1) * 2 + 0) * 128 + row], lo = red[((ch ^ 1) * 2 + 1) * 128 + row];
+    const float m = fmaxf(mref, mo);
+    const float w_me = a_ex2(mref - m), w_ot = a_ex2(mo - m);  // exp2(-inf) = 0: a stream that never saw a valid key
+    const float inv = 1.0f / (l * w_me + lo * w_ot);
+    const float wa = (ch ? w_ot : w_me) * inv, wb = (ch ? w_me : w_ot) * inv;
+    a_mbar_wait(o_full, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    uint32_t oa[32], ob[32];
+    a_tmem_ld32(tmem_Oa + lane_base + (uint32_t)(ch * 32), oa);
+    a_tmem_ld32(tmem_Ob + lane_base + (uint32_t)(ch * 32), ob);
+    const int qrow = q0 + row;
+    if (qrow < Nq) {
+      __nv_bfloat16* op = O + (long long)b * so_b + (long long)qrow * so_n + (long long)h * so_h + ch * 32;
+#pragma unroll
+      for (int c = 0; c < 32; c += 8) {
+        uint4 u;
+        __nv_bfloat162* hu = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+        for (int t = 0; t < 4; t++)
+          hu[t] = __floats2bfloat162_rn(__uint_as_float(oa[c + 2 * t]) * wa + __uint_as_float(ob[c + 2 * t]) * wb,
+                                        __uint_as_float(oa[c + 2 * t + 1]) * wa + __uint_as_float(ob[c + 2 * t + 1]) * wb);
+        *reinterpret_cast<uint4*>(op + c) = u;
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256) : "memory");
+  }
+}
+
+// S3R_TUNE_ATTN_ONEPASS: 0 / 1 = one pass (default), 2 = the two-pass kernel
+static int g_attn_onepass = 0;
+int& s3r_attn_onepass() { return g_attn_onepass; }
+
 typedef CUresult (*PFN_encodeTiledA)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                      const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                      CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -381,8 +635,13 @@ extern "C" int s3r_attention_bf16(const void* q, const void* k, const void* v, v
   if ((rc = att_make_map(&tq, q, B, Nq, H, q_strides[0], q_strides[1], q_strides[2], ATT_BM)) != S3R_OK) return rc;
   if ((rc = att_make_map(&tk, k, B, Nk, H, k_strides[0], k_strides[1], k_strides[2], ATT_BN)) != S3R_OK) return rc;
   if ((rc = att_make_map(&tv, v, B, Nk, H, v_strides[0], v_strides[1], v_strides[2], ATT_BN)) != S3R_OK) return rc;
-  static size_t configured[64] = {};  // per device (cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute)
+  static size_t configured[64] = {}, configured1[64] = {};  // per device (cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute)
   if ((rc = s3r_ensure_dynamic_smem(s3r_attention_kernel, (size_t)AttSmem::TOTAL, configured)) != S3R_OK) return rc;
+  if ((rc = s3r_ensure_dynamic_smem(s3r_attention1_kernel, (size_t)AttSmem::TOTAL, configured1)) != S3R_OK) return rc;
+  const int nkv_tiles = (Nk + ATT_BN - 1) / ATT_BN;
+  // measured on B200 (scripts/bench_attn.py): one pass wins on every encoder shape (257^2: 9.4 -> 7.8 us, 1028^2: 45.0 -> 35.1)
+  const bool one_pass = g_attn_onepass != 2;
+  (void)nkv_tiles;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((Nq + ATT_BM - 1) / ATT_BM, H, B);
   cfg.blockDim = dim3(ATT_THREADS, 1, 1);
@@ -396,7 +655,7 @@ extern "C" int s3r_attention_bf16(const void* q, const void* k, const void* v, v
     cfg.attrs = attr;
     cfg.numAttrs = 1;
   }
-  S3R_CUDA_CHECK(cudaLaunchKernelEx(&cfg, s3r_attention_kernel, tq, tk, tv, (__nv_bfloat16*)o, (int)H, (int)Nq, (int)Nk,
+  S3R_CUDA_CHECK(cudaLaunchKernelEx(&cfg, one_pass ? s3r_attention1_kernel : s3r_attention_kernel, tq, tk, tv, (__nv_bfloat16*)o, (int)H, (int)Nq, (int)Nk,
                                     (long long)o_strides[0], (long long)o_strides[1], (long long)o_strides[2],
                                     scale * 1.4426950408889634f, pdl));
   return S3R_OK;

@@ -23,6 +23,8 @@
 
 #include "s3r_common.cuh"
 
+int& s3r_attn_onepass();  // attention_tcgen05.cu
+
 #define GEMM_BM 128
 #define GEMM_BK 64
 #define GEMM_THREADS 256
@@ -1433,6 +1435,11 @@ extern "C" int s3r_set_tunable(int32_t key, int32_t value) {
   if (key == S3R_TUNE_GEMM_PAIR) {
     if (value < 0 || value > 5) return S3R_ERR_INVALID_ARG;
     g_gemm_pair = value;
+    return S3R_OK;
+  }
+  if (key == S3R_TUNE_ATTN_ONEPASS) {
+    if (value < 0 || value > 2) return S3R_ERR_INVALID_ARG;
+    s3r_attn_onepass() = value;
     return S3R_OK;
   }
   if (key == S3R_TUNE_GEMM_SHALLOW) {
