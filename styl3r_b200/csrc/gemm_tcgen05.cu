@@ -1070,7 +1070,11 @@ static int launch_gemm_persist(const CUtensorMap& a, const CUtensorMap& b, const
   const int mt_pairs = ((M + GEMM_BM - 1) / GEMM_BM + 1) / 2, nt = (N + BN - 1) / BN;
   const int total = mt_pairs * nt;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(2 * (unsigned)(total < pairs[dev] ? total : pairs[dev]), 1, 1);
+  // as many pairs as the tile list needs for its number of rounds and no more (117 tiles over 74 pairs take 2 rounds - so do
+  // 59 pairs, and the other 15 TPCs stay free for the kernels of concurrent stream branches)
+  const int rounds = (total + pairs[dev] - 1) / pairs[dev];
+  const int use_pairs = (total + rounds - 1) / rounds;
+  cfg.gridDim = dim3(2 * (unsigned)use_pairs, 1, 1);
   cfg.blockDim = dim3(GEMM_P_THREADS, 1, 1);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
@@ -1362,8 +1366,19 @@ extern "C" int s3r_gemm_bf16_majors(const void* A, const void* B, const void* bi
   if ((rc = b_mn_major ? make_map(&tb, B, K, N, ldb, 64) : make_map(&tb, B, N, K, ldb, 128)) != S3R_OK) return rc;
   RopeArgs rope{nullptr, nullptr, 0, 0};
   cudaStream_t st = (cudaStream_t)stream;
-  if (a_mn_major && b_mn_major)
+  if (a_mn_major && b_mn_major) {
+    // wgrad: a small output (dW of a 768..4096-wide layer: 36-256 tiles) under a long contraction (all tokens of the batch):
+    // cluster split-K spreads the token range of every tile over 2 / 4 SMs and sums the partial tiles through DSMEM
+    const long tiles = (long)((M + 127) / 128) * ((N + 127) / 128);
+    const int total_kb = (K + GEMM_BK - 1) / GEMM_BK;
+    if (g_gemm_ksplit != 1 && total_kb >= 16) {
+      if (tiles * 4 <= 300)
+        return launch_gemm<128, 3, false, 1, 1, 3, S3R_EPI_ALL, 4>(ta, tb, bias, aux, C, M, N, K, ldc, ldaux, flags, rope, 1, nullptr, nullptr, st);
+      if (tiles * 2 <= 400)
+        return launch_gemm<128, 3, false, 1, 1, 3, S3R_EPI_ALL, 2>(ta, tb, bias, aux, C, M, N, K, ldc, ldaux, flags, rope, 1, nullptr, nullptr, st);
+    }
     return launch_gemm<128, 3, false, 1, 1, 3>(ta, tb, bias, aux, C, M, N, K, ldc, ldaux, flags, rope, 1, nullptr, nullptr, st);
+  }
   if (a_mn_major)
     return launch_gemm<128, 3, false, 1, 1, 1>(ta, tb, bias, aux, C, M, N, K, ldc, ldaux, flags, rope, 1, nullptr, nullptr, st);
   return launch_gemm<128, 3, false, 1, 1, 2>(ta, tb, bias, aux, C, M, N, K, ldc, ldaux, flags, rope, 1, nullptr, nullptr, st);
