@@ -13,9 +13,9 @@ ROOT = Path(__file__).resolve().parents[1]
 sys.path.insert(0, str(ROOT))
 from styl3r_b200 import build as B  # noqa: E402
 
-MNEMONICS = ["UTCHMMA", "UTCQMMA", "UTCBAR", "UTMALDG", "UTMAPF", "UBLKCP", "LDTM", "STTM", "SYNCS", "UTCATOM", "ACQBULK",
+MNEMONICS = ["UTCHMMA.2CTA", "UTMALDG.2D.2CTA", "UTMALDG.4D.2CTA", "UTCBAR.2CTA", "UTCHMMA", "UTCQMMA", "UTCBAR", "UTMALDG", "UTMAPF", "UBLKCP", "LDTM", "STTM", "SYNCS", "UTCATOM", "ACQBULK",
              "MUFU.EX2", "FFMA", "HMMA", "LDS", "STS", "ATOMS", "RED", "VOTE", "SHFL"]
-PTX = ["tcgen05.mma", "tcgen05.ld", "tcgen05.alloc", "tcgen05.commit", "cp.async.bulk.tensor", "cp.async.bulk.shared",
+PTX = ["tcgen05.mma.cta_group::2", "cta_group::2.shared::cluster.global", "tcgen05.st", "tcgen05.mma", "tcgen05.ld", "tcgen05.alloc", "tcgen05.commit", "cp.async.bulk.tensor", "cp.async.bulk.shared",
        "mbarrier.try_wait", "mbarrier.arrive", "griddepcontrol", "ex2.approx"]
 
 
@@ -42,7 +42,8 @@ def main():
     demangled = subprocess.run(["c++filt"], input="\n".join(kernels), capture_output=True, text=True).stdout.splitlines()
     out = ["# SASS mnemonic counts per kernel of styl3r_b200/lib/libstyl3r_b200.so (cuobjdump -sass, sm_100a)",
            "# UTCHMMA = tcgen05.mma (kind::f16), LDTM = tcgen05.ld, UTMALDG = TMA tensor load, UBLKCP = cp.async.bulk,",
-           "# SYNCS = mbarrier ops, UTCBAR = tcgen05.commit; a kernel without them does not use that hardware", ""]
+           "# SYNCS = mbarrier ops, UTCBAR = tcgen05.commit; a kernel without them does not use that hardware;",
+           "# the .2CTA forms (counted separately AND inside their base mnemonic) are the cta_group::2 CTA-pair instructions", ""]
     for (name, c), dn in zip(kernels.items(), demangled):
         short = re.sub(r"\(.*", "", dn)
         hits = " ".join(f"{k}={v}" for k, v in c.items() if k != "_total" and v)
