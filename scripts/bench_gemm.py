@@ -25,8 +25,12 @@ for M, N, K in shapes:
     x = torch.randn(M, K, device="cuda").to(torch.bfloat16); w = torch.randn(N, K, device="cuda").to(torch.bfloat16)
     b = torch.randn(N, device="cuda").to(torch.bfloat16); r = torch.randn(M, N, device="cuda").to(torch.bfloat16)
     reps = 5 if M >= 8192 else 50
+    from styl3r_b200 import _lib
+    _lib.lib().s3r_set_tunable(13, 2)
+    s1 = gtime(lambda: linear(x, w, b), reps); s2 = gtime(lambda: linear(x, w, b, gelu=True), reps); s3 = gtime(lambda: linear(x, w, b, residual=r), reps)
+    _lib.lib().s3r_set_tunable(13, 0)
     o1 = gtime(lambda: linear(x, w, b), reps); t1 = gtime(lambda: torch.nn.functional.linear(x, w, b), reps)
     o2 = gtime(lambda: linear(x, w, b, gelu=True), reps); t2 = gtime(lambda: torch.nn.functional.gelu(torch.nn.functional.linear(x, w, b)), reps)
     o3 = gtime(lambda: linear(x, w, b, residual=r), reps); t3 = gtime(lambda: r + torch.nn.functional.linear(x, w, b), reps)
     fl = 2.0 * M * N * K
-    print(f"M={M:5d} N={N:5d} K={K:5d} | bias: ours {o1*1e3:7.1f} us ({fl/o1/1e9:5.0f} TF) torch {t1*1e3:7.1f} | +gelu: {o2*1e3:7.1f} vs {t2*1e3:7.1f} | +res: {o3*1e3:7.1f} vs {t3*1e3:7.1f}", flush=True)
+    print(f"M={M:5d} N={N:5d} K={K:5d} | bias: ours {o1*1e3:7.1f} us ({fl/o1/1e9:5.0f} TF) torch {t1*1e3:7.1f} | +gelu: {o2*1e3:7.1f} vs {t2*1e3:7.1f} | +res: {o3*1e3:7.1f} vs {t3*1e3:7.1f} | staged epilogue: {s1*1e3:6.1f}/{s2*1e3:6.1f}/{s3*1e3:6.1f}", flush=True)

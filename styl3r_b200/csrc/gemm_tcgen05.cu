@@ -262,8 +262,15 @@ struct ConvArgs {
 // narrow-N / long-K GEMMs of the batch-1 encoder (fc2, proj: 18-80 tiles for 148 SMs, every SM bound by its ~50 B/cycle
 // TMA ingress) this spreads the K stream over KS times as many SMs without the L2 workspace + ticket round trips of the
 // global split-K.
-template <int BN, int STAGES_, bool kConv, int CM = 1, int CN = 1, int MAJ = 0, int EPI = S3R_EPI_ALL, int KS = 1, int PAIR = 0>
-__global__ void __launch_bounds__(GEMM_THREADS, (GemmSmem<BN, STAGES_, PAIR>::STAGES * GemmSmem<BN, STAGES_, PAIR>::STAGE_BYTES <= 100 * 1024) ? 2 : 1)
+// DIRECT: register epilogue straight from TMEM for the latency-bound batch-1 shapes (one tile per CTA, grid <= ~1 wave):
+// warps 2-9 (the block has 320 threads) - two per TMEM lane quarter, column halves - fetch bias / residual / positions
+// while the main loop runs, then each thread walks its output row in 32-column blocks (tcgen05.ld -> bias / GELU /
+// residual / RoPE with the rotation pair in the same thread -> 64 contiguous bytes to global memory).  No staging tile, no
+// CTA barrier, no exposed global latency after the accumulator is complete: the staged two-phase epilogue costs ~1.5 us
+// of a 9 us launch at 514x3072x1024.
+#define GEMM_DIRECT_THREADS 320
+template <int BN, int STAGES_, bool kConv, int CM = 1, int CN = 1, int MAJ = 0, int EPI = S3R_EPI_ALL, int KS = 1, int PAIR = 0, int DIRECT = 0>
+__global__ void __launch_bounds__(DIRECT ? GEMM_DIRECT_THREADS : GEMM_THREADS, (GemmSmem<BN, STAGES_, PAIR>::STAGES * GemmSmem<BN, STAGES_, PAIR>::STAGE_BYTES <= 100 * 1024) ? 2 : 1)
 s3r_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const __nv_bfloat16* __restrict__ bias, const __nv_bfloat16* __restrict__ residual, void* __restrict__ Cout,
                      int M, int N, int K, int ldc, int ldr, int flags, RopeArgs rope, int splits, float* __restrict__ ws,
@@ -308,6 +315,7 @@ s3r_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   static_assert(!PAIR || (CM * CN == 1 && KS == 1 && MAJ == 0), "CTA pairs: K-major operands, no multicast / split-K");
   const uint32_t prank = PAIR ? g_cluster_ctarank() : 0u;  // rank inside the CTA pair (0 = leader: issues the MMAs)
   static_assert(KS == 1 || (CM * CN == 1 && BN <= 128 && !kConv), "cluster split-K: plain GEMM tiles, single epilogue pass");
+  static_assert(!DIRECT || (CM * CN == 1 && KS == 1 && !PAIR && MAJ == 0 && BN <= 128), "register epilogue: plain one-tile GEMM");
   uint32_t xr = 0, yr = 0;       // this CTA's position inside its cluster (x = M direction, fastest)
   uint16_t mask_a = 1, mask_b = 1, mask_rel = 1;
   if (CM * CN > 1) {
@@ -441,6 +449,135 @@ s3r_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   // phase 2 (all 256 threads; only the 128 epilogue threads when split-K is on): the tile is walked row-wise, 4
   //          consecutive columns per lane, so that every global access (partials, bias, residual, output) is a fully
   //          coalesced 256/512-byte row segment.
+  if constexpr (DIRECT != 0) {
+    if (warp >= 2) {
+      const int q = warp & 3, half = (warp - 2) >> 2;
+      constexpr int NBLK = BN / 64;  // 32-column blocks per warp
+      float* sb = reinterpret_cast<float*>(smem + GEMM_STAGES * S::STAGE_BYTES + 256) + (warp - 2) * (BN / 2);
+      const int row = m0 + q * 32 + lane;
+      const bool row_ok = row < M;
+      const bool has_bias = EF(S3R_EPI_BIAS), gelu = EF(S3R_EPI_GELU), has_res = EF(S3R_EPI_RESIDUAL), relu = EF(S3R_EPI_RELU),
+                 out_f32 = EF(S3R_EPI_OUT_F32);
+      const int cb0 = n0 + half * (BN / 2);
+      // everything that does not depend on the accumulator is requested now, while the main loop runs
+      int py = 0, px = 0;
+      if (EF(S3R_EPI_ROPE) && row_ok) {
+        const long long y = rope.pos[(size_t)row * 2], x = rope.pos[(size_t)row * 2 + 1];
+        py = (int)(y < 0 ? 0 : (y > rope.max_pos ? rope.max_pos : y));
+        px = (int)(x < 0 ? 0 : (x > rope.max_pos ? rope.max_pos : x));
+      }
+      if (has_bias) {
+#pragma unroll
+        for (int c = lane; c < BN / 2; c += 32) sb[c] = (cb0 + c < N) ? __bfloat162float(bias[cb0 + c]) : 0.0f;
+        __syncwarp();
+      }
+      const bool vec_ok = (N % 8 == 0) && !(((uintptr_t)residual | (uintptr_t)Cout) & 15) && (ldr % 8 == 0);
+      uint4 rq[NBLK][4];
+      if (has_res) {
+#pragma unroll
+        for (int blk = 0; blk < NBLK; blk++)
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            rq[blk][j] = make_uint4(0u, 0u, 0u, 0u);
+            const int c = cb0 + blk * 32 + 8 * j;
+            if (row_ok && vec_ok && c + 8 <= N) rq[blk][j] = *reinterpret_cast<const uint4*>(residual + (size_t)row * ldr + c);
+          }
+      }
+      g_mbar_wait(tmem_full, 0);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+      for (int blk = 0; blk < NBLK; blk++) {
+        const int c0 = half * (BN / 2) + blk * 32;
+        const int col = n0 + c0;
+        uint32_t v[32];
+        g_tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+        float f[32];
+        if (has_bias) {
+#pragma unroll
+          for (int j = 0; j < 8; j++) {
+            const float4 b4 = *reinterpret_cast<const float4*>(sb + blk * 32 + 4 * j);
+            f[4 * j] = __uint_as_float(v[4 * j]) + b4.x;
+            f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b4.y;
+            f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b4.z;
+            f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b4.w;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; j++) f[j] = __uint_as_float(v[j]);
+        }
+        if (EF(S3R_EPI_ROPE) && col < rope.cols) {
+          const float2* tb = rope.table + (((col >> 5) & 1) ? px : py) * 16;
+#pragma unroll
+          for (int d = 0; d < 16; d++) {
+            const float2 cs = __ldg(tb + d);
+            const float u = f[d], w2 = f[d + 16];
+            f[d] = u * cs.x - w2 * cs.y;
+            f[d + 16] = w2 * cs.x + u * cs.y;
+          }
+        }
+        if (gelu) {
+#pragma unroll
+          for (int j = 0; j < 32; j++) f[j] = 0.5f * f[j] * (1.0f + g_fast_erf(f[j] * 0.70710678118654752f));
+        }
+        if (relu) {
+#pragma unroll
+          for (int j = 0; j < 32; j++) f[j] = fmaxf(f[j], 0.0f);
+        }
+        if (has_res) {
+          if (vec_ok) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+              const uint32_t rw[4] = {rq[blk][j].x, rq[blk][j].y, rq[blk][j].z, rq[blk][j].w};
+#pragma unroll
+              for (int k = 0; k < 4; k++) {
+                const float2 rr = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rw[k]));
+                f[8 * j + 2 * k] += rr.x;
+                f[8 * j + 2 * k + 1] += rr.y;
+              }
+            }
+          } else if (row_ok) {
+#pragma unroll
+            for (int j = 0; j < 32; j++)
+              if (col + j < N) f[j] += __bfloat162float(residual[(size_t)row * ldr + col + j]);
+          }
+        }
+        if (row_ok) {
+          if (out_f32) {
+            float* op = (float*)Cout + (size_t)row * ldc + col;
+            if (vec_ok) {
+#pragma unroll
+              for (int j = 0; j < 8; j++)
+                if (col + 4 * j + 4 <= N)
+                  *reinterpret_cast<float4*>(op + 4 * j) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; j++)
+                if (col + j < N) op[j] = f[j];
+            }
+          } else {
+            __nv_bfloat16* op = (__nv_bfloat16*)Cout + (size_t)row * ldc + col;
+            if (vec_ok) {
+#pragma unroll
+              for (int j = 0; j < 4; j++) {
+                if (col + 8 * j + 8 <= N) {
+                  uint4 u;
+                  *reinterpret_cast<__nv_bfloat162*>(&u.x) = __floats2bfloat162_rn(f[8 * j], f[8 * j + 1]);
+                  *reinterpret_cast<__nv_bfloat162*>(&u.y) = __floats2bfloat162_rn(f[8 * j + 2], f[8 * j + 3]);
+                  *reinterpret_cast<__nv_bfloat162*>(&u.z) = __floats2bfloat162_rn(f[8 * j + 4], f[8 * j + 5]);
+                  *reinterpret_cast<__nv_bfloat162*>(&u.w) = __floats2bfloat162_rn(f[8 * j + 6], f[8 * j + 7]);
+                  *reinterpret_cast<uint4*>(op + 8 * j) = u;
+                }
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; j++)
+                if (col + j < N) op[j] = __float2bfloat16_rn(f[j]);
+            }
+          }
+        }
+      }
+    }
+  } else {
   const bool is_p1 = warp >= 2 && warp < 6;
   const int NT2 = (splits == 1 || KS > 1) ? GEMM_THREADS : 128;   // threads of phase 2
   // phase-2 thread index: epilogue warps 0..127, then the TMA / MMA warps, then warps 6-7
@@ -675,6 +812,7 @@ s3r_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     if (BN > CG) asm volatile("bar.sync 1, %0;" ::"r"(NT2) : "memory");  // staging tile is reused by the next column group
     }  // cg
   }
+  }  // staged epilogue
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncwarp();
   if (kCluster || KS > 1) g_cluster_sync();  // no CTA may retire while a peer can still multicast into it / read its tile
@@ -974,6 +1112,7 @@ int s3r_pdl_enabled() { return g_pdl; }
 static int g_gemm_ksplit = 0;    // S3R_TUNE_GEMM_KSPLIT: 0 = auto, 1 = never, 2 / 4 = force that cluster split-K factor on 64-wide tiles
 static int g_gemm_shallow = 0;   // S3R_TUNE_GEMM_SHALLOW: small grids use the 4-stage (96 KB, 2 CTAs/SM) ring too
 static int g_conv_cluster = 0;   // S3R_TUNE_CONV_CLUSTER: pairs of pixel tiles multicast the weight tile
+static int g_gemm_direct = 0;    // S3R_TUNE_GEMM_DIRECT: register epilogue of the one-tile kernel: 0 = auto (grids <= 1.5 waves), 1 = whenever possible, 2 = never
 static int g_gemm_pair = 0;      // S3R_TUNE_GEMM_PAIR: CTA pairs (cta_group::2, M = 256 per MMA): 0 = auto, 1 = 256x128 pair tiles whenever possible, 2 = never, 3 = 256x256 pair tiles whenever possible, 4 / 5 = PERSISTENT 256x128 / 256x256 pair tiles whenever possible
 
 static PFN_encodeTiled get_encode() {
@@ -1003,13 +1142,13 @@ static int make_map(CUtensorMap* map, const void* ptr, int rows, int cols, int l
   return r == CUDA_SUCCESS ? S3R_OK : S3R_ERR_CUDA;
 }
 
-template <int BN, int STAGES_, bool kConv = false, int CM = 1, int CN = 1, int MAJ = 0, int EPI = S3R_EPI_ALL, int KS = 1, int PAIR = 0>
+template <int BN, int STAGES_, bool kConv = false, int CM = 1, int CN = 1, int MAJ = 0, int EPI = S3R_EPI_ALL, int KS = 1, int PAIR = 0, int DIRECT = 0>
 static int launch_gemm(const CUtensorMap& a, const CUtensorMap& b, const void* bias, const void* residual, void* C, int M,
                        int N, int K, int ldc, int ldr, int flags, const RopeArgs& rope, int splits, float* ws, unsigned* counters,
                        cudaStream_t st, const ConvArgs& conv = ConvArgs{}, int batch = 0, long long batch_stride_c = 0) {
   static size_t configured[64] = {};  // per device: cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute
-  const int smem = GemmSmem<BN, STAGES_, PAIR>::TOTAL;
-  auto kern = s3r_gemm_bf16_kernel<BN, STAGES_, kConv, CM, CN, MAJ, EPI, KS, PAIR>;
+  const int smem = GemmSmem<BN, STAGES_, PAIR>::TOTAL + (DIRECT ? 8 * (BN / 2) * 4 : 0);  // + per-warp bias rows
+  auto kern = s3r_gemm_bf16_kernel<BN, STAGES_, kConv, CM, CN, MAJ, EPI, KS, PAIR, DIRECT>;
   constexpr int CMX = PAIR ? 2 : CM;  // cluster extent along M
   if (KS > 1) splits = KS, ws = nullptr, counters = nullptr;
   {
@@ -1021,7 +1160,7 @@ static int launch_gemm(const CUtensorMap& a, const CUtensorMap& b, const void* b
   const unsigned gx = ((M + GEMM_BM - 1) / GEMM_BM + CMX - 1) / CMX * CMX, gy = ((N + BN - 1) / BN + CN - 1) / CN * CN;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(gx, gy, batch > 0 ? batch : splits);
-  cfg.blockDim = dim3(GEMM_THREADS, 1, 1);
+  cfg.blockDim = dim3(DIRECT ? GEMM_DIRECT_THREADS : GEMM_THREADS, 1, 1);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[2];
@@ -1266,6 +1405,19 @@ extern "C" int s3r_gemm_bf16_rope(const void* A, const void* W, const void* bias
   // the inference feature sets of the ViT trunks get their own instances (no cluster, no split-K)
   constexpr int E_BASE = S3R_EPI_BIAS | S3R_EPI_OUT_F32 | S3R_EPI_PDL;
   const int extra = flags & ~E_BASE;
+#define S3R_GEMM_EPI_DIRECT(BN_, ST_)                                                                                   \
+  do {                                                                                                                  \
+    if (cm == 1 && cn == 1 && splits == 1 && g_gemm_direct != 2) {                                                      \
+      if (extra == 0)                                                                                                   \
+        return launch_gemm<BN_, ST_, false, 1, 1, 0, E_BASE, 1, 0, 1>(ta, tb, bias, residual, C, M, N, K, ldc, ldr, flags, rope, 1, ws, counters, st); \
+      if (extra == S3R_EPI_GELU)                                                                                        \
+        return launch_gemm<BN_, ST_, false, 1, 1, 0, E_BASE | S3R_EPI_GELU, 1, 0, 1>(ta, tb, bias, residual, C, M, N, K, ldc, ldr, flags, rope, 1, ws, counters, st); \
+      if (extra == S3R_EPI_RESIDUAL)                                                                                    \
+        return launch_gemm<BN_, ST_, false, 1, 1, 0, E_BASE | S3R_EPI_RESIDUAL, 1, 0, 1>(ta, tb, bias, residual, C, M, N, K, ldc, ldr, flags, rope, 1, ws, counters, st); \
+      if (extra == S3R_EPI_ROPE)                                                                                        \
+        return launch_gemm<BN_, ST_, false, 1, 1, 0, E_BASE | S3R_EPI_ROPE, 1, 0, 1>(ta, tb, bias, residual, C, M, N, K, ldc, ldr, flags, rope, 1, ws, counters, st); \
+    }                                                                                                                   \
+  } while (0)
 #define S3R_GEMM_EPI(BN_, ST_)                                                                                          \
   do {                                                                                                                  \
     if (cm == 1 && cn == 1 && splits == 1) {                                                                            \
@@ -1308,11 +1460,16 @@ extern "C" int s3r_gemm_bf16_rope(const void* A, const void* W, const void* bias
 #undef S3R_GEMM_KS
     }
   }
+  // register epilogue for grids of at most ~1.5 waves (the batch-1 shapes): S3R_TUNE_GEMM_DIRECT 0 = auto, 1 = whenever
+  // possible, 2 = never
+  const bool direct_ok = !t_pre_out && (g_gemm_direct == 1 || (g_gemm_direct == 0 && (BN == 64 ? tiles64 : tiles128) <= 222));
   if (BN == 64) {
     if (tiles64 * splits < 148 && !g_gemm_shallow) {
+      if (direct_ok) S3R_GEMM_EPI_DIRECT(64, 8);
       S3R_GEMM_EPI(64, 8);
       S3R_GEMM_CLUSTERS(64, 8);
     }
+    if (direct_ok) S3R_GEMM_EPI_DIRECT(64, 4);
     S3R_GEMM_EPI(64, 4);
     S3R_GEMM_CLUSTERS(64, 4);
   }
@@ -1322,8 +1479,12 @@ extern "C" int s3r_gemm_bf16_rope(const void* A, const void* W, const void* bias
     S3R_GEMM_EPI(256, 2);
     S3R_GEMM_CLUSTERS(256, 2);
   }
+  // (measured: with 128-wide tiles - two 32-column blocks per warp - the register epilogue loses to the staged one:
+  // 514x3072x1024 9.8 -> 11.5 us; it is used for the 64-wide tiles only unless forced)
+  if (g_gemm_direct == 1 && direct_ok && BN == 128) S3R_GEMM_EPI_DIRECT(128, 3);
   S3R_GEMM_EPI(128, 3);
   S3R_GEMM_CLUSTERS(128, 3);
+#undef S3R_GEMM_EPI_DIRECT
 #undef S3R_GEMM_EPI
 #undef S3R_GEMM_CLUSTERS
 #undef S3R_GEMM_GO
@@ -1455,6 +1616,11 @@ extern "C" int s3r_set_tunable(int32_t key, int32_t value) {
   if (key == S3R_TUNE_ATTN_ONEPASS) {
     if (value < 0 || value > 2) return S3R_ERR_INVALID_ARG;
     s3r_attn_onepass() = value;
+    return S3R_OK;
+  }
+  if (key == S3R_TUNE_GEMM_DIRECT) {
+    if (value < 0 || value > 2) return S3R_ERR_INVALID_ARG;
+    g_gemm_direct = value;
     return S3R_OK;
   }
   if (key == S3R_TUNE_GEMM_SHALLOW) {

@@ -21,17 +21,25 @@ def ref(x, w, b, r, gelu):
 @pytest.mark.parametrize("M,N,K", [(514, 3072, 1024), (514, 1024, 4096), (128, 128, 64), (257, 768, 768), (1, 64, 72),
                                    (4112, 4096, 1024), (771, 2304, 768), (300, 200, 136)])
 @pytest.mark.parametrize("epi", ["none", "bias", "bias_gelu", "bias_res", "bias_gelu_res_f32"])
-def test_gemm_matches_fp32_reference(M, N, K, epi):
+@pytest.mark.parametrize("direct", [0, 1, 2])
+def test_gemm_matches_fp32_reference(M, N, K, epi, direct):
+    """direct = 1 / 2 force / forbid the register epilogue of the one-tile kernel (S3R_TUNE_GEMM_DIRECT), 0 = dispatch by
+    grid size."""
     import torch
+    from styl3r_b200 import _lib
     from styl3r_b200.gemm import linear
+    _lib.check(_lib.lib().s3r_set_tunable(13, direct))
     torch.manual_seed(M * 7 + N * 3 + K)
     x = (torch.randn(M, K, device="cuda") * 0.5).to(torch.bfloat16)
     w = (torch.randn(N, K, device="cuda") * K ** -0.5).to(torch.bfloat16)
     b = (torch.randn(N, device="cuda") * 0.1).to(torch.bfloat16) if "bias" in epi else None
     r = torch.randn(M, N, device="cuda").to(torch.bfloat16) if "res" in epi else None
     out_dtype = torch.float32 if "f32" in epi else torch.bfloat16
-    y = linear(x, w, b, r, gelu="gelu" in epi, out_dtype=out_dtype)
-    torch.cuda.synchronize()
+    try:
+        y = linear(x, w, b, r, gelu="gelu" in epi, out_dtype=out_dtype)
+        torch.cuda.synchronize()
+    finally:
+        _lib.lib().s3r_set_tunable(13, 0)
     expect = ref(x, w, b, r, "gelu" in epi)
     err = (y.float() - expect).abs().max().item()
     tol = (2e-3 if out_dtype == torch.float32 else 1e-2) * expect.abs().max().item()
@@ -50,7 +58,7 @@ def test_gemm_batched_leading_dims_and_strided_rows():
     assert (y.float() - expect).abs().max() <= 1e-2 * expect.abs().max()
 
 
-@pytest.mark.parametrize("M,H,pair", [(514, 16, 0), (257, 12, 0), (771, 12, 0), (514, 16, 5), (771, 12, 5), (2570, 16, 0)])
+@pytest.mark.parametrize("M,H,pair", [(514, 16, 0), (257, 12, 0), (771, 12, 0), (514, 16, 5), (771, 12, 5), (2570, 16, 0), (514, 16, -1), (257, 12, -2)])
 def test_gemm_with_fused_rope_epilogue_matches_gemm_then_rope_oracle(M, H, pair):
     """qkv projection with RoPE-2D on the q and k thirds fused in the epilogue == fp32 GEMM followed by the RoPE
     oracle (oracle/rope_oracle.c restating curope.cpp:11-47).  pair = 5: the persistent CTA-pair kernel's register
@@ -60,7 +68,10 @@ def test_gemm_with_fused_rope_epilogue_matches_gemm_then_rope_oracle(M, H, pair)
     from oracle import raster_oracle as ro
     from styl3r_b200 import _lib
     from styl3r_b200.gemm import linear
-    _lib.check(_lib.lib().s3r_set_tunable(11, pair))
+    if pair < 0:   # -1 / -2: one-tile kernel with the register epilogue forced / forbidden
+        _lib.check(_lib.lib().s3r_set_tunable(13, -pair))
+    else:
+        _lib.check(_lib.lib().s3r_set_tunable(11, pair))
     torch.manual_seed(M)
     C_ = H * 64
     x = (torch.randn(M, C_, device="cuda") * 0.5).to(torch.bfloat16)
@@ -72,6 +83,7 @@ def test_gemm_with_fused_rope_epilogue_matches_gemm_then_rope_oracle(M, H, pair)
         torch.cuda.synchronize()
     finally:
         _lib.lib().s3r_set_tunable(11, 0)
+        _lib.lib().s3r_set_tunable(13, 0)
     ref = (x.float() @ w.float().t() + b.float()).cpu().numpy().reshape(1, M, 3, H, 64)
     expect = ref.copy()
     for part in (0, 1):  # q and k thirds
