@@ -314,7 +314,7 @@ s3r_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   constexpr bool kCluster = CM * CN > 1 || PAIR;
   static_assert(!PAIR || (CM * CN == 1 && KS == 1 && MAJ == 0), "CTA pairs: K-major operands, no multicast / split-K");
   const uint32_t prank = PAIR ? g_cluster_ctarank() : 0u;  // rank inside the CTA pair (0 = leader: issues the MMAs)
-  static_assert(KS == 1 || (CM * CN == 1 && BN <= 128 && !kConv), "cluster split-K: plain GEMM tiles, single epilogue pass");
+  static_assert(KS == 1 || (CM * CN == 1 && BN <= 128), "cluster split-K: single epilogue pass");
   static_assert(!DIRECT || (CM * CN == 1 && KS == 1 && !PAIR && MAJ == 0 && BN <= 128), "register epilogue: plain one-tile GEMM");
   uint32_t xr = 0, yr = 0;       // this CTA's position inside its cluster (x = M direction, fastest)
   uint16_t mask_a = 1, mask_b = 1, mask_rel = 1;
@@ -1742,6 +1742,15 @@ extern "C" int s3r_conv2d_bf16(const void* x, const void* w, const void* bias, c
     if (BN == 256)
       return launch_gemm<256, 2, true, 2, 1>(ta, tb, bias, residual, y, (int)M, cout, K, cout, cout, flags, rope, 1, nullptr, nullptr, st, conv);
     return launch_gemm<128, 3, true, 2, 1>(ta, tb, bias, residual, y, (int)M, cout, K, cout, cout, flags, rope, 1, nullptr, nullptr, st, conv);
+  }
+  // small pyramid levels (8^2 .. 32^2 at batch 1-2: 2-32 CTAs under a 36-k-block loop): cluster split-K over the taps
+  if (g_gemm_ksplit != 1 && BN == 128 && cm == 1) {
+    const long ctas = ((M + GEMM_BM - 1) / GEMM_BM) * ((cout + 127) / 128);
+    const int total_kb = K / GEMM_BK;
+    if (total_kb >= 16 && ctas * 4 <= 160)
+      return launch_gemm<128, 3, true, 1, 1, 0, S3R_EPI_ALL, 4>(ta, tb, bias, residual, y, (int)M, cout, K, cout, cout, flags, rope, 1, nullptr, nullptr, st, conv);
+    if (total_kb >= 16 && ctas * 2 <= 200)
+      return launch_gemm<128, 3, true, 1, 1, 0, S3R_EPI_ALL, 2>(ta, tb, bias, residual, y, (int)M, cout, K, cout, cout, flags, rope, 1, nullptr, nullptr, st, conv);
   }
   if (BN == 64) return launch_gemm<64, 4, true>(ta, tb, bias, residual, y, (int)M, cout, K, cout, cout, flags, rope, 1, nullptr, nullptr, st, conv);
   if (BN == 256 && variant == 1)

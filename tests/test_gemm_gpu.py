@@ -207,7 +207,8 @@ def test_conv_cluster_multicast_matches_plain():
             torch.cuda.synchronize()
         finally:
             L.s3r_set_tunable(4, 0)
-        assert torch.equal(y, base)
+        # (the plain call may take the cluster split-K path on the small shape: another summation order)
+        assert torch.equal(y, base) or (y.float() - base.float()).abs().max().item() <= 2 ** -6
 
 
 @pytest.mark.parametrize("M,C,strided", [(514, 1024, False), (257, 768, False), (1, 256, False), (1028, 768, True), (33, 2048, False)])
