@@ -28,7 +28,7 @@ for M, N, K in [(257, 768, 3072), (257, 768, 768), (514, 1024, 4096), (514, 1024
     L = _lib.lib()
     res = {}
     outs = {}
-    for ks in (1, 0, 2, 4):  # S3R_TUNE_GEMM_KSPLIT: never / auto / forced
+    for ks in (1, 0, 2, 4, 8, 9):  # S3R_TUNE_GEMM_KSPLIT: never / auto / forced 64-wide KS / 128-wide KS4 forced / forbidden
         L.s3r_set_tunable(10, ks)
         res[ks] = gtime(lambda: linear(x, w, b, residual=r))
         outs[ks] = linear(x, w, b, residual=r).float()
@@ -36,4 +36,4 @@ for M, N, K in [(257, 768, 3072), (257, 768, 768), (514, 1024, 4096), (514, 1024
     t = gtime(lambda: r + torch.nn.functional.linear(x, w, b))
     ref = r.float() + x.float() @ w.float().t() + b.float()
     err = {k: ((v - ref).abs().max() / ref.abs().max()).item() for k, v in outs.items()}
-    print(f"M={M:5d} N={N:5d} K={K:5d} +res: never {res[1]*1e3:6.1f} | auto {res[0]*1e3:6.1f} | KS2 {res[2]*1e3:6.1f} | KS4 {res[4]*1e3:6.1f} | torch {t*1e3:6.1f} us | rel err " + " ".join(f"{k}:{e:.4f}" for k, e in err.items()), flush=True)
+    print(f"M={M:5d} N={N:5d} K={K:5d} +res: never {res[1]*1e3:6.1f} | auto {res[0]*1e3:6.1f} | KS2 {res[2]*1e3:6.1f} | KS4 {res[4]*1e3:6.1f} | 128-wide KS4 {res[8]*1e3:6.1f} | auto w/o it {res[9]*1e3:6.1f} | torch {t*1e3:6.1f} us | rel err " + " ".join(f"{k}:{e:.4f}" for k, e in err.items()), flush=True)

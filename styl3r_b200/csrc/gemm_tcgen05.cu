@@ -1444,11 +1444,21 @@ extern "C" int s3r_gemm_bf16_rope(const void* A, const void* W, const void* bias
     // cluster split-K for the narrow-N / long-K GEMMs of the batch-1 encoder (fc2, proj): KS CTAs per tile
     const int total_kb = (K + GEMM_BK - 1) / GEMM_BK;
     int ks = 1;
-    if (g_gemm_ksplit > 1) ks = g_gemm_ksplit;
+    if (g_gemm_ksplit == 2 || g_gemm_ksplit == 4) ks = g_gemm_ksplit;
     // measured on B200 (scripts/bench_splitk.py, +residual epilogue): 257x768x3072 18.2 -> 11.9 us (KS 4), 257x1024x4096
     // 22.9 -> 13.2 (KS 4), 514x1024x4096 23.9 -> 16.5 (KS 2), 1028x768x3072 19.4 -> 14.5 (KS 2); neutral below K = 1536
     else if (tiles64 * 4 <= 200 && total_kb >= 32) ks = 4;
     else if (tiles64 * 2 <= 300 && total_kb >= 24) ks = 2;
+    // 128-wide tiles under a 4-way split move a third less through L2 than 64-wide ones at the same CTA count
+    // (514x1024x4096: 40 tiles x 4 = 160 CTAs, 82 MB instead of 123 MB) - measured SLOWER (19.7 vs 16.2 us; 257x768x3072
+    // 14.4 vs 11.4): the DSMEM reduction of four 128-wide partial tiles costs more than the traffic saves.  Kept behind
+    // S3R_TUNE_GEMM_KSPLIT = 8 for A/B runs only.
+    if (g_gemm_ksplit == 8 && N % 128 == 0) {
+      if ((rc = make_map(&tb, W, N, K, ldw, 128)) != S3R_OK) return rc;
+      if (extra == S3R_EPI_RESIDUAL || extra == 0)
+        return launch_gemm<128, 3, false, 1, 1, 0, E_BASE | S3R_EPI_RESIDUAL, 4>(ta, tb, bias, residual, C, M, N, K, ldc, ldr, flags, rope, 1, nullptr, nullptr, st);
+      return launch_gemm<128, 3, false, 1, 1, 0, S3R_EPI_ALL, 4>(ta, tb, bias, residual, C, M, N, K, ldc, ldr, flags, rope, 1, nullptr, nullptr, st);
+    }
     if (ks == 4 || ks == 2) {
       const bool res_only = extra == S3R_EPI_RESIDUAL || extra == 0;
 #define S3R_GEMM_KS(KS_, EPI_) \
@@ -1604,7 +1614,7 @@ extern "C" int s3r_set_tunable(int32_t key, int32_t value) {
     return S3R_OK;
   }
   if (key == S3R_TUNE_GEMM_KSPLIT) {
-    if (value != 0 && value != 1 && value != 2 && value != 4) return S3R_ERR_INVALID_ARG;
+    if (value != 0 && value != 1 && value != 2 && value != 4 && value != 8 && value != 9) return S3R_ERR_INVALID_ARG;
     g_gemm_ksplit = value;
     return S3R_OK;
   }
