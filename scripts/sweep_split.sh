@@ -7,6 +7,6 @@ for cfg in "-DBLEND_SPLIT=1 -DBLEND_MINB=3" "-DBLEND_SPLIT=2 -DBLEND_MINB=6" "-D
   timeout 300 python -m pytest tests/test_raster_forward_gpu.py -m gpu -q -x 2>&1 | tail -1
   for st in 1 8; do
     python bench.py --steps 300 --warmup 10 --no-cpu --no-standin --no-encoder --streams $st > gpurun_out/sweep_tmp.json 2> gpurun_out/sweep_err.log || { echo "bench failed: $cfg $st"; tail -3 gpurun_out/sweep_err.log; continue; }
-    echo -n "$cfg streams=$st: "; python scripts/pj.py gpurun_out/sweep_tmp.json
+    echo -n "$cfg streams=$st: "; python -c "import json,sys; d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1]); print(round(d[\"value\"]), d[\"stage_ms\"])" gpurun_out/sweep_tmp.json
   done
 done
