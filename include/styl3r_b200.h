@@ -284,6 +284,17 @@ int s3r_set_tunable(int32_t key, int32_t value);
 int s3r_upsample2x_nhwc_bf16(const void* x, const void* add, void* y, int32_t n, int32_t h, int32_t w, int32_t c,
                              void* stream);
 
+/* Patch matrix of the 7x7 / pad 3 image-skip convolution of the Gaussian-parameter head (dpt_gs_head.py:113-118,
+ * `input_merger`): img [B,3,H,W] bf16 planar -> cols [B*H*W, 152] bf16, column k < 147 = (ci, kh, kw) in F.unfold order,
+ * columns 147..151 zero. */
+int s3r_im2col7x7_bf16(const void* img, void* cols, int32_t B, int32_t H, int32_t W, void* stream);
+
+/* Cross-view context of the second decoder (backbone_croco_multiview.py:170-178): x0 [b,l,c] (view 0), x1 [b,v-1,l,c]
+ * (views 1..v-1) -> ctx [b, v-1, (v-1)*l, c]: for query view i >= 1 the tokens of all other views in view order.
+ * bf16, c % 8 == 0, v >= 2. */
+int s3r_gather_other_views_bf16(const void* x0, const void* x1, void* ctx, int32_t b, int32_t v, int32_t l, int32_t c,
+                                void* stream);
+
 /* ------------------------------------------------------------------------
  * LayerNorm over the last dimension, bf16 in / out, fp32 statistics - the
  * nn.LayerNorm(dim, eps=1e-6) of the ViT blocks (croco/blocks.py:140-147,

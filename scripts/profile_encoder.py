@@ -20,8 +20,14 @@ def step():
         return enc(context, style)
 for _ in range(2): step()
 torch.cuda.synchronize()
-with profile(activities=[ProfilerActivity.CUDA]) as prof:
+SHAPES = len(sys.argv) > 4
+with profile(activities=[ProfilerActivity.CUDA] + ([ProfilerActivity.CPU] if SHAPES else []), record_shapes=SHAPES) as prof:
     step(); torch.cuda.synchronize()
+if SHAPES:  # which ATen ops (with input shapes) own the glue kernels
+    evs = [e for e in prof.key_averages(group_by_input_shape=True) if e.key.startswith("aten::") and e.device_time_total > 0]
+    for e in sorted(evs, key=lambda e: -e.device_time_total)[:40]:
+        print(f"{e.device_time_total/1000:8.3f} ms n={e.count:4d} {e.key[:32]:32s} {str(e.input_shapes)[:140]}")
+    sys.exit(0)
 ev = prof.key_averages()
 rows = sorted(ev, key=lambda e: -e.device_time_total)[:32]
 tot = sum(e.device_time_total for e in ev)

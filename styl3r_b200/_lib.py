@@ -102,6 +102,8 @@ def lib():
     L.s3r_layernorm_f32_bf16.argtypes = [C.c_void_p] * 4 + [C.c_int32, C.c_int32, C.c_int64, C.c_float, C.c_void_p]
     L.s3r_layernorm_bwd_bf16.argtypes = [C.c_void_p] * 6 + [C.c_int32, C.c_int32, C.c_int64, C.c_float, C.c_void_p]
     L.s3r_set_tunable.argtypes = [C.c_int32, C.c_int32]
+    L.s3r_im2col7x7_bf16.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
+    L.s3r_gather_other_views_bf16.argtypes = [C.c_void_p] * 3 + [C.c_int32] * 4 + [C.c_void_p]
     L.s3r_rope_table.argtypes = [C.c_void_p, C.c_int32, C.c_float, C.c_void_p]
     L.s3r_attention_bf16.argtypes = [C.c_void_p] * 4 + [C.c_int32] * 5 + [C.POINTER(C.c_int64)] * 4 + [C.c_float, C.c_void_p]
     L.s3r_se3_update_w2c.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
@@ -122,4 +124,5 @@ EXPORTED_SYMBOLS = (
     "s3r_raster_read_status", "s3r_raster_backward_scratch_bytes", "s3r_raster_backward", "s3r_rope2d",
     "s3r_se3_update_w2c", "s3r_camera_setup", "s3r_gaussian_adapter", "s3r_gemm_bf16", "s3r_gemm_bf16_rope", "s3r_gemm_bf16_majors", "s3r_gemm_bf16_batched", "s3r_softmax_rows_bf16", "s3r_attention_ds_bf16", "s3r_rope_table", "s3r_attention_bf16",
     "s3r_conv2d_bf16", "s3r_upsample2x_nhwc_bf16", "s3r_gaussian_adapter_nhwc", "s3r_set_tunable", "s3r_ply_pack", "s3r_rescale_crop", "s3r_layernorm_bf16", "s3r_layernorm_f32_bf16", "s3r_layernorm_bwd_bf16",
+    "s3r_im2col7x7_bf16", "s3r_gather_other_views_bf16",
 )

@@ -216,9 +216,17 @@ def dpt_forward_nhwc(m: "DPTAdapter", tokens: List[Tensor], image_size, img: Ten
     else:
         add = None
         if m.kind == "gs_params":
+            # patch matrix [B*H*W, 152] (columns (ci, kh, kw) like F.unfold, zero-padded to a multiple of 8) in one pass -
+            # F.unfold + transpose copy + F.pad were three passes over it (1.4 ms for the 12 images of cfg3)
+            import ctypes as C
+            from .. import _lib
             B = img.shape[0]
-            cols = F.unfold(img.to(torch.bfloat16), 7, padding=3).transpose(1, 2)   # [B, H*W, 147], columns (ci, kh, kw)
-            add = linear(F.pad(cols, (0, 5)).reshape(B * H * W, 152), prep.mg_w, prep.mg_b, relu=True).view(B, H, W, -1)
+            imb = img.to(torch.bfloat16).contiguous()
+            cols = torch.empty(B * H * W, 152, dtype=torch.bfloat16, device=img.device)
+            _lib.check(_lib.lib().s3r_im2col7x7_bf16(C.c_void_p(imb.data_ptr()), C.c_void_p(cols.data_ptr()), B, H, W,
+                                                      C.c_void_p(torch.cuda.current_stream(img.device).cuda_stream)),
+                       "s3r_im2col7x7_bf16")
+            add = linear(cols, prep.mg_w, prep.mg_b, relu=True).view(B, H, W, -1)
         p = conv2d_nhwc(upsample2x_nhwc(p, add), prep.h0_w, (3, 3), relu=True)
     return linear(p.reshape(-1, p.shape[-1]), prep.last_w, prep.last_b, out_dtype=torch.float32)   # [B*H*W, ld] fp32
 

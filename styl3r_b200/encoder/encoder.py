@@ -137,14 +137,44 @@ class AsymmetricCroCoMulti(CroCoTrunk):
         feat, pos = self.encode(img.reshape(b * v, *img.shape[2:]), tok)
         return feat.reshape(b, v, *feat.shape[1:]), pos.reshape(b, v, *pos.shape[1:])
 
-    def decode_views(self, feat: Tensor, pos: Tensor, parallel: bool = False):
+    def decode_views(self, feat: Tensor, pos: Tensor, parallel: bool = False, hooked_only: bool = False):
         """The two cross-view decoders; `parallel`: view 0 (`dec_blocks`) and views >= 1 (`dec_blocks2`) of a layer
-        are independent given the previous layer's output and run as concurrent branches (streams.fork_join)."""
+        are independent given the previous layer's output and run as concurrent branches (streams.fork_join).
+        `hooked_only` (bf16 inference layout): only the layers the DPT heads hook are assembled into [b, v, l, c]
+        tensors (the other list entries are None); the two branches keep their own contiguous tensors from layer to
+        layer and the context of views >= 1 is gathered by one kernel (`s3r_gather_other_views_bf16`) instead of
+        cat + index + two reshape copies per layer."""
         b, v = feat.shape[:2]
         outs = [feat]
         cur = _lin(self.decoder_embed, feat, stream=True)
         pos_ctx = self._others(pos)
         blocks2 = self.dec_blocks2 if self.asymmetric else self.dec_blocks
+        if (hooked_only and v >= 2 and cur.is_cuda and cur.dtype == torch.bfloat16 and not torch.is_grad_enabled()
+                and cur.shape[-1] % 8 == 0):
+            import ctypes as C
+            l, c = cur.shape[2:]
+            L = _lib.lib()
+            cur0, cur1 = cur[:, 0].contiguous(), cur[:, 1:].contiguous()           # [b, l, c], [b, v-1, l, c]
+            pos0, pctx0 = pos[:, 0], pos_ctx[:, 0]
+            pos1 = pos[:, 1:].reshape(b * (v - 1), *pos.shape[2:])
+            pctx1 = pos_ctx[:, 1:].reshape(b * (v - 1), *pos_ctx.shape[2:])
+            n_layers = len(self.dec_blocks)
+            for li, (blk1, blk2) in enumerate(zip(self.dec_blocks, blocks2)):
+                ctx0 = cur1.view(b, (v - 1) * l, c)
+                ctx1 = torch.empty(b * (v - 1), (v - 1) * l, c, dtype=cur.dtype, device=cur.device)
+                _lib.check(L.s3r_gather_other_views_bf16(C.c_void_p(cur0.data_ptr()), C.c_void_p(cur1.data_ptr()),
+                                                         C.c_void_p(ctx1.data_ptr()), b, v, l, c,
+                                                         C.c_void_p(torch.cuda.current_stream(cur.device).cuda_stream)),
+                           "s3r_gather_other_views_bf16")
+                x1 = cur1.view(b * (v - 1), l, c)
+                r0, r1 = fork_join([lambda: blk1(cur0, ctx0, pos0, pctx0, parallel=parallel),
+                                    lambda: blk2(x1, ctx1, pos1, pctx1, parallel=parallel)], feat.device, parallel=parallel)
+                cur0, cur1 = r0, r1.view(b, v - 1, l, c)
+                last = li + 1 == n_layers
+                outs.append(torch.cat((cur0[:, None], cur1), dim=1) if ((li + 1) in HOOKS or last) else None)
+            outs[-1] = _ln(self.dec_norm, outs[-1])
+            return [None if o is None else (_feature(o[:, :, :-1], feat.dtype) if i in HOOKS else o[:, :, :-1])
+                    for i, o in enumerate(outs)]
         # loop-invariant position slices (a [b, v-1, ...] slice of a batched tensor is a copy: once, not once per layer)
         pos0, pctx0 = pos[:, 0], pos_ctx[:, 0]
         pos1 = pos[:, 1:].reshape(b * (v - 1), *pos.shape[2:]) if v > 1 else None
@@ -303,8 +333,10 @@ class EncoderNoPoSplatMultiTokenStyle(nn.Module):
         (enc_feat, enc_pos), (sty_y, sty_pos) = fork_join(
             [lambda: self.backbone.encode_views(context), lambda: self.token_stylizer.encode_style(style)], img.device,
             parallel=par)
+        from .dpt import nhwc_supported
+        nhwc = getattr(self, "_nhwc_heads", False) and not torch.is_grad_enabled() and nhwc_supported(shape)
         dec_feat, sty_feat = fork_join(
-            [lambda: self.backbone.decode_views(enc_feat, enc_pos, parallel=par),
+            [lambda: self.backbone.decode_views(enc_feat, enc_pos, parallel=par, hooked_only=nhwc),
              lambda: self.token_stylizer.decode(sty_y, sty_pos, enc_feat, enc_pos, parallel=par)], img.device, parallel=par)
         HW, G, d_sh = h * w, v * h * w, self.gaussian_adapter.d_sh
         dev = img.device
@@ -316,8 +348,6 @@ class EncoderNoPoSplatMultiTokenStyle(nn.Module):
         rots = torch.empty(b, G, 4, device=dev) if visualization_dump is not None else None
         L = _lib.lib()
         p = lambda t: None if t is None else C.c_void_p(t.data_ptr())
-        from .dpt import nhwc_supported
-        nhwc = getattr(self, "_nhwc_heads", False) and not torch.is_grad_enabled() and nhwc_supported(shape)
 
         def head_branch(head, feats, i, with_img):
             """One DPT pyramid of view i: bf16 NHWC on the tcgen05 implicit-GEMM convolutions (pixel-major fp32 rows
