@@ -155,7 +155,7 @@ class AsymmetricCroCoMulti(CroCoTrunk):
             l, c = cur.shape[2:]
             L = _lib.lib()
             cur0, cur1 = cur[:, 0].contiguous(), cur[:, 1:].contiguous()           # [b, l, c], [b, v-1, l, c]
-            pos0, pctx0 = pos[:, 0], pos_ctx[:, 0]
+            pos0, pctx0 = pos[:, 0].contiguous(), pos_ctx[:, 0].contiguous()   # (a strided slice is re-copied by every RoPE call)
             pos1 = pos[:, 1:].reshape(b * (v - 1), *pos.shape[2:])
             pctx1 = pos_ctx[:, 1:].reshape(b * (v - 1), *pos_ctx.shape[2:])
             n_layers = len(self.dec_blocks)
