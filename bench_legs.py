@@ -233,19 +233,23 @@ def train_step_leg(dev, batch, steps=3, world=1, layout="bf16"):
     enc.train()
     torch.backends.cuda.matmul.allow_tf32 = True   # the reference's setting (croco.py:13)
     torch.backends.cudnn.allow_tf32 = True
-    step(batch_d)                                  # warm-up (allocator, cuDNN plans, DDP buckets)
+    for _ in range(2):                             # warm-up (allocator growth, cuDNN plans, DDP buckets)
+        step(batch_d)
     torch.cuda.synchronize()
     torch.cuda.reset_peak_memory_stats(dev)
-    e0, e1 = _events()
-    e0.record()
-    for _ in range(steps):
+    per_step = []
+    for _ in range(steps + 1):                     # every step timed on its own; the median is reported (a single step
+        e0, e1 = _events()                         # that hits an allocator re-shuffle after the previous legs took 1.5x)
+        e0.record()
         loss, logs = step(batch_d)
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / steps
+        e1.record()
+        torch.cuda.synchronize()
+        per_step.append(e0.elapsed_time(e1))
+    ms = sorted(per_step)[len(per_step) // 2]
     res = {"ms_per_step": ms, "scenes_per_s_per_gpu": batch / (ms * 1e-3), "batch_per_gpu": batch, "target_views": V,
            "trainable_params": n_train, "grad_allreduce_bytes": 4 * n_train if world > 1 else 0,
            "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 1e9, "loss": float(loss),
+           "ms_per_step_each": [round(t, 1) for t in per_step], "timing": "median of the individually timed steps",
            "what": "stage-2 step: encoder fwd x2 (style + identity pass) -> rasterizer fwd+bwd (our kernels) -> VGG style / identity "
                    "losses (tcgen05 convolutions, fwd + dgrad) -> encoder backward -> "
                    + ("DDP bucketed NCCL all-reduce -> " if world > 1 else "") + "clip -> AdamW",
