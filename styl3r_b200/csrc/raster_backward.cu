@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(BB_THREADS, 2) s3r_blend_bwd_kernel(
 
   // ===== consumers
   const float pxf = (float)px, pyf = (float)py;
-  const float bx0 = (float)X0, by0 = (float)Y0;
+  const uint32_t cellbits = 3u << (4 * (w >> 1) + 2 * (w & 1));
   const uint32_t lt = (1u << lane) - 1u;
   uint8_t* list = sm.list[w];
   const float T_final = inside ? final_T[(size_t)view * HW + pix] : 0.f;
@@ -180,13 +180,8 @@ __global__ void __launch_bounds__(BB_THREADS, 2) s3r_blend_bwd_kernel(
 #pragma unroll
       for (int j = 0; j < BB_CHUNK / 32; j++) {
         const int i = j * 32 + lane;
-        bool hit = false;
-        if ((uint32_t)i < cnt) {
-          const float4 r0 = sm.rec[s][i * 3];
-          const float4 r2 = sm.rec[s][i * 3 + 2];
-          hit = r2.z >= 0.f && (r0.x + r2.z >= bx0) && (r0.x - r2.z <= bx0 + 7.f) && (r0.y + r2.w >= by0) &&
-                (r0.y - r2.w <= by0 + 3.f);
-        }
+        // the instance's cell mask (sort epilogue): bits of the two 4x4 cells that make up this warp's 8x4 block
+        const bool hit = (uint32_t)i < cnt && (__float_as_uint(sm.rec[s][i * 3 + 2].z) & cellbits) != 0u;
         const uint32_t m = __ballot_sync(0xffffffffu, hit);
         if (hit) list[count + __popc(m & lt)] = (uint8_t)i;
         count += __popc(m);
@@ -211,12 +206,12 @@ __global__ void __launch_bounds__(BB_THREADS, 2) s3r_blend_bwd_kernel(
           const float dx = r0.x - pxf, dy = r0.y - pyf;
           // same fast log2-domain evaluation and guard bands as the forward kernel (raster_blend.cu), so that the
           // set of contributing Gaussians is the one the forward pass composited
-          const float l2g = fmaf(dx, fmaf(r0.z, dx, r0.w * dy), (r1.x * dy) * dy);
+          const float l2g = fmaf(dx, fmaf(r1.x, dx, r0.z * dy), (r0.w * dy) * dy);
           float G = bfast_exp2(l2g);
           float alpha = fminf(0.99f, r1.y * G);
           bool kp = kk >= 0 && (base_idx + (uint32_t)i) < last;
-          // the true conic for the gradient formulas (the record holds A' = KA*A, B' = KB*B, C' = KA*C)
-          float cA = r0.z * S3R_INV_KA, cB = r0.w * S3R_INV_KB, cC = r1.x * S3R_INV_KA;
+          // the true conic for the gradient formulas (the record holds B' = KB*B, C' = KA*C | A' = KA*A)
+          float cA = r1.x * S3R_INV_KA, cB = r0.z * S3R_INV_KB, cC = r0.w * S3R_INV_KA;
           if (kp) {
             if ((alpha >= ALPHA_LO && alpha < ALPHA_HI) || fabsf(l2g) < S3R_PZERO_BAND) {
               const uint32_t gid = __ldg(point_list + (size_t)rg.x + base_idx + i);

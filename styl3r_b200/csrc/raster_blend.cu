@@ -51,6 +51,49 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                : "memory");
 }
 
+// packed fp32 pairs (sm_100: FADD2 / FMUL2 / FFMA2 on 64-bit register pairs)
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+
+// shared-memory loads by 32-bit shared-window address (the survivor lists hold such addresses; volatile: ordered with the
+// mbarrier waits / arrivals, which are volatile asm as well)
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float2 lds64(uint32_t addr) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint2 lds64u(uint32_t addr) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+  return v;
+}
+
 // exact (oracle-identical) alpha for threshold-band evaluations
 __device__ __noinline__ float exact_alpha(float power, float opacity) {
   const float e = (float)exp((double)power);
@@ -58,7 +101,12 @@ __device__ __noinline__ float exact_alpha(float power, float opacity) {
 }
 
 #ifndef BLEND_U
-#define BLEND_U 4        // survivors evaluated per batch (independent alpha chains -> ILP)
+#define BLEND_U 4        // survivors evaluated per batch (independent alpha chains -> ILP); must stay 4 (two f32x2 pairs)
+#endif
+#ifndef BLEND_HALVES
+// survivor lists per consumer warp: 2 = each half-warp owns a 4x4 pixel block with its own compacted list (the cull is
+// twice as fine: a splat that covers only one half of the 8x4 block costs the other half nothing), 1 = one list per 8x4 block
+#define BLEND_HALVES 2
 #endif
 #ifndef BLEND_STAGES
 #define BLEND_STAGES 4   // depth of the TMA ring
@@ -75,9 +123,14 @@ __device__ __noinline__ float exact_alpha(float power, float opacity) {
 #define BLEND_CWARPS (8 / BLEND_SPLIT)  // consumer warps (one 8x4 pixel block each); the last warp is the TMA producer
 #define BLEND_THREADS (32 * (BLEND_CWARPS + 1))
 
+#define BLEND_STAGE_BYTES ((BLEND_CHUNK + 1) * S3R_REC_BYTES)
+#define BLEND_LIST_LEN (BLEND_CHUNK + 2 * BLEND_U + 8)
 struct __align__(128) BlendSmem {
   float4 rec[BLEND_STAGES][(BLEND_CHUNK + 1) * 3];  // + one dummy record per stage (never hits): pads survivor batches
-  uint8_t list[BLEND_CWARPS][BLEND_CHUNK + 2 * BLEND_U + 8];  // per-warp compacted survivor indices
+  // per-(half-)warp compacted survivors, stored as the record's 16-bit shared-memory address (the kernel is never
+  // launched in a cluster, so the CTA's shared window starts at rank 0 and the whole struct lies below 2^16; checked at
+  // kernel start): the compositing loop turns a list entry into an LDS address with one instruction
+  uint16_t list[BLEND_CWARPS][BLEND_HALVES][BLEND_LIST_LEN];
   uint64_t full[BLEND_STAGES];                   // producer -> consumers (expect_tx / complete_tx)
   uint64_t empty[BLEND_STAGES];                  // consumers -> producer (one arrival per consumer warp)
   int done_warps;
@@ -131,10 +184,11 @@ __global__ void __launch_bounds__(BLEND_THREADS, BLEND_MINB) s3r_blend_fwd_kerne
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
 
   if (tid < BLEND_STAGES) {  // dummy record: so far away that log2 G = -1.8e19 -> alpha = 0 (no range predicates in the loop)
-    sm.rec[tid][BLEND_CHUNK * 3] = make_float4(3e9f, 3e9f, -1.0f, 0.0f);
+    sm.rec[tid][BLEND_CHUNK * 3] = make_float4(3e9f, 3e9f, 0.0f, -1.0f);
     sm.rec[tid][BLEND_CHUNK * 3 + 1] = make_float4(-1.0f, 0.0f, 0.0f, 0.0f);
-    sm.rec[tid][BLEND_CHUNK * 3 + 2] = make_float4(0.0f, 0.0f, -1.0f, -1.0f);
+    sm.rec[tid][BLEND_CHUNK * 3 + 2] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
   }
+  if (smem_u32(&sm) + (uint32_t)sizeof(BlendSmem) > 0x10000u) __trap();  // survivor lists hold 16-bit shared addresses
   s3r_grid_dependency_sync();  // the prologue above is shared-memory only
 
   // Persistent CTA: work units (view, tile, part) are fetched from a device-side queue in the order bin_scan wrote to
@@ -197,18 +251,29 @@ __global__ void __launch_bounds__(BLEND_THREADS, BLEND_MINB) s3r_blend_fwd_kerne
   const int tx = tile % tiles_x, ty = tile / tiles_x;
   const int wt = part * BLEND_CWARPS + w;                                            // warp index inside the tile
   const int X0 = tx * S3R_TILE + (wt & 1) * 8, Y0 = ty * S3R_TILE + (wt >> 1) * 4;  // this warp's 8x4 block
+#if BLEND_HALVES == 2
+  const int half = lane >> 4;  // half-warp h owns the 4x4 block at x offset 4h
+  const int px = X0 + 4 * half + (lane & 3), py = Y0 + ((lane >> 2) & 3);
+#else
+  const int half = 0;
   const int px = X0 + (lane & 7), py = Y0 + (lane >> 3);
+#endif
   const bool inside = px < W && py < H;
   const float pxf = (float)px, pyf = (float)py;
-  const float bx0 = (float)X0, by0 = (float)Y0;
+  const uint32_t cellbit = 1u << (4 * (wt >> 1) + 2 * (wt & 1));  // left 4x4 cell of the block (the right one is the next bit)
   const uint32_t lt = (1u << lane) - 1u;
-  uint8_t* list = sm.list[w];
+  uint16_t* list = sm.list[w][half];
+  const uint32_t list_s = smem_u32(list);
 
   // A pixel that has terminated (test_T < 1e-4), or lies outside the image, is "dead": its lane keeps running in
   // lockstep with a poisoned pixel coordinate (+inf), so every later alpha evaluates to exactly 0 and its T, colour and
   // n_contrib stay frozen without any `done` predicate in the loop.
-  float T = 1.0f, Cr = 0.f, Cg = 0.f, Cb = 0.f, D = 0.f;
-  float pxe = inside ? pxf : __int_as_float(0x7f800000);  // x coordinate used for evaluation
+  // Blackwell packed fp32 (add / mul / fma .f32x2: one issue slot for two lanes of a register pair, each half rounded
+  // like the scalar instruction): (dx, dy), the two (1 - alpha) / weight pairs of a batch and the (Cr, Cg) / (Cb, D)
+  // accumulators - the record keeps (r, g) and (b, depth) in aligned register pairs.
+  float T = 1.0f;
+  uint64_t Crg = pack2(0.f, 0.f), Cbd = pack2(0.f, 0.f);
+  uint64_t negpix = pack2(inside ? -pxf : -__int_as_float(0x7f800000), -pyf);  // (-x, -y) used for evaluation
   bool alive = inside;
   uint32_t last = 0;
   bool warp_done = !__any_sync(0xffffffffu, inside);
@@ -233,142 +298,175 @@ __global__ void __launch_bounds__(BLEND_THREADS, BLEND_MINB) s3r_blend_fwd_kerne
       continue;
     }
     const uint32_t cnt = min((uint32_t)BLEND_CHUNK, n - c * BLEND_CHUNK);
+    const uint32_t stage_off = smem_u32(&sm.rec[s][0]);  // shared address of the stage's first record
     mbar_wait(&sm.full[s], (c / BLEND_STAGES) & 1);
-    // ---- cull this stage against the warp's own pixel block and compact the survivors
-    int count = 0;
+    // ---- cull this stage against the warp's pixel block(s) and compact the survivors: one bit test per record on
+    // the cell mask the sort epilogue stored in the record (bit 4*cy + cx over the tile's 4x4-pixel cells)
+    int count = 0;  // survivors of this lane's list
+#if BLEND_HALVES == 2
+    int count_other = 0;
+#endif
 #pragma unroll
     for (int j = 0; j < BLEND_CHUNK / 32; j++) {
       const int i = j * 32 + lane;
-      bool hit = false;
-      if ((uint32_t)i < cnt) {
-        const float4 r0 = sm.rec[s][i * 3];
-        const float4 r2 = sm.rec[s][i * 3 + 2];
-        // axis-aligned box of { alpha >= 1/255 } against the block (a tighter corner-cut test and skipping all-dead
-        // batches were measured and cost more than they save)
-        hit = r2.z >= 0.f && (r0.x + r2.z >= bx0) && (r0.x - r2.z <= bx0 + 7.f) && (r0.y + r2.w >= by0) &&
-              (r0.y - r2.w <= by0 + 3.f);
-      }
+      const uint16_t off = (uint16_t)(stage_off + (uint32_t)i * S3R_REC_BYTES);
+      const uint32_t cm = (uint32_t)i < cnt ? __float_as_uint(sm.rec[s][i * 3 + 2].z) : 0u;
+#if BLEND_HALVES == 2
+      const bool hit0 = (cm & cellbit) != 0u, hit1 = (cm & (cellbit << 1)) != 0u;
+      const uint32_t m0 = __ballot_sync(0xffffffffu, hit0);
+      const uint32_t m1 = __ballot_sync(0xffffffffu, hit1);
+      const int c0 = half ? count_other : count, c1 = half ? count : count_other;
+      if (hit0) sm.list[w][0][c0 + __popc(m0 & lt)] = off;
+      if (hit1) sm.list[w][1][c1 + __popc(m1 & lt)] = off;
+      const int n0 = __popc(m0), n1 = __popc(m1);
+      count += half ? n1 : n0;
+      count_other += half ? n0 : n1;
+#else
+      const bool hit = (cm & (cellbit * 3u)) != 0u;
       const uint32_t m = __ballot_sync(0xffffffffu, hit);
-      if (hit) list[count + __popc(m & lt)] = (uint8_t)i;
+      if (hit) list[count + __popc(m & lt)] = off;
       count += __popc(m);
+#endif
     }
-    if (lane < BLEND_U) list[count + lane] = (uint8_t)BLEND_CHUNK;  // pad the last batch with the dummy record
+    // pad with the stage's dummy record up to the end of the last batch (of the longer list)
+    const uint16_t dummy_off = (uint16_t)(stage_off + BLEND_CHUNK * S3R_REC_BYTES);
+#if BLEND_HALVES == 2
+    const int nbatch = max(count, count_other);
+    for (int p = count + (lane & 15); p < nbatch + BLEND_U; p += 16) list[p] = dummy_off;
+#else
+    const int nbatch = count;
+    if (lane < BLEND_U) list[count + lane] = dummy_off;
+#endif
     __syncwarp();
     const uint32_t base_idx = c * BLEND_CHUNK;
-    int lastpos = -1;
-    uint32_t packed_next[(BLEND_U + 3) / 4];  // survivor indices of the next batch, fetched one batch ahead
-#pragma unroll
-    for (int q4 = 0; q4 < (BLEND_U + 3) / 4; q4++) packed_next[q4] = *reinterpret_cast<const uint32_t*>(list + 4 * q4);
+    uint32_t lastoff = 0xffffffffu;  // list entry (record offset) of the last composited splat of this chunk
+    uint2 packed_next = lds64u(list_s);  // survivor addresses of the next batch, fetched one batch ahead
+    uint32_t lp = list_s;
 #pragma unroll 1
-    for (int k = 0; k < count; k += BLEND_U) {
-      uint32_t packed[(BLEND_U + 3) / 4];
-#pragma unroll
-      for (int q4 = 0; q4 < (BLEND_U + 3) / 4; q4++) {
-        packed[q4] = packed_next[q4];
-        packed_next[q4] = *reinterpret_cast<const uint32_t*>(list + k + BLEND_U + 4 * q4);
-      }
-      float alpha[BLEND_U], cr[BLEND_U], cg[BLEND_U], cb[BLEND_U], dp[BLEND_U];  // alpha: 0 unless the splat is kept
+    for (int k = 0; k < nbatch; k += BLEND_U) {
+      const uint2 packed = packed_next;
+      lp += 2 * BLEND_U;
+      packed_next = lds64u(lp);
+      const uint32_t off[BLEND_U] = {packed.x & 0xffffu, packed.x >> 16, packed.y & 0xffffu, packed.y >> 16};
+      float alpha[BLEND_U];  // 0 unless the splat is kept
+      uint64_t crg[BLEND_U], cbd[BLEND_U];
       float t[BLEND_U + 1];
-      const int lastpos_in = lastpos;
+      const uint32_t lastoff_in = lastoff;
       bool near_thr = false;
-      // ---- BLEND_U independent alpha chains (branch-free)
+      // ---- BLEND_U independent alpha chains (branch-free); entries past the list's end are the dummy record
 #pragma unroll
       for (int u = 0; u < BLEND_U; u++) {
-        const int i = (packed[u >> 2] >> (8 * (u & 3))) & 0xff;  // entries past `count` are the dummy record
-        const float4 r0 = sm.rec[s][i * 3];
-        const float4 r1 = sm.rec[s][i * 3 + 1];
-        const float2 r2 = *reinterpret_cast<const float2*>(&sm.rec[s][i * 3 + 2]);
-        const float dx = r0.x - pxe, dy = r0.y - pyf;
-        // log2 G = dx*(A'*dx + B'*dy) + C'*dy*dy on the pre-scaled conic: 2 FMUL + 2 FFMA + 1 FMUL, then MUFU.EX2
-        const float l2g = fmaf(dx, fmaf(r0.z, dx, r0.w * dy), (r1.x * dy) * dy);
+        const float4 r0 = lds128(off[u]);
+        const float4 r1 = lds128(off[u] + 16);
+        const float2 r2 = lds64(off[u] + 32);
+        float dx, dy;
+        unpack2(add2(pack2(r0.x, r0.y), negpix), dx, dy);
+        // log2 G = dx*(A'*dx + B'*dy) + (C'*dy)*dy on the pre-scaled conic: FMUL2 + 2 FFMA + FMUL, then MUFU.EX2
+        float bdy, cdy;
+        unpack2(mul2(pack2(r0.z, r0.w), pack2(dy, dy)), bdy, cdy);
+        const float l2g = fmaf(dx, fmaf(r1.x, dx, bdy), cdy * dy);
         const float a = fminf(0.99f, r1.y * fast_exp2(l2g));
         const bool keep = a >= ALPHA_HI;
         // guard bands: alpha within 1e-4 (relative) below 1/255, or an exponent that is positive / so close to 0 that
         // its sign is in doubt (the oracle skips `power > 0`): those evaluations are decided exactly below
         near_thr = near_thr || ((a >= ALPHA_LO) && !keep) || (l2g > -S3R_PZERO_BAND);
         alpha[u] = keep ? a : 0.0f;
-        lastpos = keep ? (k + u) : lastpos;
-        cr[u] = r1.z;
-        cg[u] = r1.w;
-        cb[u] = r2.x;
-        dp[u] = r2.y;
-      }
-      // ---- rare: some evaluation landed in a guard band -> decide it like the oracle, from the exact conic
-      if (__any_sync(0xffffffffu, near_thr)) {
-        lastpos = lastpos_in;
-#pragma unroll
-        for (int u = 0; u < BLEND_U; u++) {
-          if (k + u < count) {
-            const int i = (packed[u >> 2] >> (8 * (u & 3))) & 0xff;
-            const float4 r0 = sm.rec[s][i * 3];
-            const float4 r1 = sm.rec[s][i * 3 + 1];
-            const float dx = r0.x - pxe, dy = r0.y - pyf;
-            const float l2g = fmaf(dx, fmaf(r0.z, dx, r0.w * dy), (r1.x * dy) * dy);
-            const float a = fminf(0.99f, r1.y * fast_exp2(l2g));
-            if ((a >= ALPHA_LO && a < ALPHA_HI) || l2g > -S3R_PZERO_BAND) {
-              const uint32_t gid = point_list[(size_t)rg.x + base_idx + i];
-              float ax = a;
-              const bool kx = exact_decide(conic_opacity[(size_t)view * P + gid], dx, dy, &ax);
-              alpha[u] = (kx && alive) ? ax : 0.0f;
-            }
-          }
-          lastpos = alpha[u] > 0.0f ? (k + u) : lastpos;
-        }
+        lastoff = keep ? off[u] : lastoff;
+        crg[u] = pack2(r1.z, r1.w);
+        cbd[u] = pack2(r2.x, r2.y);
       }
       // ---- transmittance chain of the batch; T only decreases, so the batch contains a termination iff t[U] < 1e-4
+      const uint64_t a01 = pack2(alpha[0], alpha[1]), a23 = pack2(alpha[2], alpha[3]);
+      float om[BLEND_U];  // 1 - alpha: fma(alpha, -1, 1) rounds once, like the subtraction
+      unpack2(fma2(a01, pack2(-1.0f, -1.0f), pack2(1.0f, 1.0f)), om[0], om[1]);
+      unpack2(fma2(a23, pack2(-1.0f, -1.0f), pack2(1.0f, 1.0f)), om[2], om[3]);
       t[0] = T;
 #pragma unroll
-      for (int u = 0; u < BLEND_U; u++) t[u + 1] = t[u] * (1.0f - alpha[u]);
-      if (!__any_sync(0xffffffffu, t[BLEND_U] < 0.0001f)) {
-        // common case: front-to-back compositing of the whole batch without a single predicate
+      for (int u = 0; u < BLEND_U; u++) t[u + 1] = t[u] * om[u];
+      // common case: front-to-back compositing of the whole batch without a single predicate (instantiated twice, so
+      // that the rare path below does not constrain the register allocation of the hot one)
+      auto composite_all = [&](uint64_t p01, uint64_t p23) {
+        float wgt[BLEND_U];
+        unpack2(mul2(p01, pack2(t[0], t[1])), wgt[0], wgt[1]);
+        unpack2(mul2(p23, pack2(t[2], t[3])), wgt[2], wgt[3]);
 #pragma unroll
         for (int u = 0; u < BLEND_U; u++) {
-          const float wgt = alpha[u] * t[u];
-          Cr = fmaf(cr[u], wgt, Cr);
-          Cg = fmaf(cg[u], wgt, Cg);
-          Cb = fmaf(cb[u], wgt, Cb);
-          D = fmaf(dp[u], wgt, D);
+          const uint64_t w2 = pack2(wgt[u], wgt[u]);
+          Crg = fma2(crg[u], w2, Crg);
+          Cbd = fma2(cbd[u], w2, Cbd);
           if (kHasNT) {
             if (alpha[u] > 0.0f && t[u + 1] > 0.5f) {
-              const int i = (packed[u >> 2] >> (8 * (u & 3))) & 0xff;
+              const uint32_t i = (off[u] - stage_off) / S3R_REC_BYTES;
               atomicAdd(&n_touched[(size_t)view * P + point_list[(size_t)rg.x + base_idx + i]], 1);
             }
           }
         }
         T = t[BLEND_U];
+      };
+      // one vote covers both rare events of a batch: an evaluation inside a guard band, or a pixel that terminates
+      if (!__any_sync(0xffffffffu, near_thr || t[BLEND_U] < 0.0001f)) {
+        composite_all(a01, a23);
       } else {
-        // some pixel of the warp terminates inside this batch (at most once per pixel): predicated version
-        lastpos = lastpos_in;
+        // ---- some evaluation landed in a guard band -> decide it like the oracle, from the exact conic
+        if (__any_sync(0xffffffffu, near_thr)) {
+          lastoff = lastoff_in;
 #pragma unroll
-        for (int u = 0; u < BLEND_U; u++) {
-          const bool stop = t[u + 1] < 0.0001f;  // stays true for the rest of the batch
-          const bool acc = !stop && alpha[u] > 0.0f;
-          const float wgt = stop ? 0.0f : alpha[u] * t[u];
-          Cr = fmaf(cr[u], wgt, Cr);
-          Cg = fmaf(cg[u], wgt, Cg);
-          Cb = fmaf(cb[u], wgt, Cb);
-          D = fmaf(dp[u], wgt, D);
-          if (kHasNT) {
-            if (acc && t[u + 1] > 0.5f) {
-              const int i = (packed[u >> 2] >> (8 * (u & 3))) & 0xff;
-              atomicAdd(&n_touched[(size_t)view * P + point_list[(size_t)rg.x + base_idx + i]], 1);
+          for (int u = 0; u < BLEND_U; u++) {
+            if (k + u < count) {
+              const float4 r0 = lds128(off[u]);
+              const float4 r1 = lds128(off[u] + 16);
+              float dx, dy;
+              unpack2(add2(pack2(r0.x, r0.y), negpix), dx, dy);
+              const float l2g = fmaf(dx, fmaf(r1.x, dx, r0.z * dy), (r0.w * dy) * dy);
+              const float a = fminf(0.99f, r1.y * fast_exp2(l2g));
+              if ((a >= ALPHA_LO && a < ALPHA_HI) || l2g > -S3R_PZERO_BAND) {
+                const uint32_t i = (off[u] - stage_off) / S3R_REC_BYTES;
+                const uint32_t gid = point_list[(size_t)rg.x + base_idx + i];
+                float ax = a;
+                const bool kx = exact_decide(conic_opacity[(size_t)view * P + gid], dx, dy, &ax);
+                alpha[u] = (kx && alive) ? ax : 0.0f;
+              }
             }
+            lastoff = alpha[u] > 0.0f ? off[u] : lastoff;
           }
-          T = stop ? T : t[u + 1];
-          lastpos = acc ? (k + u) : lastpos;
+#pragma unroll
+          for (int u = 0; u < BLEND_U; u++) t[u + 1] = t[u] * (1.0f - alpha[u]);
         }
-        if (t[BLEND_U] < 0.0001f) {
-          alive = false;
-          pxe = __int_as_float(0x7f800000);
-        }
-        if (!__any_sync(0xffffffffu, alive)) {
-          warp_done = true;
-          break;
+        if (!__any_sync(0xffffffffu, t[BLEND_U] < 0.0001f)) {
+          composite_all(pack2(alpha[0], alpha[1]), pack2(alpha[2], alpha[3]));
+        } else {
+          // some pixel of the warp terminates inside this batch (at most once per pixel): predicated version
+          lastoff = lastoff_in;
+#pragma unroll
+          for (int u = 0; u < BLEND_U; u++) {
+            const bool stop = t[u + 1] < 0.0001f;  // stays true for the rest of the batch
+            const bool acc = !stop && alpha[u] > 0.0f;
+            const float wgt = stop ? 0.0f : alpha[u] * t[u];
+            const uint64_t w2 = pack2(wgt, wgt);
+            Crg = fma2(crg[u], w2, Crg);
+            Cbd = fma2(cbd[u], w2, Cbd);
+            if (kHasNT) {
+              if (acc && t[u + 1] > 0.5f) {
+                const uint32_t i = (off[u] - stage_off) / S3R_REC_BYTES;
+                atomicAdd(&n_touched[(size_t)view * P + point_list[(size_t)rg.x + base_idx + i]], 1);
+              }
+            }
+            T = stop ? T : t[u + 1];
+            lastoff = acc ? off[u] : lastoff;
+          }
+          if (t[BLEND_U] < 0.0001f) {
+            alive = false;
+            negpix = pack2(-__int_as_float(0x7f800000), -pyf);
+          }
+          if (!__any_sync(0xffffffffu, alive)) {
+            warp_done = true;
+            break;
+          }
         }
       }
     }
-    // n_contrib = 1-based index of the last composited splat: resolve this chunk's list position while the list is live
-    if (lastpos >= 0) last = base_idx + list[lastpos] + 1u;
+    // n_contrib = 1-based index of the last composited splat
+    if (lastoff != 0xffffffffu) last = base_idx + (lastoff - stage_off) / S3R_REC_BYTES + 1u;
     __syncwarp();
     if (lane == 0) {
       if (warp_done) atomicAdd(&sm.done_warps, 1);
@@ -380,6 +478,9 @@ __global__ void __launch_bounds__(BLEND_THREADS, BLEND_MINB) s3r_blend_fwd_kerne
     const size_t pix = (size_t)py * W + px;
     const float* bg = background + view * 3;
     float* oc = out_color + (size_t)view * 3 * HW;
+    float Cr, Cg, Cb, D;
+    unpack2(Crg, Cr, Cg);
+    unpack2(Cbd, Cb, D);
     oc[pix] = Cr + T * bg[0];
     oc[HW + pix] = Cg + T * bg[1];
     oc[2 * HW + pix] = Cb + T * bg[2];

@@ -214,7 +214,8 @@ __global__ void __launch_bounds__(S3R_CHUNK, 4) s3r_preprocess_kernel(
     rect_out[vi] = rect;
     if (rect != 0u) {
       // 48-byte blend record of this (view, Gaussian), gathered into sorted order by the tile sort:
-      //   (x, y, A', B' | C', opacity, r, g | b, depth, ex, ey)   A' = -0.5*log2(e)*A ... (s3r_common.cuh)
+      //   (x, y, B', C' | A', opacity, r, g | b, depth, ex, ey)   A' = -0.5*log2(e)*A ... (s3r_common.cuh); the sort
+      //   epilogue replaces (ex, ey) by the instance's cell mask
       // (ex, ey) = half-extent in pixels of { alpha >= 1/255 }: quadratic form q <= 2 ln(255 o);
       // |dx| <= sqrt(q C / det), |dy| <= sqrt(q A / det).  Not a parity quantity (a conservative cull box).
       float ex = -1.f, ey = -1.f;
@@ -228,8 +229,8 @@ __global__ void __launch_bounds__(S3R_CHUNK, 4) s3r_preprocess_kernel(
         ex = ey = 1e30f;  // degenerate conic: never cull
       }
       float4* r = grecords + vi * 3;
-      r[0] = make_float4(pix.x, pix.y, co.x * S3R_KA, co.y * S3R_KB);
-      r[1] = make_float4(co.z * S3R_KA, co.w, col.x, col.y);
+      r[0] = make_float4(pix.x, pix.y, co.y * S3R_KB, co.z * S3R_KA);
+      r[1] = make_float4(co.x * S3R_KA, co.w, col.x, col.y);
       r[2] = make_float4(col.z, depth, ex, ey);
     }
   }

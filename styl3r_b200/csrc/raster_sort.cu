@@ -106,14 +106,34 @@ __device__ bool radix_pass(const unsigned long long* src, unsigned long long* ds
 #define SORT_MAX_BUCKET 48  // above this the rank-by-counting step could go quadratic: use the LSD path
 #define SORT_KPT ((S3R_SORT_SMEM_CAP + SORT_THREADS - 1) / SORT_THREADS)  // keys per thread in the bucket path
 
+// 16-bit incidence mask of the splat's { alpha >= 1/255 } box (centre (x, y), half-extents (ex, ey) from preprocess) over
+// the 4x4-pixel cells of the 16x16 tile at (tx0, ty0): bit 4*cy + cx.  Built once per instance here, so that the blend
+// kernels' per-warp cull is one bit test per record instead of four float comparisons repeated by all 8 warps.
+// Conservative like the box itself (never a parity quantity); ex < 0 (alpha can never reach 1/255) gives 0.
+__device__ __forceinline__ uint32_t cell_mask(float x, float y, float ex, float ey, float tx0, float ty0) {
+  if (!(ex >= 0.f)) return 0u;
+  const float xlo = x - ex, xhi = x + ex, ylo = y - ey, yhi = y + ey;
+  uint32_t mx = 0u, my = 0u;
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    mx |= (xhi >= tx0 + 4.f * i && xlo <= tx0 + 4.f * i + 3.f) ? (1u << i) : 0u;
+    my |= (yhi >= ty0 + 4.f * i && ylo <= ty0 + 4.f * i + 3.f) ? (1u << (4 * i)) : 0u;
+  }
+  return mx * my;  // outer product: no carries (my has one bit per nibble)
+}
+
 __device__ __forceinline__ void write_sorted(uint32_t o, unsigned long long k, unsigned long long tile_hi, size_t vbase,
-                                             const float4* __restrict__ grecords, uint32_t* __restrict__ point_list,
+                                             float tx0, float ty0, const float4* __restrict__ grecords,
+                                             uint32_t* __restrict__ point_list,
                                              unsigned long long* __restrict__ point_keys, float4* __restrict__ records) {
   const uint32_t id = (uint32_t)k, dbits = (uint32_t)(k >> 32);
   point_list[o] = id;
   if (point_keys) point_keys[o] = tile_hi | dbits;
   const float4* g = grecords + (vbase + id) * 3;
-  const float4 a = __ldg(g), b = __ldg(g + 1), c = __ldg(g + 2);
+  const float4 a = __ldg(g), b = __ldg(g + 1);
+  float4 c = __ldg(g + 2);
+  c.z = __uint_as_float(cell_mask(a.x, a.y, c.z, c.w, tx0, ty0));  // (ex, ey) -> per-instance cell mask
+  c.w = 0.f;
   float4* r = records + (size_t)o * 3;
   r[0] = a;
   r[1] = b;
@@ -151,7 +171,7 @@ __device__ void build_work_order(int n, const uint32_t* __restrict__ tile_count,
 
 // grid (tiles + 1, n_views): block (tiles, 0) builds the blend work queue, blocks (tiles, v > 0) exit
 __global__ void __launch_bounds__(SORT_THREADS) s3r_tile_sort_kernel(
-    int P, int tiles, const uint2* __restrict__ ranges, unsigned long long* __restrict__ keys_a,
+    int P, int tiles, int tiles_x, const uint2* __restrict__ ranges, unsigned long long* __restrict__ keys_a,
     unsigned long long* __restrict__ keys_b, const float4* __restrict__ grecords, uint32_t* __restrict__ point_list,
     unsigned long long* __restrict__ point_keys, float4* __restrict__ records, const uint32_t* __restrict__ tile_count,
     const long long* __restrict__ status, uint32_t* __restrict__ work_order) {
@@ -180,6 +200,7 @@ __global__ void __launch_bounds__(SORT_THREADS) s3r_tile_sort_kernel(
   unsigned long long* gb = keys_b + rg.x;
   const size_t vbase = (size_t)view * P;
   const unsigned long long tile_hi = ((unsigned long long)((uint32_t)view * (uint32_t)tiles + (uint32_t)tile)) << 32;
+  const float tx0 = (float)((tile % tiles_x) * S3R_TILE), ty0 = (float)((tile / tiles_x) * S3R_TILE);
 
   if (n <= S3R_SORT_SMEM_CAP) {
     // ================= bucket path
@@ -269,7 +290,7 @@ __global__ void __launch_bounds__(SORT_THREADS) s3r_tile_sort_kernel(
         const uint32_t b0 = s_start[d], b1 = s_start[d + 1];
         uint32_t rank = 0;
         for (uint32_t q = b0; q < b1; q++) rank += (s_keys[q] < key) ? 1u : 0u;
-        write_sorted(rg.x + b0 + rank, key, tile_hi, vbase, grecords, point_list, point_keys, records);
+        write_sorted(rg.x + b0 + rank, key, tile_hi, vbase, tx0, ty0, grecords, point_list, point_keys, records);
       }
       return;
     }
@@ -290,7 +311,7 @@ __global__ void __launch_bounds__(SORT_THREADS) s3r_tile_sort_kernel(
       }
     }
     for (uint32_t i = tid; i < n; i += SORT_THREADS)
-      write_sorted(rg.x + i, cur[i], tile_hi, vbase, grecords, point_list, point_keys, records);
+      write_sorted(rg.x + i, cur[i], tile_hi, vbase, tx0, ty0, grecords, point_list, point_keys, records);
     return;
   }
   // ================= global path: tiles above the shared-memory capacity
@@ -304,7 +325,7 @@ __global__ void __launch_bounds__(SORT_THREADS) s3r_tile_sort_kernel(
     __threadfence_block();
   }
   for (uint32_t i = tid; i < n; i += SORT_THREADS)
-    write_sorted(rg.x + i, __ldcg(cur + i), tile_hi, vbase, grecords, point_list, point_keys, records);
+    write_sorted(rg.x + i, __ldcg(cur + i), tile_hi, vbase, tx0, ty0, grecords, point_list, point_keys, records);
 }
 
 int s3r_launch_sort(const s3r_raster_params& p, const s3r_raster_layout& L, char* state, cudaStream_t st) {
@@ -314,7 +335,7 @@ int s3r_launch_sort(const s3r_raster_params& p, const s3r_raster_layout& L, char
   int rc = s3r_ensure_dynamic_smem(s3r_tile_sort_kernel, smem, configured);
   if (rc != S3R_OK) return rc;
   dim3 grid(L.tiles + 1, p.n_views);
-  S3R_CUDA_CHECK(s3r_launch_pdl(s3r_tile_sort_kernel, grid, dim3(SORT_THREADS), smem, st, (s3r_raster_pdl_mask() >> 3) & 1, p.P, L.tiles,
+  S3R_CUDA_CHECK(s3r_launch_pdl(s3r_tile_sort_kernel, grid, dim3(SORT_THREADS), smem, st, (s3r_raster_pdl_mask() >> 3) & 1, p.P, L.tiles, L.tiles_x,
                                 (const uint2*)(state + L.ranges), (unsigned long long*)(state + L.keys_unsorted),
                                 (unsigned long long*)(state + L.keys_tmp), (const float4*)(state + L.grecords),
                                 (uint32_t*)(state + L.point_list), (unsigned long long*)(state + L.point_keys),

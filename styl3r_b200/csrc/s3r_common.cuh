@@ -6,7 +6,10 @@
 #include "../../include/styl3r_b200.h"
 
 #define S3R_CHUNK 256          // Gaussians per preprocess / emit CTA (= one bit-mask row of 8 words)
-#define S3R_REC_FLOATS 12      // blend record: x y A' B' | C' o r g | b depth ex ey
+#define S3R_REC_FLOATS 12      // blend record: x y B' C' | A' o r g | b depth cellmask -  ((B', C'), (r, g), (b, depth) are
+                               // aligned register pairs for the packed f32x2 instructions; per Gaussian the last two
+                               // floats are the cull half-extents (ex, ey), which the sort epilogue turns into the
+                               // instance's 16-bit mask over the 4x4-pixel cells of its tile)
 // The record carries the conic pre-scaled into the log2 domain, A' = -0.5*log2(e)*A, B' = -log2(e)*B,
 // C' = -0.5*log2(e)*C, so that the blend kernels evaluate  log2(G) = dx*(A'*dx + B'*dy) + C'*dy*dy  with two FMAs and
 // feed MUFU.EX2 directly (5 FP32 ops instead of 10).  Decisions that must equal the oracle's unfused fp32 arithmetic
