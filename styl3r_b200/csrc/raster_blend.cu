@@ -209,7 +209,9 @@ __global__ void __launch_bounds__(BLEND_THREADS, BLEND_MINB) s3r_blend_fwd_kerne
       mbar_init(&sm.empty[s], BLEND_CWARPS);
     }
     sm.done_warps = 0;
-    sm.unit = atomicAdd(&counters[1], 1u);
+    // first unit: the queue entry at this CTA's own index (the tile sort laid the first gridDim.x entries out for the
+    // block scheduler's placement, raster_sort.cu:queue_position); afterwards the shared counter
+    sm.unit = first_unit ? blockIdx.x : gridDim.x + atomicAdd(&counters[1], 1u);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -514,28 +516,38 @@ int& s3r_blend_only_tile() {
   return v;
 }
 
-int s3r_launch_blend(const s3r_raster_params& p, const s3r_raster_outputs& o, const s3r_raster_layout& L,
-                     char* state, cudaStream_t st) {
-  auto kern = o.n_touched ? s3r_blend_fwd_kernel<true> : s3r_blend_fwd_kernel<false>;
-  // persistent grid: as many CTAs as the device holds at once (per device, cached), never more than there are units
-  static int slots[64] = {};
+int s3r_blend_grid(int* sms_out, int* slots_out) {
+  static int slots[64] = {}, sms[64] = {};
   int dev = 0;
   S3R_CUDA_CHECK(cudaGetDevice(&dev));
   dev &= 63;
   if (slots[dev] == 0) {
-    int sms = 0, per_sm = 0;
-    S3R_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    int n = 0, per_sm = 0;
+    S3R_CUDA_CHECK(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
     S3R_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, s3r_blend_fwd_kernel<false>, BLEND_THREADS, 0));
     if (per_sm > BLEND_CTAS_PER_SM) per_sm = BLEND_CTAS_PER_SM;
-    slots[dev] = sms * (per_sm > 0 ? per_sm : 1);
+    sms[dev] = n;
+    slots[dev] = n * (per_sm > 0 ? per_sm : 1);
   }
+  *sms_out = sms[dev];
+  *slots_out = slots[dev];
+  return S3R_OK;
+}
+
+int s3r_launch_blend(const s3r_raster_params& p, const s3r_raster_outputs& o, const s3r_raster_layout& L,
+                     char* state, cudaStream_t st) {
+  auto kern = o.n_touched ? s3r_blend_fwd_kernel<true> : s3r_blend_fwd_kernel<false>;
+  // persistent grid: as many CTAs as the device holds at once (per device, cached), never more than there are units
+  int n_sms = 0, n_slots = 0;
+  int rc = s3r_blend_grid(&n_sms, &n_slots);
+  if (rc != S3R_OK) return rc;
   uint32_t n_units = (uint32_t)L.tiles * (uint32_t)p.n_views * BLEND_SPLIT;
   int only_tile = -1;
   if (s3r_blend_only_tile() > 0 && s3r_blend_only_tile() <= L.tiles) {  // development probe: one tile of view 0
     only_tile = s3r_blend_only_tile() - 1;
     n_units = BLEND_SPLIT;
   }
-  dim3 grid(n_units < (uint32_t)slots[dev] ? n_units : (uint32_t)slots[dev]);
+  dim3 grid(n_units < (uint32_t)n_slots ? n_units : (uint32_t)n_slots);
   S3R_CUDA_CHECK(s3r_launch_pdl(kern, grid, dim3(BLEND_THREADS), 0, st, (s3r_raster_pdl_mask() >> 4) & 1, p.width, p.height,
                                 p.P, L.tiles_x, L.tiles, only_tile, n_units, (const uint32_t*)(state + L.work_order),
                                 (unsigned*)(state + L.counters), (const uint2*)(state + L.ranges),

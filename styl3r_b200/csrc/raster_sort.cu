@@ -143,8 +143,25 @@ __device__ __forceinline__ void write_sorted(uint32_t o, unsigned long long k, u
 // The blend stage's work queue: (view, tile) indices by descending instance count (256-bucket counting sort; the order
 // inside a bucket is arbitrary - it only affects scheduling, never results).  Runs as ONE extra CTA of the tile-sort grid
 // (block (tiles, 0)), i.e. concurrently with the sorts and off the critical path of the chain.
+//
+// Queue position: the blend kernel is a persistent grid of `slots` = sms x CTAs-per-SM CTAs whose FIRST unit is the queue
+// entry at their own blockIdx (later units come from an atomic counter).  On an idle GPU the block scheduler places
+// blocks b and b + sms on the same SM, so the first `slots` ranks are laid out boustrophedon: wave 0 in descending
+// weight, wave 1 in ascending weight, ... - the SM that got the heaviest tile gets the lightest one next.  (Placement
+// only changes which CTA renders which tile, never a result; under concurrency with other streams it is merely
+// another valid order.)  With one 256-tile view on 148 SMs the busiest SM's load drops from n[0] + n[148] to
+// n[0] + n[255].
+__device__ __forceinline__ uint32_t queue_position(uint32_t rank, uint32_t n, uint32_t sms, uint32_t slots) {
+  if (sms == 0u || rank >= slots) return rank;
+  const uint32_t wave = rank / sms, s = rank - wave * sms;
+  if ((wave & 1u) == 0u) return rank;
+  const uint32_t width = min(sms, min(n, slots) - wave * sms);  // the last wave may be partial
+  return wave * sms + (width - 1u - s);
+}
+
 __device__ void build_work_order(int n, const uint32_t* __restrict__ tile_count, const long long* __restrict__ status,
-                                 uint32_t* __restrict__ work_order, uint32_t* s_bucket /* [256] */, uint32_t* s_w /* [8] */) {
+                                 uint32_t* __restrict__ work_order, uint32_t* s_bucket /* [256] */, uint32_t* s_w /* [8] */,
+                                 uint32_t sms, uint32_t slots) {
   static_assert(SORT_THREADS == 256, "one bucket per thread");
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   s_bucket[tid] = 0u;
@@ -166,7 +183,8 @@ __device__ void build_work_order(int n, const uint32_t* __restrict__ tile_count,
   s_bucket[tid] = off;
   __syncthreads();
   for (int i = tid; i < n; i += SORT_THREADS)
-    work_order[atomicAdd(&s_bucket[255u - min(255u, tile_count[i] / width)], 1u)] = (uint32_t)i;
+    work_order[queue_position(atomicAdd(&s_bucket[255u - min(255u, tile_count[i] / width)], 1u), (uint32_t)n, sms, slots)] =
+        (uint32_t)i;
 }
 
 // grid (tiles + 1, n_views): block (tiles, 0) builds the blend work queue, blocks (tiles, v > 0) exit
@@ -174,7 +192,7 @@ __global__ void __launch_bounds__(SORT_THREADS) s3r_tile_sort_kernel(
     int P, int tiles, int tiles_x, const uint2* __restrict__ ranges, unsigned long long* __restrict__ keys_a,
     unsigned long long* __restrict__ keys_b, const float4* __restrict__ grecords, uint32_t* __restrict__ point_list,
     unsigned long long* __restrict__ point_keys, float4* __restrict__ records, const uint32_t* __restrict__ tile_count,
-    const long long* __restrict__ status, uint32_t* __restrict__ work_order) {
+    const long long* __restrict__ status, uint32_t* __restrict__ work_order, uint32_t blend_sms, uint32_t blend_slots) {
   extern __shared__ unsigned long long s_keys[];  // [2][S3R_SORT_SMEM_CAP]; bucket path: [0] = grouped keys, [1] = bucket table
   __shared__ uint32_t s_hist[SORT_WARPS][256];
   __shared__ uint32_t s_scan[SORT_WARPS];
@@ -190,7 +208,8 @@ __global__ void __launch_bounds__(SORT_THREADS) s3r_tile_sort_kernel(
   }
   s3r_grid_dependency_sync();
   if (tile == tiles) {
-    if (view == 0) build_work_order((int)gridDim.y * tiles, tile_count, status, work_order, &s_hist[0][0], s_scan);
+    if (view == 0) build_work_order((int)gridDim.y * tiles, tile_count, status, work_order, &s_hist[0][0], s_scan, blend_sms,
+                                    blend_slots);
     return;
   }
   const uint2 rg = ranges[(size_t)view * tiles + tile];
@@ -335,11 +354,15 @@ int s3r_launch_sort(const s3r_raster_params& p, const s3r_raster_layout& L, char
   int rc = s3r_ensure_dynamic_smem(s3r_tile_sort_kernel, smem, configured);
   if (rc != S3R_OK) return rc;
   dim3 grid(L.tiles + 1, p.n_views);
+  int blend_sms = 0, blend_slots = 0;
+  rc = s3r_blend_grid(&blend_sms, &blend_slots);
+  if (rc != S3R_OK) return rc;
   S3R_CUDA_CHECK(s3r_launch_pdl(s3r_tile_sort_kernel, grid, dim3(SORT_THREADS), smem, st, (s3r_raster_pdl_mask() >> 3) & 1, p.P, L.tiles, L.tiles_x,
                                 (const uint2*)(state + L.ranges), (unsigned long long*)(state + L.keys_unsorted),
                                 (unsigned long long*)(state + L.keys_tmp), (const float4*)(state + L.grecords),
                                 (uint32_t*)(state + L.point_list), (unsigned long long*)(state + L.point_keys),
                                 (float4*)(state + L.records), (const uint32_t*)(state + L.tile_count),
-                                (const long long*)(state + L.status), (uint32_t*)(state + L.work_order)));
+                                (const long long*)(state + L.status), (uint32_t*)(state + L.work_order),
+                                (uint32_t)blend_sms, (uint32_t)blend_slots));
   return S3R_OK;
 }

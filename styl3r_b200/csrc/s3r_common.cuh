@@ -55,6 +55,10 @@ int s3r_launch_sort(const s3r_raster_params& p, const s3r_raster_layout& L, char
 int s3r_launch_blend(const s3r_raster_params& p, const s3r_raster_outputs& o, const s3r_raster_layout& L,
                      char* state, cudaStream_t st);
 
+// persistent grid of the blend kernel on the current device: SM count and resident CTAs (raster_blend.cu); the tile sort
+// lays the blend work queue out for it
+int s3r_blend_grid(int* sms, int* slots);
+
 // Programmatic dependent launch switch shared by all kernels (S3R_TUNE_PDL; defined in gemm_tcgen05.cu)
 int s3r_pdl_enabled();
 int& s3r_blend_only_tile();  // S3R_TUNE_BLEND_ONLY_TILE (defined in raster_blend.cu)
