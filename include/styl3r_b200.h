@@ -276,6 +276,7 @@ int s3r_conv2d_bf16(const void* x, const void* w, const void* bias, const void* 
 #define S3R_TUNE_ATTN_ONEPASS 12 /* s3r_attention_bf16: 0 / 1 = single pass over the keys with two independent softmax streams per row (default), 2 = the two-pass kernel (exact row maximum first) */
 #define S3R_TUNE_GEMM_DIRECT 13 /* one-tile GEMM kernel: register epilogue straight from TMEM (no staging tile): 0 = auto (grids of at most ~1.5 waves: the batch-1 shapes), 1 = whenever the epilogue feature set allows, 2 = never */
 #define S3R_TUNE_RASTER_PDL 9 /* bit k != 0: raster stage k (0 preprocess, 1 bin scan, 2 bin emit, 3 tile sort, 4 blend) is launched with programmatic dependent launch */
+#define S3R_TUNE_BWD_ALL 14 /* != 0: s3r_raster_backward always runs the 10-value blend-backward kernel instead of the geometry-only / colour-only variants it selects from the requested outputs (tests compare them) */
 #define S3R_TUNE_BLEND_ONLY_TILE 8 /* development probe: != 0 -> the blend launch renders only tile (value - 1) of every view (one CTA per view): times the critical path of one tile without contention */
 int s3r_set_tunable(int32_t key, int32_t value);
 

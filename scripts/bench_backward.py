@@ -22,5 +22,7 @@ def run(v, V):
         return e0.elapsed_time(e1) / it * 1000
     full = t(lambda: rz.backward_raw(ctx, gc, gd))
     pose = t(lambda: rz.backward_raw(ctx, gc, None, only_pose=True))
-    print(f"v={v} V={V} P={ctx.P} R={ctx.status()['num_instances']}: backward all grads {full:.0f} us ({full/V:.0f}/view), pose-only {pose:.0f} us ({pose/V:.0f}/view)", flush=True)
+    only_sh = dict(means=False, cov=False, opacities=False, shs=True, colors=False, means2D=False)
+    sh = t(lambda: rz.backward_raw(ctx, gc, None, need_pose=False, needs=only_sh))
+    print(f"v={v} V={V} P={ctx.P} R={ctx.status()['num_instances']}: backward all grads {full:.0f} us ({full/V:.0f}/view), pose-only {pose:.0f} us ({pose/V:.0f}/view), SH-only {sh:.0f} us ({sh/V:.0f}/view)", flush=True)
 run(2, 1); run(2, 6)

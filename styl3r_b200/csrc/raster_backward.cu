@@ -82,6 +82,31 @@ __device__ __forceinline__ float warp_multi_reduce32(float (&v)[32], int lane) {
   return v[0];
 }
 
+// packed fp32 pairs (sm_100 FADD2 / FMUL2 / FFMA2)
+__device__ __forceinline__ uint64_t bpack2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void bunpack2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t bmul2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t bfma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ float bfast_rcp(float x) {  // MUFU.RCP, 1 ulp; x = 1 - alpha >= 0.01
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 struct __align__(128) BwdSmem {
   float4 rec[BB_STAGES][BB_CHUNK * 3];
   uint8_t list[BB_CWARPS][BB_CHUNK + 16];
@@ -90,14 +115,35 @@ struct __align__(128) BwdSmem {
   unsigned max_last;
 };
 
+// Which per-splat gradients a launch accumulates (chosen on the host from the NULL-ness of the requested outputs):
+//   ALL   10 values per splat (mean2D 2, conic 3, opacity 1, colour 3, depth 1), 3 splats per reduction batch
+//   GEOM   6 values (mean2D, conic, depth): the pose-align loop (dL/dtau only, colours independent of the pose), 5 per batch
+//   COLOR  3 values: stage-2 training (only dL/dSH is needed, model_wrapper_style.py:854-868), 10 per batch; the
+//          dL/dalpha recurrence is not evaluated at all
+// Every batch fills a 32-lane butterfly (30 values), so the reduction costs 124 / 3, 124 / 5 or 124 / 10 instructions
+// per splat.
+enum { BWD_ALL = 0, BWD_GEOM = 1, BWD_COLOR = 2 };
+template <int MODE> struct BwdMode;
+template <> struct BwdMode<BWD_ALL> { static constexpr int NV = 10, U = 3; };
+template <> struct BwdMode<BWD_GEOM> { static constexpr int NV = 6, U = 5; };
+template <> struct BwdMode<BWD_COLOR> { static constexpr int NV = 3, U = 10; };
+__device__ __forceinline__ int bwd_slot(int mode, int j) {  // accumulator column of value j
+  return mode == BWD_ALL ? j : (mode == BWD_GEOM ? (j < 5 ? j : 9) : 6 + j);
+}
+
+template <int MODE>
 __global__ void __launch_bounds__(BB_THREADS, 2) s3r_blend_bwd_kernel(
-    int W, int H, int P, int tiles_x, int tiles, const uint2* __restrict__ ranges, const float4* __restrict__ records,
-    const uint32_t* __restrict__ point_list, const float4* __restrict__ conic_opacity,
+    int W, int H, int P, int tiles_x, int tiles, const uint32_t* __restrict__ work_order, const uint2* __restrict__ ranges,
+    const float4* __restrict__ records, const uint32_t* __restrict__ point_list, const float4* __restrict__ conic_opacity,
     const float* __restrict__ background, const float* __restrict__ final_T,
     const uint32_t* __restrict__ n_contrib, const float* __restrict__ dL_dcolor, const float* __restrict__ dL_ddepth,
     float* __restrict__ acc) {
+  constexpr int NV = BwdMode<MODE>::NV, U = BwdMode<MODE>::U;
   __shared__ BwdSmem sm;
-  const int view = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x;
+  // (view, tile) in the order of the forward pass's blend queue (raster_sort.cu: heaviest tiles first, the first waves laid
+  // out so that an SM's second CTA gets a light tile)
+  const uint32_t vt = work_order[blockIdx.x];
+  const int view = vt / tiles, tile = vt % tiles, tid = threadIdx.x;
   const int lane = tid & 31, w = tid >> 5;
   const uint2 rg = ranges[(size_t)view * tiles + tile];
   const float4* src = records + (size_t)rg.x * 3;
@@ -163,10 +209,12 @@ __global__ void __launch_bounds__(BB_THREADS, 2) s3r_blend_bwd_kernel(
     if (dL_ddepth) dLd = dL_ddepth[(size_t)view * HW + pix];
   }
   const float* bg = background + view * 3;
-  const float bg_dot = bg[0] * dLp0 + bg[1] * dLp1 + bg[2] * dLp2;
-  const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
-  float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, accd = 0.f;      // accum_rec / accum_depth_rec
-  float lc0 = 0.f, lc1 = 0.f, lc2 = 0.f, ld = 0.f, last_alpha = 0.f;
+  const float nbg = -T_final * (bg[0] * dLp0 + bg[1] * dLp1 + bg[2] * dLp2);  // d(T_final * bg) / dalpha = nbg / (1 - alpha)
+  const float fW = (float)W, fH = (float)H;  // 2 * ddelx_dx, 2 * ddely_dy
+  const uint64_t dLp01 = bpack2(dLp0, dLp1), dLp2d = bpack2(dLp2, dLd);
+  uint64_t acc01 = bpack2(0.f, 0.f), acc2d = bpack2(0.f, 0.f);  // accum_rec / accum_depth_rec (colours behind the splat)
+  uint64_t lc01 = bpack2(0.f, 0.f), lc2d = bpack2(0.f, 0.f);    // colour / depth of the last kept splat
+  float last_alpha = 0.f;
   float* accv = acc + (size_t)view * P * ACC_STRIDE;
 
   for (uint32_t q = 0; q < nch; q++) {
@@ -187,22 +235,19 @@ __global__ void __launch_bounds__(BB_THREADS, 2) s3r_blend_bwd_kernel(
         count += __popc(m);
       }
       __syncwarp();
-      // walk the survivors back to front, BB_U at a time
+      // walk the survivors back to front, U at a time
 #pragma unroll 1
-      for (int k = count; k > 0; k -= BB_U) {
+      for (int k = count; k > 0; k -= U) {
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; j++) v[j] = 0.f;
-        int idx[BB_U];
         bool any_keep = false;
 #pragma unroll
-        for (int u = 0; u < BB_U; u++) {
+        for (int u = 0; u < U; u++) {
           const int kk = k - 1 - u;  // list position, descending
           const int i = kk >= 0 ? (int)list[kk] : 0;
-          idx[u] = i;
           const float4 r0 = sm.rec[s][i * 3];
           const float4 r1 = sm.rec[s][i * 3 + 1];
-          const float4 r2 = sm.rec[s][i * 3 + 2];
           const float dx = r0.x - pxf, dy = r0.y - pyf;
           // same fast log2-domain evaluation and guard bands as the forward kernel (raster_blend.cu), so that the
           // set of contributing Gaussians is the one the forward pass composited
@@ -212,62 +257,72 @@ __global__ void __launch_bounds__(BB_THREADS, 2) s3r_blend_bwd_kernel(
           bool kp = kk >= 0 && (base_idx + (uint32_t)i) < last;
           // the true conic for the gradient formulas (the record holds B' = KB*B, C' = KA*C | A' = KA*A)
           float cA = r1.x * S3R_INV_KA, cB = r0.z * S3R_INV_KB, cC = r0.w * S3R_INV_KA;
-          if (kp) {
-            if ((alpha >= ALPHA_LO && alpha < ALPHA_HI) || fabsf(l2g) < S3R_PZERO_BAND) {
-              const uint32_t gid = __ldg(point_list + (size_t)rg.x + base_idx + i);
-              const float4 co = __ldg(conic_opacity + (size_t)view * P + gid);
-              const float qf = __fadd_rn(__fmul_rn(__fmul_rn(co.x, dx), dx), __fmul_rn(__fmul_rn(co.z, dy), dy));
-              const float power = __fsub_rn(__fmul_rn(-0.5f, qf), __fmul_rn(__fmul_rn(co.y, dx), dy));
-              kp = !(power > 0.0f);
-              if (kp) {
-                alpha = bexact_alpha(power, co.w);
-                kp = alpha >= ALPHA_MIN;
-                G = __expf(power);
-                cA = co.x, cB = co.y, cC = co.z;
-              }
-            } else {
-              kp = !(l2g > 0.0f) && alpha >= ALPHA_HI;
+          if (kp && ((alpha >= ALPHA_LO && alpha < ALPHA_HI) || fabsf(l2g) < S3R_PZERO_BAND)) {
+            // rare: decided like the forward pass, from the exact conic
+            const uint32_t gid = __ldg(point_list + (size_t)rg.x + base_idx + i);
+            const float4 co = __ldg(conic_opacity + (size_t)view * P + gid);
+            const float qf = __fadd_rn(__fmul_rn(__fmul_rn(co.x, dx), dx), __fmul_rn(__fmul_rn(co.z, dy), dy));
+            const float power = __fsub_rn(__fmul_rn(-0.5f, qf), __fmul_rn(__fmul_rn(co.y, dx), dy));
+            kp = !(power > 0.0f);
+            if (kp) {
+              alpha = bexact_alpha(power, co.w);
+              kp = alpha >= ALPHA_MIN;
+              G = __expf(power);
+              cA = co.x, cB = co.y, cC = co.z;
             }
+          } else {
+            kp = kp && !(l2g > 0.0f) && alpha >= ALPHA_HI;
           }
-          if (kp) {
-            any_keep = true;
-            T = T / (1.f - alpha);
-            const float dchannel_dcolor = alpha * T;
-            float dL_dalpha;
-            acc0 = last_alpha * lc0 + (1.f - last_alpha) * acc0;
-            acc1 = last_alpha * lc1 + (1.f - last_alpha) * acc1;
-            acc2 = last_alpha * lc2 + (1.f - last_alpha) * acc2;
-            accd = last_alpha * ld + (1.f - last_alpha) * accd;
-            lc0 = r1.z; lc1 = r1.w; lc2 = r2.x; ld = r2.y;
-            dL_dalpha = (lc0 - acc0) * dLp0 + (lc1 - acc1) * dLp1 + (lc2 - acc2) * dLp2 + (ld - accd) * dLd;
-            dL_dalpha *= T;
+          // branch-free from here: a splat that is not kept runs with alpha = 0, G = 0 - T, the colour recurrence and
+          // every gradient value come out exactly as if it had been skipped
+          any_keep = any_keep || kp;
+          alpha = kp ? alpha : 0.f;
+          G = kp ? G : 0.f;
+          const float inv = bfast_rcp(1.f - alpha);
+          T *= inv;
+          const float dch = alpha * T;  // d channel / d colour
+          if (MODE != BWD_GEOM) {
+            const int o = MODE == BWD_ALL ? u * NV + 6 : u * NV;
+            float c0, c1;
+            bunpack2(bmul2(dLp01, bpack2(dch, dch)), c0, c1);
+            v[o] = c0;
+            v[o + 1] = c1;
+            v[o + 2] = dch * dLp2;
+            if (MODE == BWD_ALL) v[o + 3] = dch * dLd;
+          }
+          if (MODE != BWD_COLOR) {
+            const float2 r2 = *reinterpret_cast<const float2*>(&sm.rec[s][i * 3 + 2]);
+            // colour behind this splat: acc = last_alpha * last_colour + (1 - last_alpha) * acc
+            const float oml = 1.f - last_alpha;
+            acc01 = bfma2(bpack2(last_alpha, last_alpha), lc01, bmul2(bpack2(oml, oml), acc01));
+            acc2d = bfma2(bpack2(last_alpha, last_alpha), lc2d, bmul2(bpack2(oml, oml), acc2d));
+            lc01 = bpack2(r1.z, r1.w);
+            lc2d = bpack2(r2.x, r2.y);
             last_alpha = alpha;
-            dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot;
-            const float dL_dG = r1.y * dL_dalpha;
-            const float gdx = G * dx, gdy = G * dy;
-            const float dG_ddelx = -gdx * cA - gdy * cB;
-            const float dG_ddely = -gdy * cC - gdx * cB;
-            v[u * 10 + 0] = dL_dG * dG_ddelx * ddelx_dx;
-            v[u * 10 + 1] = dL_dG * dG_ddely * ddely_dy;
-            v[u * 10 + 2] = -0.5f * gdx * dx * dL_dG;
-            v[u * 10 + 3] = -0.5f * gdx * dy * dL_dG;
-            v[u * 10 + 4] = -0.5f * gdy * dy * dL_dG;
-            v[u * 10 + 5] = G * dL_dalpha;
-            v[u * 10 + 6] = dchannel_dcolor * dLp0;
-            v[u * 10 + 7] = dchannel_dcolor * dLp1;
-            v[u * 10 + 8] = dchannel_dcolor * dLp2;
-            v[u * 10 + 9] = dchannel_dcolor * dLd;
+            // dL/dalpha = T * sum_c (colour_c - acc_c) * dL/dpixel_c  -  T_final / (1 - alpha) * (bg . dL/dpixel)
+            float s0, s1;
+            bunpack2(bfma2(bfma2(acc2d, bpack2(-1.f, -1.f), lc2d), dLp2d,
+                           bmul2(bfma2(acc01, bpack2(-1.f, -1.f), lc01), dLp01)), s0, s1);
+            const float dL_dalpha = fmaf(s0 + s1, T, nbg * inv);
+            const float h = -0.5f * (r1.y * dL_dalpha);  // -0.5 * dL/dG
+            const float hgx = h * (G * dx), hgy = h * (G * dy);
+            const int o = u * NV;
+            v[o + 0] = fW * fmaf(hgx, cA, hgy * cB);  // dL/dG * dG/ddelx * ddelx/dx (ddelx/dx = W / 2)
+            v[o + 1] = fH * fmaf(hgy, cC, hgx * cB);
+            v[o + 2] = hgx * dx;
+            v[o + 3] = hgx * dy;
+            v[o + 4] = hgy * dy;
+            v[o + 5] = MODE == BWD_ALL ? G * dL_dalpha : dch * dLd;  // opacity (ALL) / depth (GEOM) column
           }
         }
         if (__any_sync(0xffffffffu, any_keep)) {
-          // lane L < 30 will own value L = (record L/10, component L%10): fetch that record's Gaussian id early
-          const int u_l = lane / 10, comp = lane - u_l * 10;
-          const int i_l = u_l == 0 ? idx[0] : (u_l == 1 ? idx[1] : idx[2]);
-          const bool owner = lane < 30 && (k - 1 - u_l) >= 0;
+          // lane L < U * NV will own value L = (splat L / NV, component L % NV): fetch that splat's Gaussian id early
+          const int u_l = lane / NV, comp = lane - u_l * NV;
+          const bool owner = lane < U * NV && (k - 1 - u_l) >= 0;
           uint32_t gid = 0;
-          if (owner) gid = __ldg(point_list + (size_t)rg.x + base_idx + i_l);
+          if (owner) gid = __ldg(point_list + (size_t)rg.x + base_idx + list[k - 1 - u_l]);
           const float total = warp_multi_reduce32(v, lane);
-          if (owner && total != 0.f) atomicAdd(accv + (size_t)gid * ACC_STRIDE + comp, total);
+          if (owner && total != 0.f) atomicAdd(accv + (size_t)gid * ACC_STRIDE + bwd_slot(MODE, comp), total);
         }
       }
     }
@@ -554,6 +609,11 @@ __global__ void __launch_bounds__(256) s3r_preprocess_bwd_kernel(s3r_raster_para
   }
 }
 
+int& s3r_bwd_mode_override() {  // S3R_TUNE_BWD_ALL: != 0 forces the 10-value kernel (tests compare the modes against it)
+  static int v = 0;
+  return v;
+}
+
 extern "C" size_t s3r_raster_backward_scratch_bytes(int32_t n_views, int32_t P) {
   return (size_t)n_views * P * ACC_STRIDE * sizeof(float);
 }
@@ -572,12 +632,22 @@ extern "C" int s3r_raster_backward(const s3r_raster_params* params, const void* 
   const char* s = (const char*)state;
   float* acc = (float*)grads->scratch;
   S3R_CUDA_CHECK(cudaMemsetAsync(acc, 0, need, st));
-  dim3 g1(L.tiles, params->n_views);
-  s3r_blend_bwd_kernel<<<g1, BB_THREADS, 0, st>>>(
-      params->width, params->height, params->P, L.tiles_x, L.tiles, (const uint2*)(s + L.ranges),
-      (const float4*)(s + L.records), (const uint32_t*)(s + L.point_list), (const float4*)(s + L.conic_opacity),
-      params->background,
-      (const float*)(s + L.final_T), (const uint32_t*)(s + L.n_contrib), grads->dL_dcolor, grads->dL_ddepth, acc);
+  dim3 g1(L.tiles * params->n_views);
+  // which per-splat gradients are needed (see BwdMode): colours enter the geometry only through the view direction of
+  // SH degree > 0
+  const bool geom = grads->dL_dmeans3D || grads->dL_dcov3D || grads->dL_dtau || grads->dL_dmeans2D;
+  const bool colour = grads->dL_dshs || grads->dL_dcolors || (geom && !params->colors_precomp && params->sh_degree > 0);
+  const bool opac = grads->dL_dopacities != nullptr;
+  auto kern = s3r_blend_bwd_kernel<BWD_ALL>;
+  if (s3r_bwd_mode_override() == 0) {
+    if (geom && !colour && !opac) kern = s3r_blend_bwd_kernel<BWD_GEOM>;
+    else if (colour && !geom && !opac) kern = s3r_blend_bwd_kernel<BWD_COLOR>;
+  }
+  kern<<<g1, BB_THREADS, 0, st>>>(
+      params->width, params->height, params->P, L.tiles_x, L.tiles, (const uint32_t*)(s + L.work_order),
+      (const uint2*)(s + L.ranges), (const float4*)(s + L.records), (const uint32_t*)(s + L.point_list),
+      (const float4*)(s + L.conic_opacity), params->background, (const float*)(s + L.final_T),
+      (const uint32_t*)(s + L.n_contrib), grads->dL_dcolor, grads->dL_ddepth, acc);
   S3R_CUDA_CHECK(cudaGetLastError());
   dim3 g2((params->P + 255) / 256, params->n_views);
   s3r_preprocess_bwd_kernel<<<g2, 256, 0, st>>>(*params, *grads, (const uint32_t*)(s + L.rect),

@@ -62,6 +62,7 @@ int s3r_blend_grid(int* sms, int* slots);
 // Programmatic dependent launch switch shared by all kernels (S3R_TUNE_PDL; defined in gemm_tcgen05.cu)
 int s3r_pdl_enabled();
 int& s3r_blend_only_tile();  // S3R_TUNE_BLEND_ONLY_TILE (defined in raster_blend.cu)
+int& s3r_bwd_mode_override();  // S3R_TUNE_BWD_ALL (defined in raster_backward.cu)
 
 // Launch with the programmatic-stream-serialization attribute: the grid may become resident while the previous kernel
 // of the stream drains; the kernel runs its global-memory-free prologue (shared-memory zeroing, mbarrier init), then

@@ -146,3 +146,39 @@ def test_only_requested_gradients_are_computed():
     only = run({"harmonics"})
     assert only[0] is None and only[1] is None and only[3] is None
     assert torch.allclose(only[2], full[2], rtol=1e-4, atol=1e-9) and only[2].abs().max() > 0
+
+
+def test_backward_kernel_variants_agree():
+    """The blend-backward kernel is specialised on the requested outputs (geometry only = pose-align loop, colour only =
+    stage-2 training, all): every variant must reproduce the 10-value kernel (S3R_TUNE_BWD_ALL) on what it returns."""
+    import torch
+
+    from styl3r_b200 import _lib
+    from styl3r_b200 import rasterizer as rz
+
+    scene = syn.make_scene(seed=7, v=2, V=2, hw=64)
+    outs, cams = oracle_scene(scene, render=False)
+    *_, ctx = gpu_scene(scene, cams, want_n_touched=False)
+    rng = np.random.default_rng(1)
+    gc = torch.as_tensor(rng.normal(size=(2, 3, 64, 64)).astype(np.float32)).cuda()
+    gd = torch.as_tensor((0.1 * rng.normal(size=(2, 64, 64))).astype(np.float32)).cuda()
+    only_sh = dict(means=False, cov=False, opacities=False, shs=True, colors=False, means2D=False)
+
+    def three():
+        return (rz.backward_raw(ctx, gc, gd), rz.backward_raw(ctx, gc, gd, only_pose=True),
+                rz.backward_raw(ctx, gc, gd, need_pose=False, needs=only_sh))
+
+    try:
+        _lib.lib().s3r_set_tunable(14, 1)
+        ref_full, ref_pose, ref_sh = three()
+    finally:
+        _lib.lib().s3r_set_tunable(14, 0)
+    full, pose, sh = three()
+    torch.cuda.synchronize()
+    close("tau (geometry-only kernel)", pose["tau"].cpu().numpy(), ref_pose["tau"].cpu().numpy(), rel=1e-4)
+    close("tau (geometry-only vs full)", pose["tau"].cpu().numpy(), full["tau"].cpu().numpy(), rel=1e-4)
+    close("shs (colour-only kernel)", sh["shs"].cpu().numpy(), ref_sh["shs"].cpu().numpy(), rel=1e-4)
+    close("shs (colour-only vs full)", sh["shs"].cpu().numpy(), full["shs"].cpu().numpy(), rel=1e-4)
+    for k in ("means", "cov", "opacities", "shs", "tau"):
+        close(k, full[k].cpu().numpy(), ref_full[k].cpu().numpy(), rel=1e-5)
+    assert pose["means"] is None and sh["means"] is None and sh["opacities"] is None
