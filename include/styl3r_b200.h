@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define S3R_ABI_VERSION 2
+#define S3R_ABI_VERSION 3
 
 /* error codes */
 #define S3R_OK 0
@@ -111,6 +111,10 @@ typedef struct s3r_raster_layout {
   int64_t n_contrib;     /* uint32  [n_views*H*W]                             */
   int64_t grecords;      /* 48 B    [nvP]   per-(view, Gaussian) blend record, written by preprocess */
   int64_t work_order;    /* uint32  [nvT]   (view*tiles + tile) by descending instance count: blend work queue */
+  int64_t blists;        /* uint32  [8*cap] per (view, tile, 8x4-pixel block): indices (inside the tile's sorted range) of the
+                            instances whose alpha >= 1/255 box touches the block, in sorted order; block b of a tile with
+                            range [s, e) starts at 8*s + b*(e - s)                                                        */
+  int64_t bcounts;       /* uint32  [8*nvT] length of every block list                                                  */
   int32_t tiles_x, tiles_y, tiles, chunks;
 } s3r_raster_layout;
 
@@ -277,6 +281,7 @@ int s3r_conv2d_bf16(const void* x, const void* w, const void* bias, const void* 
 #define S3R_TUNE_GEMM_DIRECT 13 /* one-tile GEMM kernel: register epilogue straight from TMEM (no staging tile): 0 = auto (grids of at most ~1.5 waves: the batch-1 shapes), 1 = whenever the epilogue feature set allows, 2 = never */
 #define S3R_TUNE_RASTER_PDL 9 /* bit k != 0: raster stage k (0 preprocess, 1 bin scan, 2 bin emit, 3 tile sort, 4 blend) is launched with programmatic dependent launch */
 #define S3R_TUNE_BWD_ALL 14 /* != 0: s3r_raster_backward always runs the 10-value blend-backward kernel instead of the geometry-only / colour-only variants it selects from the requested outputs (tests compare them) */
+#define S3R_TUNE_BLEND_KERNEL 15 /* blend (forward) kernel: 0 = warp-granular over the per-block survivor lists (default), 1 = tile-granular (TMA ring, per-warp cull) */
 #define S3R_TUNE_BLEND_ONLY_TILE 8 /* development probe: != 0 -> the blend launch renders only tile (value - 1) of every view (one CTA per view): times the critical path of one tile without contention */
 int s3r_set_tunable(int32_t key, int32_t value);
 

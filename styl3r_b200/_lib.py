@@ -14,7 +14,7 @@ _LIB_PATH = Path(__file__).resolve().parent / "lib" / (f"libstyl3r_b200_{_TAG}.s
 _lib = None
 
 S3R_OK = 0
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class RasterParams(C.Structure):
@@ -37,7 +37,7 @@ class RasterLayout(C.Structure):
     _fields_ = [(n, C.c_int64) for n in (
         "total_bytes", "status", "counters", "depths", "xy", "conic_opacity", "rgb", "rect", "chunk_hist",
         "chunk_base", "tile_count", "ranges", "keys_unsorted", "keys_tmp", "point_list", "point_keys", "records",
-        "final_T", "n_contrib", "grecords", "work_order")] + [(n, C.c_int32) for n in ("tiles_x", "tiles_y", "tiles", "chunks")]
+        "final_T", "n_contrib", "grecords", "work_order", "blists", "bcounts")] + [(n, C.c_int32) for n in ("tiles_x", "tiles_y", "tiles", "chunks")]
 
 
 class RasterGrads(C.Structure):

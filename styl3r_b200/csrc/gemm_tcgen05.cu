@@ -1654,6 +1654,11 @@ extern "C" int s3r_set_tunable(int32_t key, int32_t value) {
     s3r_raster_pdl_mask() = value & 31;
     return S3R_OK;
   }
+  if (key == S3R_TUNE_BLEND_KERNEL) {
+    if (value < 0 || value > 1) return S3R_ERR_INVALID_ARG;
+    s3r_blend_kernel_choice() = value;
+    return S3R_OK;
+  }
   if (key == S3R_TUNE_BWD_ALL) {
     s3r_bwd_mode_override() = value != 0;
     return S3R_OK;

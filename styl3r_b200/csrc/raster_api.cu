@@ -55,6 +55,8 @@ extern "C" int s3r_raster_layout_query(int32_t n_views, int32_t P, int32_t width
   out->n_contrib = take((int64_t)n_views * HW * 4);
   out->grecords = take(nvP * S3R_REC_BYTES);
   out->work_order = take(nvT * 4);
+  out->blists = take(cap * 8 * 4);
+  out->bcounts = take(nvT * 8 * 4);
   out->total_bytes = off;
   out->tiles_x = tx;
   out->tiles_y = ty;

@@ -523,6 +523,14 @@ int& s3r_blend_only_tile() {
   return v;
 }
 
+#ifndef BLEND_KERNEL_DEFAULT
+#define BLEND_KERNEL_DEFAULT 0
+#endif
+int& s3r_blend_kernel_choice() {
+  static int v = BLEND_KERNEL_DEFAULT;
+  return v;
+}
+
 int s3r_blend_grid(int* sms_out, int* slots_out) {
   static int slots[64] = {}, sms[64] = {};
   int dev = 0;
@@ -543,6 +551,10 @@ int s3r_blend_grid(int* sms_out, int* slots_out) {
 
 int s3r_launch_blend(const s3r_raster_params& p, const s3r_raster_outputs& o, const s3r_raster_layout& L,
                      char* state, cudaStream_t st) {
+  if (s3r_blend_kernel_choice() == 0) {  // warp-granular kernel over the per-block survivor lists (raster_blend_blocks.cu)
+    const int ot = s3r_blend_only_tile();
+    return s3r_launch_blend_blocks(p, o, L, state, st, ot > 0 && ot <= L.tiles ? ot - 1 : -1);
+  }
   auto kern = o.n_touched ? s3r_blend_fwd_kernel<true> : s3r_blend_fwd_kernel<false>;
   // persistent grid: as many CTAs as the device holds at once (per device, cached), never more than there are units
   int n_sms = 0, n_slots = 0;

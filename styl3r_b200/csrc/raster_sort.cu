@@ -122,7 +122,7 @@ __device__ __forceinline__ uint32_t cell_mask(float x, float y, float ex, float 
   return mx * my;  // outer product: no carries (my has one bit per nibble)
 }
 
-__device__ __forceinline__ void write_sorted(uint32_t o, unsigned long long k, unsigned long long tile_hi, size_t vbase,
+__device__ __forceinline__ uint32_t write_sorted(uint32_t o, unsigned long long k, unsigned long long tile_hi, size_t vbase,
                                              float tx0, float ty0, const float4* __restrict__ grecords,
                                              uint32_t* __restrict__ point_list,
                                              unsigned long long* __restrict__ point_keys, float4* __restrict__ records) {
@@ -132,12 +132,55 @@ __device__ __forceinline__ void write_sorted(uint32_t o, unsigned long long k, u
   const float4* g = grecords + (vbase + id) * 3;
   const float4 a = __ldg(g), b = __ldg(g + 1);
   float4 c = __ldg(g + 2);
-  c.z = __uint_as_float(cell_mask(a.x, a.y, c.z, c.w, tx0, ty0));  // (ex, ey) -> per-instance cell mask
+  const uint32_t cm = cell_mask(a.x, a.y, c.z, c.w, tx0, ty0);  // (ex, ey) -> per-instance cell mask
+  c.z = __uint_as_float(cm);
   c.w = 0.f;
   float4* r = records + (size_t)o * 3;
   r[0] = a;
   r[1] = b;
   r[2] = c;
+  return cm;
+}
+
+// Per-block survivor lists of one tile (second pass of the epilogue): for each of the tile's eight 8x4-pixel blocks, the
+// positions (inside the tile's sorted range) of the instances whose cell mask touches the block, in sorted order.  The
+// blend kernel's warps then stream exactly their own survivors: no cull, no shared ring, no coupling between the warps
+// of a tile.  Warp b compacts block b: one walk over the tile's masks (shared memory in the bucket path), one ballot per
+// 32 positions, the running offset in a register - no counting pass and no cross-warp scan.
+template <bool kSmemMasks>
+__device__ void build_block_lists(uint32_t n, uint32_t rgx, const float4* __restrict__ records,
+                                  uint32_t* __restrict__ blists, uint32_t* __restrict__ bcnt, uint16_t* s_mask) {
+  static_assert(SORT_WARPS == 8, "one warp per 8x4 block");
+  __syncthreads();  // every write_sorted store of this CTA (records / shared-memory masks) is visible to the CTA
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const uint32_t lt = (1u << lane) - 1u;
+  const int sh = 4 * (w >> 1) + 2 * (w & 1);  // the block's two cells are adjacent mask bits
+  const float* mask_f = reinterpret_cast<const float*>(records + (size_t)rgx * 3) + 10;  // r2.z of record 0
+  uint32_t* out = blists + (size_t)rgx * 8 + (size_t)w * n;
+  uint32_t off = 0;
+  // kSmemMasks: the bucket path left all n <= S3R_SORT_SMEM_CAP masks in shared memory.  Otherwise (LSD / global sort
+  // paths, whose key buffers are free by now) the masks are staged from the records S3R_SORT_SMEM_CAP at a time, all
+  // loads of a thread in flight together - a walk with a dependent global load per step would cost an L2 round trip
+  // per 32 positions and warp.
+  for (uint32_t c0 = 0; c0 < n; c0 += S3R_SORT_SMEM_CAP) {
+    const uint32_t cn = min((uint32_t)S3R_SORT_SMEM_CAP, n - c0);
+    if (!kSmemMasks) {
+      if (c0) __syncthreads();  // the previous window has been consumed
+      for (uint32_t i = tid; i < cn; i += SORT_THREADS)
+        s_mask[i] = (uint16_t)__float_as_uint(__ldcg(mask_f + (size_t)(c0 + i) * S3R_REC_FLOATS));
+      __syncthreads();
+    }
+#pragma unroll 4
+    for (uint32_t p = 0; p < cn; p += 32) {
+      const uint32_t q = p + lane;
+      const uint32_t cm = q < cn ? (uint32_t)s_mask[q] : 0u;
+      const bool hit = ((cm >> sh) & 3u) != 0u;
+      const uint32_t m = __ballot_sync(0xffffffffu, hit);
+      if (hit) out[off + __popc(m & lt)] = c0 + q;
+      off += __popc(m);
+    }
+  }
+  if (lane == 0) bcnt[w] = off;
 }
 
 // The blend stage's work queue: (view, tile) indices by descending instance count (256-bucket counting sort; the order
@@ -192,7 +235,8 @@ __global__ void __launch_bounds__(SORT_THREADS) s3r_tile_sort_kernel(
     int P, int tiles, int tiles_x, const uint2* __restrict__ ranges, unsigned long long* __restrict__ keys_a,
     unsigned long long* __restrict__ keys_b, const float4* __restrict__ grecords, uint32_t* __restrict__ point_list,
     unsigned long long* __restrict__ point_keys, float4* __restrict__ records, const uint32_t* __restrict__ tile_count,
-    const long long* __restrict__ status, uint32_t* __restrict__ work_order, uint32_t blend_sms, uint32_t blend_slots) {
+    const long long* __restrict__ status, uint32_t* __restrict__ work_order, uint32_t blend_sms, uint32_t blend_slots,
+    uint32_t* __restrict__ blists, uint32_t* __restrict__ bcounts) {
   extern __shared__ unsigned long long s_keys[];  // [2][S3R_SORT_SMEM_CAP]; bucket path: [0] = grouped keys, [1] = bucket table
   __shared__ uint32_t s_hist[SORT_WARPS][256];
   __shared__ uint32_t s_scan[SORT_WARPS];
@@ -214,7 +258,15 @@ __global__ void __launch_bounds__(SORT_THREADS) s3r_tile_sort_kernel(
   }
   const uint2 rg = ranges[(size_t)view * tiles + tile];
   const uint32_t n = rg.y - rg.x;
-  if (n == 0) return;
+  uint32_t* bcnt = bcounts + ((size_t)view * tiles + tile) * 8;
+  // bucket path: cell masks in sorted order, in the free tail of the second key buffer (behind the bucket table)
+  uint16_t* s_mask = reinterpret_cast<uint16_t*>(s_start + SORT_NB + 8);
+  const uint32_t s_mask_addr = (uint32_t)__cvta_generic_to_shared(s_mask);
+  static_assert((SORT_NB + 8) * 4 + S3R_SORT_SMEM_CAP * 2 <= S3R_SORT_SMEM_CAP * 8, "mask array must fit behind the bucket table");
+  if (n == 0) {
+    if (tid < 8) bcnt[tid] = 0u;
+    return;
+  }
   unsigned long long* ga = keys_a + rg.x;
   unsigned long long* gb = keys_b + rg.x;
   const size_t vbase = (size_t)view * P;
@@ -309,8 +361,13 @@ __global__ void __launch_bounds__(SORT_THREADS) s3r_tile_sort_kernel(
         const uint32_t b0 = s_start[d], b1 = s_start[d + 1];
         uint32_t rank = 0;
         for (uint32_t q = b0; q < b1; q++) rank += (s_keys[q] < key) ? 1u : 0u;
-        write_sorted(rg.x + b0 + rank, key, tile_hi, vbase, tx0, ty0, grecords, point_list, point_keys, records);
+        const uint32_t cm =
+            write_sorted(rg.x + b0 + rank, key, tile_hi, vbase, tx0, ty0, grecords, point_list, point_keys, records);
+        // plain asm store: a C++ store into the same dynamic shared array would order itself against the next key's
+        // s_keys / s_start reads (may-alias) and serialise the two gathers the unrolled loop keeps in flight
+        asm volatile("st.shared.u16 [%0], %1;" ::"r"(s_mask_addr + 2u * (b0 + rank)), "h"((unsigned short)cm));
       }
+      build_block_lists<true>(n, rg.x, records, blists, bcnt, s_mask);
       return;
     }
     // ================= LSD path (rare): stable radix passes in shared memory, keys re-staged from registers
@@ -331,6 +388,7 @@ __global__ void __launch_bounds__(SORT_THREADS) s3r_tile_sort_kernel(
     }
     for (uint32_t i = tid; i < n; i += SORT_THREADS)
       write_sorted(rg.x + i, cur[i], tile_hi, vbase, tx0, ty0, grecords, point_list, point_keys, records);
+    build_block_lists<false>(n, rg.x, records, blists, bcnt, reinterpret_cast<uint16_t*>(s_keys));
     return;
   }
   // ================= global path: tiles above the shared-memory capacity
@@ -345,6 +403,7 @@ __global__ void __launch_bounds__(SORT_THREADS) s3r_tile_sort_kernel(
   }
   for (uint32_t i = tid; i < n; i += SORT_THREADS)
     write_sorted(rg.x + i, __ldcg(cur + i), tile_hi, vbase, tx0, ty0, grecords, point_list, point_keys, records);
+  build_block_lists<false>(n, rg.x, records, blists, bcnt, reinterpret_cast<uint16_t*>(s_keys));
 }
 
 int s3r_launch_sort(const s3r_raster_params& p, const s3r_raster_layout& L, char* state, cudaStream_t st) {
@@ -363,6 +422,7 @@ int s3r_launch_sort(const s3r_raster_params& p, const s3r_raster_layout& L, char
                                 (uint32_t*)(state + L.point_list), (unsigned long long*)(state + L.point_keys),
                                 (float4*)(state + L.records), (const uint32_t*)(state + L.tile_count),
                                 (const long long*)(state + L.status), (uint32_t*)(state + L.work_order),
-                                (uint32_t)blend_sms, (uint32_t)blend_slots));
+                                (uint32_t)blend_sms, (uint32_t)blend_slots, (uint32_t*)(state + L.blists),
+                                (uint32_t*)(state + L.bcounts)));
   return S3R_OK;
 }

@@ -62,6 +62,9 @@ int s3r_blend_grid(int* sms, int* slots);
 // Programmatic dependent launch switch shared by all kernels (S3R_TUNE_PDL; defined in gemm_tcgen05.cu)
 int s3r_pdl_enabled();
 int& s3r_blend_only_tile();  // S3R_TUNE_BLEND_ONLY_TILE (defined in raster_blend.cu)
+int& s3r_blend_kernel_choice();  // S3R_TUNE_BLEND_KERNEL: 0 = warp-granular kernel over block lists, 1 = tile-granular kernel
+int s3r_launch_blend_blocks(const s3r_raster_params& p, const s3r_raster_outputs& o, const s3r_raster_layout& L,
+                            char* state, cudaStream_t st, int only_tile);
 int& s3r_bwd_mode_override();  // S3R_TUNE_BWD_ALL (defined in raster_backward.cu)
 
 // Launch with the programmatic-stream-serialization attribute: the grid may become resident while the previous kernel
