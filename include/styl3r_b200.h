@@ -115,6 +115,8 @@ typedef struct s3r_raster_layout {
                             instances whose alpha >= 1/255 box touches the block, in sorted order; block b of a tile with
                             range [s, e) starts at 8*s + b*(e - s)                                                        */
   int64_t bcounts;       /* uint32  [8*nvT] length of every block list                                                  */
+  int64_t n_contrib_blk; /* uint32  [n_views*H*W] per pixel: entries of its block list up to and including the last
+                            contributor (written by the warp-granular blend kernel, read by its backward twin)           */
   int32_t tiles_x, tiles_y, tiles, chunks;
 } s3r_raster_layout;
 

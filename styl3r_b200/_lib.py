@@ -37,7 +37,7 @@ class RasterLayout(C.Structure):
     _fields_ = [(n, C.c_int64) for n in (
         "total_bytes", "status", "counters", "depths", "xy", "conic_opacity", "rgb", "rect", "chunk_hist",
         "chunk_base", "tile_count", "ranges", "keys_unsorted", "keys_tmp", "point_list", "point_keys", "records",
-        "final_T", "n_contrib", "grecords", "work_order", "blists", "bcounts")] + [(n, C.c_int32) for n in ("tiles_x", "tiles_y", "tiles", "chunks")]
+        "final_T", "n_contrib", "grecords", "work_order", "blists", "bcounts", "n_contrib_blk")] + [(n, C.c_int32) for n in ("tiles_x", "tiles_y", "tiles", "chunks")]
 
 
 class RasterGrads(C.Structure):

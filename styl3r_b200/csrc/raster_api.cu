@@ -57,6 +57,7 @@ extern "C" int s3r_raster_layout_query(int32_t n_views, int32_t P, int32_t width
   out->work_order = take(nvT * 4);
   out->blists = take(cap * 8 * 4);
   out->bcounts = take(nvT * 8 * 4);
+  out->n_contrib_blk = take((int64_t)n_views * HW * 4);
   out->total_bytes = off;
   out->tiles_x = tx;
   out->tiles_y = ty;

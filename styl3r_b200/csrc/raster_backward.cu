@@ -332,6 +332,209 @@ __global__ void __launch_bounds__(BB_THREADS, 2) s3r_blend_bwd_kernel(
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// blend backward, warp-granular: the backward twin of raster_blend_blocks.cu.  One warp per (view, tile, 8x4 block)
+// walks the block's survivor list (tile sort epilogue) back to front, from the list position the forward pass
+// recorded per pixel (`n_contrib_blk` = entries up to and including the last contributor).  Records are gathered
+// with cp.async, 32 per group, double-buffered in the warp's private shared memory: no cull, no shared ring, warps
+// of a tile independent.  Per-splat arithmetic, guard bands and reduction as in s3r_blend_bwd_kernel above.
+// ------------------------------------------------------------------------------------------------------------
+#define BWB_WARPS 8
+#define BWB_THREADS (32 * BWB_WARPS)
+#define BWB_GROUP 32
+
+__device__ __forceinline__ void bcp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void bcp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bcp_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(BWB_THREADS, 2) s3r_blend_bwd_blocks_kernel(
+    int W, int H, int P, int tiles_x, int tiles, uint32_t n_units, const uint32_t* __restrict__ work_order,
+    const uint2* __restrict__ ranges, const float4* __restrict__ records, const uint32_t* __restrict__ blists,
+    const uint32_t* __restrict__ point_list, const float4* __restrict__ conic_opacity,
+    const float* __restrict__ background, const float* __restrict__ final_T, const uint32_t* __restrict__ n_contrib_blk,
+    const float* __restrict__ dL_dcolor, const float* __restrict__ dL_ddepth, float* __restrict__ acc) {
+  constexpr int NV = BwdMode<MODE>::NV, U = BwdMode<MODE>::U;
+  __shared__ __align__(16) float4 s_rec[BWB_WARPS][2][BWB_GROUP * 3];
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const uint32_t unit = blockIdx.x * BWB_WARPS + w;
+  if (unit >= n_units) return;
+  const uint32_t vt = work_order[unit >> 3];
+  const int blk = unit & 7;
+  const int view = vt / tiles, tile = vt % tiles;
+  const uint2 rg = ranges[vt];
+  const uint32_t n = rg.y - rg.x;
+  const uint32_t* list = blists + (size_t)rg.x * 8 + (size_t)blk * n;
+  const float4* src = records + (size_t)rg.x * 3;
+  const size_t HW = (size_t)H * W;
+  const int tx = tile % tiles_x, ty = tile / tiles_x;
+  const int X0 = tx * S3R_TILE + (blk & 1) * 8, Y0 = ty * S3R_TILE + (blk >> 1) * 4;
+  const int px = X0 + (lane & 7), py = Y0 + (lane >> 3);
+  const bool inside = px < W && py < H;
+  const size_t pix = (size_t)py * W + px;
+  const uint32_t klast = inside ? n_contrib_blk[(size_t)view * HW + pix] : 0u;  // list entries [0, klast) matter
+  uint32_t kmax = klast;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
+  if (kmax == 0) return;
+  const uint32_t ngroups = (kmax + BWB_GROUP - 1) / BWB_GROUP;
+
+  const float pxf = (float)px, pyf = (float)py;
+  const float T_final = inside ? final_T[(size_t)view * HW + pix] : 0.f;
+  float T = T_final;
+  float dLp0 = 0.f, dLp1 = 0.f, dLp2 = 0.f, dLd = 0.f;
+  if (inside) {
+    const float* g = dL_dcolor + (size_t)view * 3 * HW;
+    dLp0 = g[pix];
+    dLp1 = g[HW + pix];
+    dLp2 = g[2 * HW + pix];
+    if (dL_ddepth) dLd = dL_ddepth[(size_t)view * HW + pix];
+  }
+  const float* bg = background + view * 3;
+  const float nbg = -T_final * (bg[0] * dLp0 + bg[1] * dLp1 + bg[2] * dLp2);
+  const float fW = (float)W, fH = (float)H;
+  const uint64_t dLp01 = bpack2(dLp0, dLp1), dLp2d = bpack2(dLp2, dLd);
+  uint64_t acc01 = bpack2(0.f, 0.f), acc2d = bpack2(0.f, 0.f);
+  uint64_t lc01 = bpack2(0.f, 0.f), lc2d = bpack2(0.f, 0.f);
+  float last_alpha = 0.f;
+  float* accv = acc + (size_t)view * P * ACC_STRIDE;
+  const uint32_t buf0 = bsmem_u32(&s_rec[w][0][0]);
+  constexpr uint32_t kBufBytes = BWB_GROUP * S3R_REC_BYTES;
+
+  // groups are walked from the last one down; `it` counts iterations (buffer parity), g = ngroups - 1 - it
+  auto load_idx = [&](uint32_t it) -> uint32_t {
+    if (it >= ngroups) return 0u;
+    const uint32_t j = (ngroups - 1 - it) * BWB_GROUP + lane;
+    return j < kmax ? list[j] : 0u;
+  };
+  auto gather = [&](uint32_t it, uint32_t idx) {
+    const uint32_t j = (ngroups - 1 - it) * BWB_GROUP + lane;
+    const uint32_t dst = buf0 + (it & 1u) * kBufBytes + lane * S3R_REC_BYTES;
+    if (j < kmax) {
+      const float4* r = src + (size_t)idx * 3;
+      bcp_async16(dst, r);
+      bcp_async16(dst + 16, r + 1);
+      bcp_async16(dst + 32, r + 2);
+    } else {  // past the range: a finite dummy (never kept)
+      float4* d = &s_rec[w][it & 1u][lane * 3];
+      d[0] = make_float4(3e9f, 3e9f, 0.0f, -1.0f);
+      d[1] = make_float4(-1.0f, 0.0f, 0.0f, 0.0f);
+      d[2] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    }
+    bcp_commit();
+  };
+  uint32_t idx_cur = load_idx(0);
+  gather(0, idx_cur);
+  uint32_t idx_gath = load_idx(1);  // indices of the group whose gather is issued next
+
+  for (uint32_t it = 0; it < ngroups; it++) {
+    const uint32_t g = ngroups - 1 - it;
+    uint32_t idx_pref = 0;
+    if (it + 1 < ngroups) {
+      gather(it + 1, idx_gath);
+      idx_pref = load_idx(it + 2);
+      bcp_wait<1>();
+    } else {
+      bcp_wait<0>();
+    }
+    __syncwarp();
+    const float4* rec = &s_rec[w][it & 1u][0];
+    const int gcnt = (int)min((uint32_t)BWB_GROUP, kmax - g * BWB_GROUP);
+#pragma unroll 1
+    for (int k = gcnt; k > 0; k -= U) {
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; j++) v[j] = 0.f;
+      bool any_keep = false;
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const int kk = k - 1 - u;  // slot in the group, descending
+        const int i = kk >= 0 ? kk : 0;
+        const float4 r0 = rec[i * 3];
+        const float4 r1 = rec[i * 3 + 1];
+        const float dx = r0.x - pxf, dy = r0.y - pyf;
+        const float l2g = fmaf(dx, fmaf(r1.x, dx, r0.z * dy), (r0.w * dy) * dy);
+        float G = bfast_exp2(l2g);
+        float alpha = fminf(0.99f, r1.y * G);
+        bool kp = kk >= 0 && (g * BWB_GROUP + (uint32_t)kk) < klast;
+        float cA = r1.x * S3R_INV_KA, cB = r0.z * S3R_INV_KB, cC = r0.w * S3R_INV_KA;
+        if (kp && ((alpha >= ALPHA_LO && alpha < ALPHA_HI) || fabsf(l2g) < S3R_PZERO_BAND)) {
+          const uint32_t gid = __ldg(point_list + (size_t)rg.x + __ldg(list + g * BWB_GROUP + kk));
+          const float4 co = __ldg(conic_opacity + (size_t)view * P + gid);
+          const float qf = __fadd_rn(__fmul_rn(__fmul_rn(co.x, dx), dx), __fmul_rn(__fmul_rn(co.z, dy), dy));
+          const float power = __fsub_rn(__fmul_rn(-0.5f, qf), __fmul_rn(__fmul_rn(co.y, dx), dy));
+          kp = !(power > 0.0f);
+          if (kp) {
+            alpha = bexact_alpha(power, co.w);
+            kp = alpha >= ALPHA_MIN;
+            G = __expf(power);
+            cA = co.x, cB = co.y, cC = co.z;
+          }
+        } else {
+          kp = kp && !(l2g > 0.0f) && alpha >= ALPHA_HI;
+        }
+        any_keep = any_keep || kp;
+        alpha = kp ? alpha : 0.f;
+        G = kp ? G : 0.f;
+        const float inv = bfast_rcp(1.f - alpha);
+        T *= inv;
+        const float dch = alpha * T;
+        if (MODE != BWD_GEOM) {
+          const int o = MODE == BWD_ALL ? u * NV + 6 : u * NV;
+          float c0, c1;
+          bunpack2(bmul2(dLp01, bpack2(dch, dch)), c0, c1);
+          v[o] = c0;
+          v[o + 1] = c1;
+          v[o + 2] = dch * dLp2;
+          if (MODE == BWD_ALL) v[o + 3] = dch * dLd;
+        }
+        if (MODE != BWD_COLOR) {
+          const float2 r2 = *reinterpret_cast<const float2*>(&rec[i * 3 + 2]);
+          const float oml = 1.f - last_alpha;
+          acc01 = bfma2(bpack2(last_alpha, last_alpha), lc01, bmul2(bpack2(oml, oml), acc01));
+          acc2d = bfma2(bpack2(last_alpha, last_alpha), lc2d, bmul2(bpack2(oml, oml), acc2d));
+          lc01 = bpack2(r1.z, r1.w);
+          lc2d = bpack2(r2.x, r2.y);
+          last_alpha = alpha;
+          float s0, s1;
+          bunpack2(bfma2(bfma2(acc2d, bpack2(-1.f, -1.f), lc2d), dLp2d,
+                         bmul2(bfma2(acc01, bpack2(-1.f, -1.f), lc01), dLp01)), s0, s1);
+          const float dL_dalpha = fmaf(s0 + s1, T, nbg * inv);
+          const float h = -0.5f * (r1.y * dL_dalpha);
+          const float hgx = h * (G * dx), hgy = h * (G * dy);
+          const int o = u * NV;
+          v[o + 0] = fW * fmaf(hgx, cA, hgy * cB);
+          v[o + 1] = fH * fmaf(hgy, cC, hgx * cB);
+          v[o + 2] = hgx * dx;
+          v[o + 3] = hgx * dy;
+          v[o + 4] = hgy * dy;
+          v[o + 5] = MODE == BWD_ALL ? G * dL_dalpha : dch * dLd;
+        }
+      }
+      if (__any_sync(0xffffffffu, any_keep)) {
+        // lane L < U * NV owns value L = (splat L / NV, component L % NV); its Gaussian id comes from the group's list
+        // indices, which lane `slot` still holds (idx_cur)
+        const int u_l = lane / NV, comp = lane - u_l * NV;
+        const int slot = k - 1 - u_l;
+        const bool owner = lane < U * NV && slot >= 0;
+        const uint32_t pos = __shfl_sync(0xffffffffu, idx_cur, slot >= 0 ? slot : 0);
+        uint32_t gid = 0;
+        if (owner) gid = __ldg(point_list + (size_t)rg.x + pos);
+        const float total = warp_multi_reduce32(v, lane);
+        if (owner && total != 0.f) atomicAdd(accv + (size_t)gid * ACC_STRIDE + bwd_slot(MODE, comp), total);
+      }
+    }
+    __syncwarp();  // the buffer is refilled two iterations from now
+    idx_cur = idx_gath;
+    idx_gath = idx_pref;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // preprocess backward: one thread per (view, Gaussian).  fp32 restatement of the oracle's double-precision
 // chain (conic -> cov2D -> (Sigma, t, R);  NDC mean -> t;  depth -> t.z;  SH;  t, R -> tau).
 // ------------------------------------------------------------------------------------------------------------
@@ -638,16 +841,30 @@ extern "C" int s3r_raster_backward(const s3r_raster_params* params, const void* 
   const bool geom = grads->dL_dmeans3D || grads->dL_dcov3D || grads->dL_dtau || grads->dL_dmeans2D;
   const bool colour = grads->dL_dshs || grads->dL_dcolors || (geom && !params->colors_precomp && params->sh_degree > 0);
   const bool opac = grads->dL_dopacities != nullptr;
-  auto kern = s3r_blend_bwd_kernel<BWD_ALL>;
+  int mode = BWD_ALL;
   if (s3r_bwd_mode_override() == 0) {
-    if (geom && !colour && !opac) kern = s3r_blend_bwd_kernel<BWD_GEOM>;
-    else if (colour && !geom && !opac) kern = s3r_blend_bwd_kernel<BWD_COLOR>;
+    if (geom && !colour && !opac) mode = BWD_GEOM;
+    else if (colour && !geom && !opac) mode = BWD_COLOR;
   }
-  kern<<<g1, BB_THREADS, 0, st>>>(
-      params->width, params->height, params->P, L.tiles_x, L.tiles, (const uint32_t*)(s + L.work_order),
-      (const uint2*)(s + L.ranges), (const float4*)(s + L.records), (const uint32_t*)(s + L.point_list),
-      (const float4*)(s + L.conic_opacity), params->background, (const float*)(s + L.final_T),
-      (const uint32_t*)(s + L.n_contrib), grads->dL_dcolor, grads->dL_ddepth, acc);
+  if (s3r_blend_kernel_choice() == 0) {
+    // warp-granular twin of the default forward kernel (the state must come from that kernel: n_contrib_blk)
+    const uint32_t n_units = (uint32_t)L.tiles * (uint32_t)params->n_views * 8u;
+    auto kern = mode == BWD_GEOM ? s3r_blend_bwd_blocks_kernel<BWD_GEOM>
+                                 : (mode == BWD_COLOR ? s3r_blend_bwd_blocks_kernel<BWD_COLOR> : s3r_blend_bwd_blocks_kernel<BWD_ALL>);
+    kern<<<(n_units + BWB_WARPS - 1) / BWB_WARPS, BWB_THREADS, 0, st>>>(
+        params->width, params->height, params->P, L.tiles_x, L.tiles, n_units, (const uint32_t*)(s + L.work_order),
+        (const uint2*)(s + L.ranges), (const float4*)(s + L.records), (const uint32_t*)(s + L.blists),
+        (const uint32_t*)(s + L.point_list), (const float4*)(s + L.conic_opacity), params->background,
+        (const float*)(s + L.final_T), (const uint32_t*)(s + L.n_contrib_blk), grads->dL_dcolor, grads->dL_ddepth, acc);
+  } else {
+    auto kern = mode == BWD_GEOM ? s3r_blend_bwd_kernel<BWD_GEOM>
+                                 : (mode == BWD_COLOR ? s3r_blend_bwd_kernel<BWD_COLOR> : s3r_blend_bwd_kernel<BWD_ALL>);
+    kern<<<g1, BB_THREADS, 0, st>>>(
+        params->width, params->height, params->P, L.tiles_x, L.tiles, (const uint32_t*)(s + L.work_order),
+        (const uint2*)(s + L.ranges), (const float4*)(s + L.records), (const uint32_t*)(s + L.point_list),
+        (const float4*)(s + L.conic_opacity), params->background, (const float*)(s + L.final_T),
+        (const uint32_t*)(s + L.n_contrib), grads->dL_dcolor, grads->dL_ddepth, acc);
+  }
   S3R_CUDA_CHECK(cudaGetLastError());
   dim3 g2((params->P + 255) / 256, params->n_views);
   s3r_preprocess_bwd_kernel<<<g2, 256, 0, st>>>(*params, *grads, (const uint32_t*)(s + L.rect),

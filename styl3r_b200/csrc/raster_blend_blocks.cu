@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(BBK_THREADS, BBK_MINB) s3r_blend_blocks_fwd_ke
     const uint32_t* __restrict__ blists, const uint32_t* __restrict__ bcounts, const uint32_t* __restrict__ point_list,
     const float4* __restrict__ conic_opacity, const float* __restrict__ background, float* __restrict__ out_color,
     float* __restrict__ out_depth, float* __restrict__ out_opacity, float* __restrict__ final_T,
-    uint32_t* __restrict__ n_contrib, int32_t* __restrict__ n_touched) {
+    uint32_t* __restrict__ n_contrib, uint32_t* __restrict__ n_contrib_blk, int32_t* __restrict__ n_touched) {
   __shared__ BlendWarpSmem sm[BBK_WARPS];
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const uint32_t buf0 = k_smem_u32(&sm[w].rec[0][0]);
@@ -313,6 +313,7 @@ __global__ void __launch_bounds__(BBK_THREADS, BBK_MINB) s3r_blend_blocks_fwd_ke
       out_opacity[(size_t)view * HW + pix] = 1.0f - T;
       final_T[(size_t)view * HW + pix] = T;
       n_contrib[(size_t)view * HW + pix] = lastk >= 0 ? list[lastk] + 1u : 0u;
+      n_contrib_blk[(size_t)view * HW + pix] = (uint32_t)(lastk + 1);  // where the backward walk of this pixel starts
     }
   }
   // the last CTA to leave rewinds the queue for the next launch on this state buffer
@@ -350,6 +351,7 @@ int s3r_launch_blend_blocks(const s3r_raster_params& p, const s3r_raster_outputs
                                 (const float4*)(state + L.records), (const uint32_t*)(state + L.blists),
                                 (const uint32_t*)(state + L.bcounts), (const uint32_t*)(state + L.point_list),
                                 (const float4*)(state + L.conic_opacity), p.background, o.color, o.depth, o.opacity,
-                                (float*)(state + L.final_T), (uint32_t*)(state + L.n_contrib), o.n_touched));
+                                (float*)(state + L.final_T), (uint32_t*)(state + L.n_contrib),
+                                (uint32_t*)(state + L.n_contrib_blk), o.n_touched));
   return S3R_OK;
 }

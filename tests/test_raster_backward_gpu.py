@@ -182,3 +182,32 @@ def test_backward_kernel_variants_agree():
     for k in ("means", "cov", "opacities", "shs", "tau"):
         close(k, full[k].cpu().numpy(), ref_full[k].cpu().numpy(), rel=1e-5)
     assert pose["means"] is None and sh["means"] is None and sh["opacities"] is None
+
+
+def test_tile_and_warp_granular_backward_agree():
+    """S3R_TUNE_BLEND_KERNEL selects the (forward, backward) kernel pair: tile-granular (TMA ring + cull) or warp-granular
+    over the per-block survivor lists (default).  Same gradients up to the summation order of the atomics."""
+    import torch
+
+    from styl3r_b200 import _lib
+    from styl3r_b200 import rasterizer as rz
+
+    scene = syn.make_scene(seed=11, v=2, V=2, hw=64)
+    outs, cams = oracle_scene(scene, render=False)
+    rng = np.random.default_rng(2)
+    gc = torch.as_tensor(rng.normal(size=(2, 3, 64, 64)).astype(np.float32)).cuda()
+    gd = torch.as_tensor((0.1 * rng.normal(size=(2, 64, 64))).astype(np.float32)).cuda()
+
+    def run():
+        *_, ctx = gpu_scene(scene, cams, want_n_touched=False)
+        return rz.backward_raw(ctx, gc, gd)
+
+    warp = run()
+    try:
+        _lib.lib().s3r_set_tunable(15, 1)
+        tile = run()
+    finally:
+        _lib.lib().s3r_set_tunable(15, 0)
+    torch.cuda.synchronize()
+    for k in ("means", "cov", "opacities", "shs", "tau", "means2D"):
+        close(k, warp[k].cpu().numpy(), tile[k].cpu().numpy(), rel=1e-4)
