@@ -350,7 +350,7 @@ def run_ours(args):
     e1.record()
     torch.cuda.synchronize()
     blend_pipe_ms = e0.elapsed_time(e1) / K
-    roof_pipe = {"kernel": "s3r_blend_fwd_kernel", "what": f"blend-only CUDA graphs of the resident scenes on {n_streams} concurrent streams",
+    roof_pipe = {"kernel": "s3r_blend_blocks_fwd_kernel", "what": f"blend-only CUDA graphs of the resident scenes on {n_streams} concurrent streams",
                  "kernel_ms_equivalent": blend_pipe_ms, "achieved": blend_bytes / (blend_pipe_ms * 1e-3) / 1e9, "unit": "GB/s",
                  "frac": blend_bytes / (blend_pipe_ms * 1e-3) / 1e9 / peak}
 
@@ -627,7 +627,7 @@ def run_ours(args):
                     "h2d_gbs": e2e_val * h2d_bytes / 1e9},
             "e2e_multi_view": e2e_multi,
             "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "kernel": "s3r_blend_fwd_kernel", "achieved": achieved, "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": "s3r_blend_blocks_fwd_kernel", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": blend_bytes, "kernel_ms": stage_ms["blend"],
                          "timing": "CUDA events around a graph of 10 back-to-back launches of the kernel, per launch",

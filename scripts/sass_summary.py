@@ -14,9 +14,10 @@ sys.path.insert(0, str(ROOT))
 from styl3r_b200 import build as B  # noqa: E402
 
 MNEMONICS = ["UTCHMMA.2CTA", "UTMALDG.2D.2CTA", "UTMALDG.4D.2CTA", "UTCBAR.2CTA", "UTCHMMA", "UTCQMMA", "UTCBAR", "UTMALDG", "UTMAPF", "UBLKCP", "LDTM", "STTM", "SYNCS", "UTCATOM", "ACQBULK",
-             "MUFU.EX2", "FFMA", "HMMA", "LDS", "STS", "ATOMS", "RED", "VOTE", "SHFL"]
+             "MUFU.EX2", "FFMA2", "FMUL2", "FADD2", "LDGSTS", "FFMA", "HMMA", "LDS", "STS", "ATOMS", "RED", "VOTE", "SHFL"]
 PTX = ["tcgen05.mma.cta_group::2", "cta_group::2.shared::cluster.global", "tcgen05.st", "tcgen05.mma", "tcgen05.ld", "tcgen05.alloc", "tcgen05.commit", "cp.async.bulk.tensor", "cp.async.bulk.shared",
-       "mbarrier.try_wait", "mbarrier.arrive", "griddepcontrol", "ex2.approx"]
+       "mbarrier.try_wait", "mbarrier.arrive", "griddepcontrol", "ex2.approx", "fma.rn.f32x2", "mul.rn.f32x2", "add.rn.f32x2",
+       "cp.async.cg.shared.global"]
 
 
 def main():
