@@ -104,8 +104,10 @@ __global__ void __launch_bounds__(BBK_THREADS, BBK_MINB) s3r_blend_blocks_fwd_ke
 
   const uint32_t n_warps = gridDim.x * BBK_WARPS;
   for (bool first = true;; first = false) {
-    // first unit: the warp's own index (no atomic round trip in front of a single view's only unit), then the queue
-    uint32_t unit = blockIdx.x * BBK_WARPS + w;
+    // first unit: by the warp's own index (no atomic round trip in front of a single view's only unit), strided so that
+    // the eight warps of a CTA start on blocks of eight different tiles across the weight-ordered queue (the busiest
+    // blocks then share their SM with light ones), afterwards the queue
+    uint32_t unit = w * gridDim.x + blockIdx.x;
     if (!first) {
       if (lane == 0) unit = n_warps + atomicAdd(&counters[1], 1u);
       unit = __shfl_sync(0xffffffffu, unit, 0);
