@@ -341,6 +341,8 @@ __global__ void __launch_bounds__(BB_THREADS, 2) s3r_blend_bwd_kernel(
 #define BWB_WARPS 8
 #define BWB_THREADS (32 * BWB_WARPS)
 #define BWB_GROUP 32
+#define BWB_RED_STRIDE 36
+#define BWB_SMEM_BYTES (sizeof(float4) * BWB_WARPS * 2 * BWB_GROUP * 3 + sizeof(float) * BWB_WARPS * 30 * BWB_RED_STRIDE)
 
 __device__ __forceinline__ void bcp_async16(uint32_t dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
@@ -359,9 +361,14 @@ __global__ void __launch_bounds__(BWB_THREADS, 2) s3r_blend_bwd_blocks_kernel(
     const float* __restrict__ background, const float* __restrict__ final_T, const uint32_t* __restrict__ n_contrib_blk,
     const float* __restrict__ dL_dcolor, const float* __restrict__ dL_ddepth, float* __restrict__ acc) {
   constexpr int NV = BwdMode<MODE>::NV, U = BwdMode<MODE>::U;
-  __shared__ __align__(16) float4 s_rec[BWB_WARPS][2][BWB_GROUP * 3];
+  extern __shared__ __align__(16) unsigned char s_dyn[];
+  float4 (*s_rec)[2][BWB_GROUP * 3] = reinterpret_cast<float4 (*)[2][BWB_GROUP * 3]>(s_dyn);  // [BWB_WARPS][2][96]
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  const uint32_t unit = blockIdx.x * BWB_WARPS + w;
+  // per-warp transpose buffer of the gradient reduction: value j of lane l at [j * BWB_RED_STRIDE + l]
+  float* red = reinterpret_cast<float*>(s_dyn + sizeof(float4) * BWB_WARPS * 2 * BWB_GROUP * 3) + w * (30 * BWB_RED_STRIDE);
+  // strided like the forward kernel's first units: a CTA's warps work on blocks of eight different tiles across the
+  // weight-ordered queue (n_units is a multiple of 8, the grid is n_units / 8)
+  const uint32_t unit = w * gridDim.x + blockIdx.x;
   if (unit >= n_units) return;
   const uint32_t vt = work_order[unit >> 3];
   const int blk = unit & 7;
@@ -524,7 +531,22 @@ __global__ void __launch_bounds__(BWB_THREADS, 2) s3r_blend_bwd_blocks_kernel(
         const uint32_t pos = __shfl_sync(0xffffffffu, idx_cur, slot >= 0 ? slot : 0);
         uint32_t gid = 0;
         if (owner) gid = __ldg(point_list + (size_t)rg.x + pos);
-        const float total = warp_multi_reduce32(v, lane);
+        // sum of every value over the 32 pixels through a shared-memory transpose: 30 conflict-free stores, then lane L
+        // adds up row L with 8 LDS.128 (row stride 36 floats: a quarter warp covers all banks once) - 70 instructions
+        // instead of the 124 of the select / shuffle butterfly
+#pragma unroll
+        for (int j = 0; j < U * NV; j++) red[j * BWB_RED_STRIDE + lane] = v[j];
+        __syncwarp();
+        float total = 0.f;
+        if (lane < U * NV) {
+          const float4* row = reinterpret_cast<const float4*>(red + lane * BWB_RED_STRIDE);
+#pragma unroll
+          for (int q = 0; q < 8; q++) {
+            const float4 x = row[q];
+            total += (x.x + x.y) + (x.z + x.w);
+          }
+        }
+        __syncwarp();  // the next batch overwrites the buffer
         if (owner && total != 0.f) atomicAdd(accv + (size_t)gid * ACC_STRIDE + bwd_slot(MODE, comp), total);
       }
     }
@@ -851,7 +873,10 @@ extern "C" int s3r_raster_backward(const s3r_raster_params* params, const void* 
     const uint32_t n_units = (uint32_t)L.tiles * (uint32_t)params->n_views * 8u;
     auto kern = mode == BWD_GEOM ? s3r_blend_bwd_blocks_kernel<BWD_GEOM>
                                  : (mode == BWD_COLOR ? s3r_blend_bwd_blocks_kernel<BWD_COLOR> : s3r_blend_bwd_blocks_kernel<BWD_ALL>);
-    kern<<<(n_units + BWB_WARPS - 1) / BWB_WARPS, BWB_THREADS, 0, st>>>(
+    static size_t configured[3][64] = {};
+    rc = s3r_ensure_dynamic_smem(kern, BWB_SMEM_BYTES, configured[mode]);
+    if (rc != S3R_OK) return rc;
+    kern<<<(n_units + BWB_WARPS - 1) / BWB_WARPS, BWB_THREADS, BWB_SMEM_BYTES, st>>>(
         params->width, params->height, params->P, L.tiles_x, L.tiles, n_units, (const uint32_t*)(s + L.work_order),
         (const uint2*)(s + L.ranges), (const float4*)(s + L.records), (const uint32_t*)(s + L.blists),
         (const uint32_t*)(s + L.point_list), (const float4*)(s + L.conic_opacity), params->background,
