@@ -167,6 +167,30 @@ def run_reference(args):
 # ----------------------------------------------------------------------------- our arm
 
 
+def bind_to_gpu_numa_node(index):
+    """Multi-rank runs: pin this rank's threads (and with them the first-touch placement of its pinned host buffers) to
+    the NUMA node its GPU hangs off, so that the e2e copies do not cross the socket interconnect.  Returns what was
+    done (for the JSON line) or None when the topology cannot be read."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(index)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read().strip())
+        if node < 0:
+            return {"pci": bdf, "node": node, "bound": False}
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if not allowed:
+            return {"pci": bdf, "node": node, "bound": False}
+        os.sched_setaffinity(0, allowed)
+        return {"pci": bdf, "node": node, "bound": True, "cpus": len(allowed)}
+    except Exception as e:  # not fatal: the run just is not pinned
+        return {"bound": False, "error": repr(e)[:120]}
+
+
 def run_ours(args):
     import torch
 
@@ -181,7 +205,9 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist = None
+    numa = None
     if world > 1:
+        numa = bind_to_gpu_numa_node(local)  # before any pinned allocation (single-rank runs keep every core for the CPU legs)
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
 
@@ -618,6 +644,7 @@ def run_ours(args):
                                  "camera matrices precomputed per scene",
                        "parallelism": f"scene-sharded x{world}, no collective"},
             "clocks": clk.summary(),
+            **({"numa": numa} if numa is not None else {}),
             "e2e": {"value": e2e_val, "unit": "views/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                     "steps": Ke, "api": "styl3r_b200.decoder.RenderSession.run(): pinned host Gaussians (covariances as the packed cov3D_precomp triangle the reference hands to its rasterizer) + cameras -> H2D -> camera kernel -> "
                            f"raster chain -> D2H pinned image (one CUDA graph per request buffer, {n_e2e_streams} streams)",
