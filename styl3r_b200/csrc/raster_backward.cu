@@ -355,7 +355,8 @@ __device__ __forceinline__ void bcp_wait() {
 
 template <int MODE>
 __global__ void __launch_bounds__(BWB_THREADS, 2) s3r_blend_bwd_blocks_kernel(
-    int W, int H, int P, int tiles_x, int tiles, uint32_t n_units, const uint32_t* __restrict__ work_order,
+    int W, int H, int P, int tiles_x, int tiles, uint32_t n_units, const unsigned* __restrict__ counters,
+    const uint32_t* __restrict__ work_order,
     const uint2* __restrict__ ranges, const float4* __restrict__ records, const uint32_t* __restrict__ blists,
     const uint32_t* __restrict__ point_list, const float4* __restrict__ conic_opacity,
     const float* __restrict__ background, const float* __restrict__ final_T, const uint32_t* __restrict__ n_contrib_blk,
@@ -368,6 +369,9 @@ __global__ void __launch_bounds__(BWB_THREADS, 2) s3r_blend_bwd_blocks_kernel(
   float* red = reinterpret_cast<float*>(s_dyn + sizeof(float4) * BWB_WARPS * 2 * BWB_GROUP * 3) + w * (30 * BWB_RED_STRIDE);
   // strided like the forward kernel's first units: a CTA's warps work on blocks of eight different tiles across the
   // weight-ordered queue (n_units is a multiple of 8, the grid is n_units / 8)
+  // the walk starts from n_contrib_blk, which only the warp-granular forward kernel writes: fail loudly on a state that
+  // the other forward kernel rendered (S3R_TUNE_BLEND_KERNEL toggled between a forward and its backward)
+  if (counters[7] != 1u) __trap();
   const uint32_t unit = w * gridDim.x + blockIdx.x;
   if (unit >= n_units) return;
   const uint32_t vt = work_order[unit >> 3];
@@ -877,8 +881,9 @@ extern "C" int s3r_raster_backward(const s3r_raster_params* params, const void* 
     rc = s3r_ensure_dynamic_smem(kern, BWB_SMEM_BYTES, configured[mode]);
     if (rc != S3R_OK) return rc;
     kern<<<(n_units + BWB_WARPS - 1) / BWB_WARPS, BWB_THREADS, BWB_SMEM_BYTES, st>>>(
-        params->width, params->height, params->P, L.tiles_x, L.tiles, n_units, (const uint32_t*)(s + L.work_order),
-        (const uint2*)(s + L.ranges), (const float4*)(s + L.records), (const uint32_t*)(s + L.blists),
+        params->width, params->height, params->P, L.tiles_x, L.tiles, n_units, (const unsigned*)(s + L.counters),
+        (const uint32_t*)(s + L.work_order), (const uint2*)(s + L.ranges), (const float4*)(s + L.records),
+        (const uint32_t*)(s + L.blists),
         (const uint32_t*)(s + L.point_list), (const float4*)(s + L.conic_opacity), params->background,
         (const float*)(s + L.final_T), (const uint32_t*)(s + L.n_contrib_blk), grads->dL_dcolor, grads->dL_ddepth, acc);
   } else {

@@ -507,6 +507,7 @@ __global__ void __launch_bounds__(BLEND_THREADS, BLEND_MINB) s3r_blend_fwd_kerne
     if (atomicAdd(&counters[2], 1u) == gridDim.x - 1) {
       counters[1] = 0u;
       counters[2] = 0u;
+      counters[7] = 2u;  // this state was rendered by the tile-granular kernel
     }
   }
 }

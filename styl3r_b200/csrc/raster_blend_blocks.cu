@@ -325,6 +325,7 @@ __global__ void __launch_bounds__(BBK_THREADS, BBK_MINB) s3r_blend_blocks_fwd_ke
     if (atomicAdd(&counters[2], 1u) == gridDim.x - 1) {
       counters[1] = 0u;
       counters[2] = 0u;
+      counters[7] = 1u;  // this state was rendered by the warp-granular kernel (its backward twin checks)
     }
   }
 }

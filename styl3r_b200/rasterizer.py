@@ -71,6 +71,8 @@ class RasterContext:
             "keys_unsorted": ("i64", cap), "point_list": ("i32", cap), "point_keys": ("i64", cap),
             "records": ("f32", cap * 12), "final_T": ("f32", nv * HW), "n_contrib": ("i32", nv * HW),
             "chunk_hist": ("u16", nv * L.chunks * L.tiles), "chunk_base": ("i32", nv * L.chunks * L.tiles),
+            "work_order": ("i32", nv * L.tiles), "blists": ("i32", cap * 8), "bcounts": ("i32", nv * L.tiles * 8),
+            "n_contrib_blk": ("i32", nv * HW),
         }[name]
         dt = _DT[spec[0]]
         off = getattr(L, name)
