@@ -214,3 +214,61 @@ def test_tile_granular_blend_kernel(seed, P, W, H, V):
     for a, b in zip(ref[:3], alt[:3]):  # colour, depth, opacity: the same operations in the same order per pixel
         assert torch.equal(a, b)
     assert torch.equal(ref[4], alt[4])  # n_touched
+
+
+def test_block_lists_match_cell_masks():
+    """Structure behind the warp-granular blend kernels: for every (view, tile) and each of its eight 8x4-pixel blocks,
+    `blists` holds exactly the sorted positions whose 16-bit cell mask (written into the record by the tile sort) touches
+    the block, in ascending order, and `bcounts` their number; the cell masks cover every (pixel, instance) pair the
+    oracle composites (conservative cull)."""
+    import torch
+
+    scene = syn.make_small_scene(seed=5, P=4000, W=96, H=80, V=2)
+    outs, cams = oracle_scene(scene)
+    *_, ctx = gpu_scene(scene, cams)
+    torch.cuda.synchronize()
+    V, T = len(cams), ctx.layout.tiles
+    tiles_x = ctx.layout.tiles_x
+    ranges = ctx.view("ranges").cpu().numpy().reshape(V * T, 2).view(np.uint32).astype(np.int64)
+    masks = ctx.view("records").cpu().numpy().reshape(-1, 12)[:, 10].copy().view(np.uint32)
+    blists = ctx.view("blists").cpu().numpy().view(np.uint32)
+    bcounts = ctx.view("bcounts").cpu().numpy().reshape(V * T, 8)
+    xy = ctx.view("xy").cpu().numpy().reshape(V, -1, 2)
+    plist = ctx.view("point_list").cpu().numpy().view(np.uint32)
+    checked = 0
+    for vt in range(V * T):
+        s, e = ranges[vt]
+        n = e - s
+        m = masks[s:e]
+        assert (m >> 16 == 0).all()
+        for b in range(8):
+            sh = 4 * (b >> 1) + 2 * (b & 1)
+            want = np.nonzero((m >> sh) & 3)[0]
+            assert bcounts[vt, b] == len(want)
+            np.testing.assert_array_equal(blists[8 * s + b * n: 8 * s + b * n + len(want)], want)
+            checked += len(want)
+    assert checked > 0
+    # conservative: every (pixel, instance) pair of a tile whose alpha reaches 1/255 (oracle arithmetic on the exact conic)
+    # lies in a cell whose bit is set
+    co_all = ctx.view("conic_opacity").cpu().numpy().reshape(V, -1, 4).astype(np.float64)
+    py, px = np.meshgrid(np.arange(16), np.arange(16), indexing="ij")
+    cell_bit = ((py // 4) * 4 + px // 4).reshape(-1)
+    pairs = 0
+    for v in range(V):
+        for t in range(T):
+            s, e = ranges[v * T + t]
+            if e == s:
+                continue
+            ids = plist[s:e]
+            gx = (t % tiles_x) * 16 + px.reshape(-1)[None, :]
+            gy = (t // tiles_x) * 16 + py.reshape(-1)[None, :]
+            dx = xy[v, ids, 0].astype(np.float64)[:, None] - gx
+            dy = xy[v, ids, 1].astype(np.float64)[:, None] - gy
+            c = co_all[v, ids]
+            power = -0.5 * (c[:, 0:1] * dx * dx + c[:, 2:3] * dy * dy) - c[:, 1:2] * dx * dy
+            alpha = np.minimum(0.99, c[:, 3:4] * np.exp(np.minimum(power, 0.0)))
+            reach = (power <= 0.0) & (alpha >= (1.0 / 255.0) * (1.0 + 1e-5))
+            covered = ((masks[s:e][:, None] >> cell_bit[None, :]) & 1).astype(bool)
+            assert not (reach & ~covered).any()
+            pairs += int(reach.sum())
+    assert pairs > 0
