@@ -1,13 +1,15 @@
-// Rasterizer stage 5: per-tile front-to-back alpha blend (forward).
+// Rasterizer stage 5: per-tile front-to-back alpha blend (forward), TILE-GRANULAR kernel.  Since the end of round 2 the
+// default is the warp-granular kernel of raster_blend_blocks.cu; this one is selected with S3R_TUNE_BLEND_KERNEL = 1
+// (same results bit for bit) and also hosts the launcher / grid helpers of the blend stage.
 //
-// One CTA per (view, 16x16 tile): 8 consumer warps + 1 producer warp.  Consumer warp w owns the 8x4 pixel
-// block (w&1, w>>1) of the tile, one pixel per lane.  The tile's sorted-gathered 48-byte records are streamed
-// through a 4-stage shared-memory ring by TMA bulk copies issued by the producer warp (cp.async.bulk +
-// mbarrier complete_tx; SASS: UBLKCP / SYNCS), 128 records per stage; full/empty mbarriers decouple the
-// consumer warps from each other (no CTA-wide barrier in the main loop).  Per stage a warp tests the
-// records' alpha>=1/255 bounding boxes against its own pixel block, compacts the survivors with ballots and
-// composites only those, BLEND_U at a time (warp-uniform compaction — skipping a record that cannot reach
-// 1/255 is result-neutral).
+// Persistent CTAs, one (view, 16x16 tile) unit at a time: 8 consumer warps + 1 producer warp.  Consumer warp w owns
+// the 8x4 pixel block (w&1, w>>1) of the tile; each half-warp owns a 4x4 cell with its own survivor list.  The tile's
+// sorted-gathered 48-byte records are streamed through a 4-stage shared-memory ring by TMA bulk copies issued by the
+// producer warp (cp.async.bulk + mbarrier complete_tx; SASS: UBLKCP / SYNCS), 128 records per stage; full/empty
+// mbarriers decouple the consumer warps from each other (no CTA-wide barrier in the main loop).  Per stage a warp
+// tests the records' cell masks (bit per 4x4 cell of the tile, written by the tile sort) against its own cells,
+// compacts the survivors with ballots into lists of 16-bit shared-memory addresses and composites only those,
+// BLEND_U at a time with packed f32x2 arithmetic (skipping a record that cannot reach 1/255 is result-neutral).
 //
 // Semantics follow upstream renderCUDA + the "-w-pose" fork (blended depth, opacity, n_touched) as restated by
 // oracle/raster_oracle.c:s3r_oracle_render.  The Gaussian exponent is evaluated
