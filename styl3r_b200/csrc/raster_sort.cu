@@ -16,7 +16,9 @@
 //
 // The epilogue writes point_list (sorted gaussian ids), the upstream-format 64-bit keys, and gathers the 48-byte blend
 // records that the preprocess stage wrote per Gaussian into sorted order (three 16-byte loads + stores per instance),
-// ready for the blend kernel's TMA bulk copies.
+// replacing their cull half-extents by the instance's 16-bit cell mask for this tile (cell_mask).  A last pass
+// (build_block_lists) compacts, per 8x4-pixel block of the tile, the sorted positions whose mask touches the block: the
+// work lists of the warp-granular blend kernels (raster_blend_blocks.cu, raster_backward.cu).
 #include "s3r_common.cuh"
 
 #define SORT_THREADS 256
